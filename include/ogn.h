@@ -1,0 +1,223 @@
+/*
+ * libogn — B200-native (sm_100a) implementation of ORIGIN's detection hot path.
+ *
+ * C ABI.  Plain pointers and sizes only; no torch / numpy types.  Every entry
+ * point replaces one numerical function of the reference's L2 library
+ * (musevlt/origin, muse_origin/lib_origin.py) or one inline block of its step
+ * layer (muse_origin/steps.py); the line ranges are quoted next to each
+ * declaration.  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *  - Cubes are C-ordered [nz][ny][nx] (lambda, y, x), as numpy arrays in the
+ *    reference.  Images are [ny][nx].
+ *  - Every data pointer may be a HOST pointer (pageable or pinned) or a DEVICE
+ *    pointer on the context's device; the library asks the CUDA runtime which
+ *    (cudaPointerGetAttributes) and stages host buffers itself.  NULL output
+ *    pointers mean "do not return this product".
+ *  - Buffers are caller-owned.  The context owns all scratch memory.
+ *  - Return value: 0 (OGN_OK) or a negative ogn_status; ogn_last_error() gives
+ *    the message.  There is no CPU fallback: without a usable CUDA device
+ *    ogn_create fails.
+ *  - One context per (process, device, stream).  Calls on one context must be
+ *    serialised by the caller; all work is enqueued on the context's stream and
+ *    every entry point that returns data to host memory synchronises that
+ *    stream before returning.  Calls whose outputs are all device pointers
+ *    return without synchronising.
+ */
+#ifndef OGN_H
+#define OGN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OGN_VERSION 100
+
+#if defined(__GNUC__)
+#define OGN_API __attribute__((visibility("default")))
+#else
+#define OGN_API
+#endif
+
+typedef struct ogn_ctx ogn_ctx;
+
+typedef enum {
+    OGN_OK = 0,
+    OGN_ERR_CUDA = -1,        /* a CUDA runtime/driver call failed            */
+    OGN_ERR_ARG = -2,         /* invalid argument                             */
+    OGN_ERR_NOMEM = -3,       /* device or host allocation failed             */
+    OGN_ERR_UNSUPPORTED = -4, /* valid request the kernels do not cover       */
+    OGN_ERR_OVERFLOW = -5     /* an output list was too small (count returned) */
+} ogn_status;
+
+typedef enum { OGN_F32 = 0, OGN_F64 = 1 } ogn_dtype;
+
+/* ---- context ---------------------------------------------------------- */
+
+/* Create a context on CUDA device `device`.  `stream` is a cudaStream_t (or
+ * NULL for the legacy default stream); the caller keeps ownership of it. */
+OGN_API int ogn_create(int device, void *stream, ogn_ctx **out);
+OGN_API void ogn_destroy(ogn_ctx *ctx);
+/* Message of the last failing call on `ctx` (or of the last failing
+ * ogn_create when ctx == NULL).  Valid until the next call. */
+OGN_API const char *ogn_last_error(const ogn_ctx *ctx);
+OGN_API int ogn_version(void);
+/* Block until everything enqueued on the context's stream has finished. */
+OGN_API int ogn_synchronize(ogn_ctx *ctx);
+/* Number of kernels this context has launched so far (bench bookkeeping). */
+OGN_API int64_t ogn_launch_count(const ogn_ctx *ctx);
+/* Release the context's scratch memory (it is re-grown on demand). */
+OGN_API int ogn_trim(ogn_ctx *ctx);
+/* Pinned host memory for fast staging (optional; any host pointer works). */
+OGN_API int ogn_host_alloc(size_t bytes, void **out);
+OGN_API int ogn_host_free(void *ptr);
+
+/* ---- step05: TGLR matched filter --------------------------------------- */
+
+/* Correlation_GLR_test (lib_origin.py:1070-1217, helpers :1027-1066) fused
+ * with the masking / maxmap / minmap glue of ComputeTGLR.run
+ * (steps.py:781-793).
+ *
+ *  cube        [nz][ny][nx], dtype `cube_dtype` (computed in f32)
+ *  nfields     1 for a single FSF (reference: weights is None), else the
+ *              number of mosaic fields
+ *  fsf         nfields pointers to [nz][psize][psize] float64 FSF cubes
+ *              (orig.PSF, origin.py:590-646)
+ *  weights     NULL (single field) or nfields pointers to [ny][nx] float64
+ *              weight maps (orig.wfields)
+ *  taps        the profiles AFTER the preparation of lib_origin.py:1155-1165
+ *              (cut at pcut, L2-normalised, mean-subtracted), float64,
+ *              concatenated; profile k is taps[tap_offsets[k]:tap_offsets[k+1]]
+ *  mask        NULL, or [nz][ny][nx] bytes (non-zero = masked): correl and
+ *              profile are zeroed under the mask (steps.py:781,788),
+ *              correl_min is not
+ *  correl, correl_min   [nz][ny][nx] float32 out
+ *  profile     [nz][ny][nx] uint8 out (first-wins argmax, lib_origin.py:1210)
+ *  maxmap      [ny][nx] float32 out = max_z correl (after masking, steps.py:792)
+ *  minmap      [ny][nx] float32 out = min_z correl_min (steps.py:793)
+ */
+OGN_API int ogn_tglr(ogn_ctx *ctx,
+             const void *cube, int cube_dtype, int nz, int ny, int nx,
+             int nfields, const double *const *fsf, int psize,
+             const double *const *weights,
+             const double *taps, const int *tap_offsets, int nprof,
+             const uint8_t *mask,
+             float *correl, float *correl_min, uint8_t *profile,
+             float *maxmap, float *minmap);
+
+/* The two intermediate cubes of the spatial stage only (_convolve_fsf,
+ * lib_origin.py:1027-1043, summed over fields :1143-1147); float32
+ * [nz][ny][nx] each.  Used by the parity tests. */
+OGN_API int ogn_fsf_stage(ogn_ctx *ctx,
+                  const void *cube, int cube_dtype, int nz, int ny, int nx,
+                  int nfields, const double *const *fsf, int psize,
+                  const double *const *weights,
+                  float *cube_fsf, float *norm_fsf);
+
+/* ---- 3-D local extrema -------------------------------------------------- */
+
+/* compute_local_max (lib_origin.py:1220-1256): local maxima of `a` and of
+ * `-b` over a (sz,sy,sx) window (odd sizes, scipy 'reflect' edges), excluding
+ * masked voxels.  `a` and `b` are float32 [nz][ny][nx] (they may alias: step01
+ * calls it on (cube_std, cube_std), steps.py:453).
+ *
+ * Dense products (either may be NULL): dense_max = a * keep(a),
+ * dense_min = (-b) * keep(-b), float32 [nz][ny][nx].
+ *
+ * Compact products: the kept voxels as lists sorted by (z, y, x) — i.e. by
+ * C-order linear index, the order of np.where (steps.py:958).  max_index /
+ * min_index receive the linear voxel index (int64), max_value / min_value the
+ * value (for the minima list: -b, as in the reference).  `capacity` is the
+ * size of each list; counts[0], counts[1] always receive the true counts and
+ * OGN_ERR_OVERFLOW is returned when a list did not fit.  Lists may be NULL
+ * (counts only). */
+OGN_API int ogn_local_extrema(ogn_ctx *ctx,
+                      const float *a, const float *b, const uint8_t *mask,
+                      int nz, int ny, int nx, int sz, int sy, int sx,
+                      float *dense_max, float *dense_min,
+                      int64_t *max_index, float *max_value,
+                      int64_t *min_index, float *min_value,
+                      int64_t capacity, int64_t *counts);
+
+/* ---- step06: purity threshold counts ------------------------------------ */
+
+/* Statistics Compute_threshold_purity derives its default threshold list from
+ * (lib_origin.py:1424-1439), computed from the compact extremum lists:
+ *   stats[0] = max of the maxima list, stats[1] = max of the background minima
+ *   list (entries whose spaxel has segmask != 0 are dropped, :1428-1429),
+ *   spaxel_max [ny][nx] float32 = per-spaxel max over lambda of the dense
+ *   local-max cube (0 where a spaxel has no positive maximum), the argument of
+ *   the median at :1438.
+ * `segmask` is NULL or [ny][nx] bytes, non-zero = spaxel belongs to a source
+ * (segmap != 0). */
+OGN_API int ogn_purity_stats(ogn_ctx *ctx,
+                     const int64_t *max_index, const float *max_value, int64_t nmax,
+                     const int64_t *min_index, const float *min_value, int64_t nmin,
+                     const uint8_t *segmask, int ny, int nx,
+                     double *stats, float *spaxel_max);
+
+/* The counting loop of Compute_threshold_purity (lib_origin.py:1443-1449):
+ * n1[t] = #{maxima > thresholds[t]}, n0[t] = #{background minima >
+ * thresholds[t]}, int64 each.  Multi-GPU callers sum n0/n1 across ranks. */
+OGN_API int ogn_purity_counts(ogn_ctx *ctx,
+                      const int64_t *max_index, const float *max_value, int64_t nmax,
+                      const int64_t *min_index, const float *min_value, int64_t nmin,
+                      const uint8_t *segmask, int ny, int nx,
+                      const double *thresholds, int nthresh,
+                      int64_t *n1, int64_t *n0);
+
+/* ---- step07: thresholding ------------------------------------------------ */
+
+/* The np.where block of Detection.run (steps.py:956-974): entries of a
+ * compact extremum list with value > threshold, in list order (= C order),
+ * optionally with the argmax profile read from `profile`
+ * ([nz][ny][nx] uint8, or NULL).  out_count receives the true count;
+ * OGN_ERR_OVERFLOW if capacity was too small. */
+OGN_API int ogn_threshold_extract(ogn_ctx *ctx,
+                          const int64_t *index, const float *value, int64_t n,
+                          double threshold, const uint8_t *profile,
+                          int64_t *out_index, float *out_value, uint8_t *out_profile,
+                          int64_t capacity, int64_t *out_count);
+
+/* ---- step01: DCT continuum ------------------------------------------------ */
+
+/* dct_residual (lib_origin.py:150-240, DCTMAT :127-146).  raw and var are
+ * [nz][ny][nx] of `in_dtype` with the NaN convention of origin.py:262-274
+ * (raw 0 / var +inf where invalid); mask is [nz][ny][nx] bytes.  The
+ * continuum is computed in float64 and returned as `out_dtype`. */
+OGN_API int ogn_dct_residual(ogn_ctx *ctx,
+                     const void *raw, const void *var, int in_dtype,
+                     const uint8_t *mask, int nz, int ny, int nx,
+                     int order, int approx,
+                     void *cont, int out_dtype);
+
+/* Preprocessing.run, array part (steps.py:431-465, :472, :480), in two
+ * phases so that the per-wavelength mean (np.nanmean over all spaxels,
+ * steps.py:442) can be reduced across ranks in between.
+ *
+ * begin : continuum fit, data = raw - cont kept on the device, and the
+ *         per-wavelength partial sums lambda_sum[nz] / lambda_cnt[nz] (float64,
+ *         host or device) of the unmasked data of THIS cube (tile).
+ * finish: given the global per-wavelength mean, standardise and reduce:
+ *         cube_std [nz][ny][nx] f32, cont_dct [nz][ny][nx] f32 (= cont/sqrt(var)),
+ *         ima_std, ima_dct, cont_sumsq (= sum_z cont_dct^2), o2map
+ *         (= mean_z cube_std^2) : [ny][nx] float64.  Any output may be NULL.
+ */
+OGN_API int ogn_preprocess_begin(ogn_ctx *ctx,
+                         const void *raw, const void *var, int in_dtype,
+                         const uint8_t *mask, int nz, int ny, int nx,
+                         int order, int approx,
+                         double *lambda_sum, double *lambda_cnt);
+OGN_API int ogn_preprocess_finish(ogn_ctx *ctx, const double *lambda_mean,
+                          float *cube_std, float *cont_dct,
+                          double *ima_std, double *ima_dct,
+                          double *cont_sumsq, double *o2map);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OGN_H */

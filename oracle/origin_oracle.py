@@ -419,3 +419,36 @@ def detection_rows(cube_local_max, cube_profile, threshold):
     value = cube_local_max[z, y, x]
     prof = cube_profile[z, y, x] if cube_profile is not None else np.zeros(len(z), np.uint8)
     return dict(x0=x, y0=y, z0=z, value=value, profile=prof)
+
+
+def spot_tglr(cube, fsf, prof_cut, points):
+    """Direct-space float64 ``T_k`` at isolated voxels of a single-field cube
+    (SURVEY.md appendix A.2 evaluated pointwise): for each ``(z, y, x)`` in
+    ``points`` returns the K normalised correlations.  Size-independent check
+    for cubes too large for the full oracle."""
+    cube = np.asarray(cube)
+    nz, ny, nx = cube.shape
+    fsf = np.asarray(fsf, dtype=np.float64)
+    p = fsf.shape[-1]
+    c = p // 2
+    out = np.zeros((len(points), len(prof_cut)))
+    half = max((len(d) - 1) // 2 for d in prof_cut) + 1
+    for n, (z, y, x) in enumerate(points):
+        z0, z1 = max(0, z - half), min(nz, z + half + 1)
+        ya, yb = max(0, y - c), min(ny, y + c + 1)
+        xa, xb = max(0, x - c), min(nx, x + c + 1)
+        ker = fsf[z0:z1] - fsf[z0:z1].mean(axis=(1, 2), keepdims=True)
+        ker = ker[:, ya - y + c:yb - y + c, xa - x + c:xb - x + c]
+        patch = np.asarray(cube[z0:z1, ya:yb, xa:xb], dtype=np.float64)
+        num_z = (patch * ker).sum(axis=(1, 2))           # cube_fsf[z0:z1, y, x]
+        den_z = (ker * ker).sum(axis=(1, 2))             # norm_fsf[z0:z1, y, x]
+        for k, d in enumerate(prof_cut):
+            ck = (len(d) - 1) // 2
+            num = den = 0.0
+            for j, dj in enumerate(d):
+                zz = z + ck - j
+                if 0 <= zz < nz:
+                    num += dj * num_z[zz - z0]
+                    den += dj * dj * den_z[zz - z0]
+            out[n, k] = num / np.sqrt(den) if den > 0 else 0.0
+    return out

@@ -1,0 +1,234 @@
+// libogn context, scratch arena and staging helpers.
+#include <stdarg.h>
+#include <string.h>
+
+#include "ogn_common.cuh"
+
+static std::string g_create_error;
+
+int ogn_fail(ogn_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+extern "C" int ogn_version(void) { return OGN_VERSION; }
+
+extern "C" int ogn_create(int device, void *stream, ogn_ctx **out) {
+    ogn_ctx *ctx = nullptr;
+    if (!out) return ogn_fail(nullptr, OGN_ERR_ARG, "ogn_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return ogn_fail(nullptr, OGN_ERR_CUDA,
+                        "ogn_create: no CUDA device (%s); libogn has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev)
+        return ogn_fail(nullptr, OGN_ERR_ARG, "ogn_create: device %d out of range [0,%d)", device, ndev);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess)
+        return ogn_fail(nullptr, OGN_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return ogn_fail(nullptr, OGN_ERR_UNSUPPORTED,
+                        "ogn_create: device %d is sm_%d%d; libogn is built for sm_100a (B200) only",
+                        device, prop.major, prop.minor);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess)
+        return ogn_fail(nullptr, OGN_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    ctx = new ogn_ctx();
+    ctx->device = device;
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return OGN_OK;
+}
+
+extern "C" int ogn_trim(ogn_ctx *ctx) {
+    if (!ctx) return OGN_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->bufs)
+        if (kv.second.p) cudaFree(kv.second.p);
+    ctx->bufs.clear();
+    for (auto &kv : ctx->pins)
+        if (kv.second.p) cudaFreeHost(kv.second.p);
+    ctx->pins.clear();
+    ctx->prep = ogn_prep_state();
+    return OGN_OK;
+}
+
+extern "C" void ogn_destroy(ogn_ctx *ctx) {
+    if (!ctx) return;
+    ogn_trim(ctx);
+    delete ctx;
+}
+
+extern "C" const char *ogn_last_error(const ogn_ctx *ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int ogn_synchronize(ogn_ctx *ctx) {
+    if (!ctx) return OGN_ERR_ARG;
+    OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->host_output_pending = false;
+    return OGN_OK;
+}
+
+extern "C" int64_t ogn_launch_count(const ogn_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int ogn_host_alloc(size_t bytes, void **out) {
+    if (!out) return OGN_ERR_ARG;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return ogn_fail(nullptr, OGN_ERR_NOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return OGN_OK;
+}
+
+extern "C" int ogn_host_free(void *ptr) {
+    return cudaFreeHost(ptr) == cudaSuccess ? OGN_OK : OGN_ERR_CUDA;
+}
+
+int ogn_scratch(ogn_ctx *ctx, const char *name, size_t bytes, void **out) {
+    ogn_buf &b = ctx->bufs[name];
+    if (bytes == 0) bytes = 16;
+    if (b.cap < bytes) {
+        if (b.p) {
+            // pending work on the stream may still use the old buffer
+            OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+            OGN_CUDA(cudaFree(b.p));
+            b.p = nullptr;
+            b.cap = 0;
+        }
+        size_t cap = (bytes + 255) / 256 * 256;
+        cudaError_t e = cudaMalloc(&b.p, cap);
+        if (e != cudaSuccess) {
+            b.p = nullptr;
+            return ogn_fail(ctx, OGN_ERR_NOMEM, "cudaMalloc(%zu bytes) for '%s' failed: %s", cap, name,
+                            cudaGetErrorString(e));
+        }
+        b.cap = cap;
+    }
+    *out = b.p;
+    return OGN_OK;
+}
+
+int ogn_pinned(ogn_ctx *ctx, const char *name, size_t bytes, void **out) {
+    ogn_buf &b = ctx->pins[name];
+    if (bytes == 0) bytes = 16;
+    if (b.cap < bytes) {
+        if (b.p) {
+            OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+            OGN_CUDA(cudaFreeHost(b.p));
+            b.p = nullptr;
+            b.cap = 0;
+        }
+        cudaError_t e = cudaHostAlloc(&b.p, bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            b.p = nullptr;
+            return ogn_fail(ctx, OGN_ERR_NOMEM, "cudaHostAlloc(%zu bytes) for '%s' failed: %s", bytes, name,
+                            cudaGetErrorString(e));
+        }
+        b.cap = bytes;
+    }
+    *out = b.p;
+    return OGN_OK;
+}
+
+bool ogn_is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+int ogn_input(ogn_ctx *ctx, const char *name, const void *p, size_t bytes, const void **dev) {
+    if (!p) return ogn_fail(ctx, OGN_ERR_ARG, "input '%s' is NULL", name);
+    if (ogn_is_device_ptr(p)) {
+        *dev = p;
+        return OGN_OK;
+    }
+    void *d = nullptr;
+    OGN_TRY(ogn_scratch(ctx, name, bytes, &d));
+    OGN_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = d;
+    return OGN_OK;
+}
+
+int ogn_output(ogn_ctx *ctx, const char *name, void *p, size_t bytes, void **dev) {
+    if (p && ogn_is_device_ptr(p)) {
+        *dev = p;
+        return OGN_OK;
+    }
+    return ogn_scratch(ctx, name, bytes, dev);
+}
+
+int ogn_output_commit(ogn_ctx *ctx, void *p, const void *dev, size_t bytes) {
+    if (!p || p == dev) return OGN_OK;
+    OGN_CUDA(cudaMemcpyAsync(p, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->host_output_pending = true;
+    return OGN_OK;
+}
+
+int ogn_finish_call(ogn_ctx *ctx) {
+    if (ctx->host_output_pending) {
+        OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->host_output_pending = false;
+    }
+    return OGN_OK;
+}
+
+// ---------------------------------------------------------------------------
+
+template <typename S, typename D>
+__global__ void convert_kernel(const S *__restrict__ src, D *__restrict__ dst, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = static_cast<D>(src[i]);
+}
+
+int ogn_convert_f64_to_f32(ogn_ctx *ctx, const double *src, float *dst, size_t n) {
+    int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+    if (blocks == 0) return OGN_OK;
+    convert_kernel<double, float><<<blocks, 256, 0, ctx->stream>>>(src, dst, n);
+    OGN_LAUNCH_CHECK("convert_f64_f32");
+    return OGN_OK;
+}
+
+int ogn_convert_f32_to_f64(ogn_ctx *ctx, const float *src, double *dst, size_t n) {
+    int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+    if (blocks == 0) return OGN_OK;
+    convert_kernel<float, double><<<blocks, 256, 0, ctx->stream>>>(src, dst, n);
+    OGN_LAUNCH_CHECK("convert_f32_f64");
+    return OGN_OK;
+}
+
+int ogn_input_cube_f32(ogn_ctx *ctx, const char *name, const void *p, int dtype, size_t n,
+                       const float **dev) {
+    if (dtype == OGN_F32) {
+        const void *d = nullptr;
+        OGN_TRY(ogn_input(ctx, name, p, n * sizeof(float), &d));
+        *dev = static_cast<const float *>(d);
+        return OGN_OK;
+    }
+    if (dtype != OGN_F64) return ogn_fail(ctx, OGN_ERR_ARG, "unknown dtype %d for '%s'", dtype, name);
+    std::string stage = std::string(name) + ".f64";
+    const void *d64 = nullptr;
+    OGN_TRY(ogn_input(ctx, stage.c_str(), p, n * sizeof(double), &d64));
+    float *d32 = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, name, n, &d32));
+    OGN_TRY(ogn_convert_f64_to_f32(ctx, static_cast<const double *>(d64), d32, n));
+    *dev = d32;
+    return OGN_OK;
+}

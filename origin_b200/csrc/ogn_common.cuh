@@ -1,0 +1,99 @@
+// Shared plumbing of libogn: context, scratch arena, host<->device staging.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ogn.h"
+
+struct ogn_buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+// State kept between ogn_preprocess_begin and ogn_preprocess_finish.
+struct ogn_prep_state {
+    bool active = false;
+    int nz = 0, ny = 0, nx = 0, in_dtype = 0;
+    const void *var = nullptr;      // device
+    const uint8_t *mask = nullptr;  // device
+    float *data = nullptr;          // device: raw - cont (f32)
+    double *cont = nullptr;         // device: continuum (f64)
+};
+
+struct ogn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 148;
+    std::map<std::string, ogn_buf> bufs;  // named device scratch, grow-only
+    std::map<std::string, ogn_buf> pins;  // named pinned host scratch, grow-only
+    bool host_output_pending = false;     // a D2H copy to caller memory was enqueued
+    ogn_prep_state prep;
+};
+
+int ogn_fail(ogn_ctx *ctx, int code, const char *fmt, ...);
+
+#define OGN_CUDA(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return ogn_fail(ctx, OGN_ERR_CUDA, "%s failed: %s (%s:%d)", #call,               \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                    \
+    } while (0)
+
+#define OGN_TRY(expr)              \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != OGN_OK) return rc__; \
+    } while (0)
+
+#define OGN_LAUNCH_CHECK(name)                                                               \
+    do {                                                                                     \
+        ctx->launches++;                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess)                                                              \
+            return ogn_fail(ctx, OGN_ERR_CUDA, "launch of %s failed: %s", name,              \
+                            cudaGetErrorString(e__));                                        \
+    } while (0)
+
+// Named device scratch buffer of at least `bytes` (contents undefined).
+int ogn_scratch(ogn_ctx *ctx, const char *name, size_t bytes, void **out);
+// Named pinned host scratch.
+int ogn_pinned(ogn_ctx *ctx, const char *name, size_t bytes, void **out);
+// true when `p` can be dereferenced by kernels on the context's device.
+bool ogn_is_device_ptr(const void *p);
+// Device view of an input: `p` itself when it is a device pointer, else a copy
+// in the scratch buffer `name` (async on the context stream).
+int ogn_input(ogn_ctx *ctx, const char *name, const void *p, size_t bytes, const void **dev);
+// Device buffer for an output: `p` itself when it is a device pointer, else
+// the scratch buffer `name`; ogn_output_commit copies it back when needed.
+int ogn_output(ogn_ctx *ctx, const char *name, void *p, size_t bytes, void **dev);
+int ogn_output_commit(ogn_ctx *ctx, void *p, const void *dev, size_t bytes);
+// Synchronise the stream if any host output is pending.
+int ogn_finish_call(ogn_ctx *ctx);
+
+template <typename T>
+static inline int ogn_scratch_t(ogn_ctx *ctx, const char *name, size_t count, T **out) {
+    void *p = nullptr;
+    int rc = ogn_scratch(ctx, name, count * sizeof(T), &p);
+    *out = static_cast<T *>(p);
+    return rc;
+}
+
+static inline int ogn_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline int64_t ogn_round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// Elementwise conversion kernels (ogn_api.cu)
+int ogn_convert_f64_to_f32(ogn_ctx *ctx, const double *src, float *dst, size_t n);
+int ogn_convert_f32_to_f64(ogn_ctx *ctx, const float *src, double *dst, size_t n);
+// Device f32 view [n] of a cube given as host/device f32/f64.
+int ogn_input_cube_f32(ogn_ctx *ctx, const char *name, const void *p, int dtype, size_t n,
+                       const float **dev);

@@ -1,0 +1,458 @@
+// 3-D local extrema (compute_local_max, lib_origin.py:1220-1256), ordered compaction,
+// step06 purity counts (lib_origin.py:1424-1449) and step07 thresholding (steps.py:956-974).
+//
+//   K3  local_extrema_kernel   window max of a / window min of b, equality test, mask,
+//                              dense products, one ballot word per 32 voxels
+//   K3b scan + scatter         order-preserving compaction of the flag words into
+//                              (linear index, value) lists = np.where order
+//   K4  purity_stats / purity_counts kernels over the lists
+//   K6  threshold_select       order-preserving selection value > threshold
+#include <math.h>
+
+#include "ogn_common.cuh"
+
+// A maximum filter with scipy's 'reflect' boundary only ever sees in-range
+// samples (the reflected positions lie inside the clipped window), so the
+// out-of-range part of the window is simply skipped.
+__global__ void local_extrema_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                     const uint8_t *__restrict__ mask, int nz, int ny, int nx, int rz, int ry,
+                                     int rx, float *__restrict__ dense_max, float *__restrict__ dense_min,
+                                     uint32_t *__restrict__ flag_max, uint32_t *__restrict__ flag_min, int nxw) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = blockIdx.z;
+    if (y >= ny) return;  // whole warp (a warp is one row of 32 x)
+    bool keep_a = false, keep_b = false;
+    float va = 0.f, vb = 0.f;
+    size_t idx = 0;
+    if (x < nx) {
+        idx = ((size_t)z * ny + y) * nx + x;
+        va = a[idx];
+        vb = b[idx];
+        float ma = -INFINITY, mb = INFINITY;
+        const int z0 = max(0, z - rz), z1 = min(nz - 1, z + rz);
+        const int y0 = max(0, y - ry), y1 = min(ny - 1, y + ry);
+        const int x0 = max(0, x - rx), x1 = min(nx - 1, x + rx);
+        for (int zz = z0; zz <= z1; ++zz)
+            for (int yy = y0; yy <= y1; ++yy) {
+                const size_t row = ((size_t)zz * ny + yy) * nx;
+                for (int xx = x0; xx <= x1; ++xx) {
+                    ma = fmaxf(ma, a[row + xx]);
+                    mb = fminf(mb, b[row + xx]);
+                }
+            }
+        const bool free_voxel = !(mask && mask[idx]);
+        keep_a = free_voxel && va == ma;
+        keep_b = free_voxel && vb == mb;
+        if (dense_max) dense_max[idx] = keep_a ? va : 0.f;
+        if (dense_min) dense_min[idx] = keep_b ? -vb : 0.f;
+    }
+    const uint32_t wa = __ballot_sync(0xffffffffu, keep_a);
+    const uint32_t wb = __ballot_sync(0xffffffffu, keep_b);
+    if (threadIdx.x == 0) {
+        const size_t w = ((size_t)z * ny + y) * nxw + blockIdx.x;
+        flag_max[w] = wa;
+        flag_min[w] = wb;
+    }
+}
+
+// ---- exclusive scan of popcounts (3 phases, 1024 words per block) ------------------------
+constexpr int SCAN_BLOCK = 1024;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
+    __shared__ int warp_sums[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int s = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const int base = warp ? warp_sums[warp - 1] : 0;
+    if (total) *total = warp_sums[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+// phase 1: per-block totals of popc(flags) (or of a 0/1 predicate array)
+template <bool POPC>
+__global__ void scan_block_totals_kernel(const uint32_t *__restrict__ in, size_t n, int64_t *__restrict__ block_tot) {
+    const size_t i = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    int v = i < n ? (POPC ? __popc(in[i]) : (int)in[i]) : 0;
+    int total;
+    block_exclusive_scan(v, &total);
+    if (threadIdx.x == 0) block_tot[blockIdx.x] = total;
+}
+
+// phase 2: one block turns block totals into exclusive offsets; total -> *grand
+__global__ void scan_block_offsets_kernel(int64_t *__restrict__ block_tot, int nblocks, int64_t *__restrict__ grand) {
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        int v = i < nblocks ? (int)block_tot[i] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, &total);
+        if (i < nblocks) block_tot[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand = carry;
+}
+
+// phase 3 (extrema): scatter the set bits of every flag word, in order
+__global__ void scatter_flags_kernel(const uint32_t *__restrict__ flags, size_t nwords,
+                                     const int64_t *__restrict__ block_off, const float *__restrict__ src,
+                                     float sign, int nx, int nxw, int64_t *__restrict__ out_index,
+                                     float *__restrict__ out_value, int64_t capacity) {
+    const size_t i = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    uint32_t w = i < nwords ? flags[i] : 0u;
+    int ex = block_exclusive_scan(__popc(w), nullptr);
+    if (!w) return;
+    int64_t pos = block_off[blockIdx.x] + ex;
+    const size_t rowid = i / nxw;  // z*ny + y
+    const int xw = (int)(i - rowid * nxw);
+    const size_t base = rowid * nx + (size_t)xw * 32;
+    while (w) {
+        const int bit = __ffs(w) - 1;
+        w &= w - 1;
+        if (pos < capacity) {
+            out_index[pos] = (int64_t)(base + bit);
+            out_value[pos] = sign * src[base + bit];
+        }
+        ++pos;
+    }
+}
+
+// ---- K4 -----------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_f32(float *addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+// stats[0] = max(list), spaxel_max[spaxel] = max(spaxel_max, value) ; background-only when segmask given
+__global__ void list_stats_kernel(const int64_t *__restrict__ index, const float *__restrict__ value, int64_t n,
+                                  const uint8_t *__restrict__ segmask, int64_t img, float *__restrict__ stat,
+                                  float *__restrict__ spaxel_max) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float m = -INFINITY;
+    if (i < n) {
+        const float v = value[i];
+        const int64_t sp = index[i] % img;
+        if (!(segmask && segmask[sp])) m = v;
+        if (spaxel_max) atomic_max_f32(spaxel_max + sp, v);
+    }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > -INFINITY) atomic_max_f32(stat, m);
+}
+
+// counts[t] += #{entries (background only when segmask) with value > thresholds[t]}
+__global__ void list_counts_kernel(const int64_t *__restrict__ index, const float *__restrict__ value, int64_t n,
+                                   const uint8_t *__restrict__ segmask, int64_t img,
+                                   const double *__restrict__ thresholds, int nthresh,
+                                   unsigned long long *__restrict__ counts) {
+    extern __shared__ unsigned int sm_counts[];
+    for (int t = threadIdx.x; t < nthresh; t += blockDim.x) sm_counts[t] = 0;
+    __syncthreads();
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = i < n;
+    double v = 0;
+    if (live) {
+        v = (double)value[i];
+        if (segmask && segmask[index[i] % img]) live = false;
+    }
+    for (int t = 0; t < nthresh; ++t) {
+        const bool hit = live && v > thresholds[t];
+        const unsigned int b = __ballot_sync(0xffffffffu, hit);
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(&sm_counts[t], __popc(b));
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nthresh; t += blockDim.x)
+        if (sm_counts[t]) atomicAdd(&counts[t], (unsigned long long)sm_counts[t]);
+}
+
+// ---- K6 -----------------------------------------------------------------------------------
+__global__ void threshold_flag_kernel(const float *__restrict__ value, int64_t n, double thr, uint32_t *__restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (double)value[i] > thr ? 1u : 0u;
+}
+
+__global__ void threshold_scatter_kernel(const uint32_t *__restrict__ flag, size_t n, const int64_t *__restrict__ block_off,
+                                         const int64_t *__restrict__ index, const float *__restrict__ value,
+                                         const uint8_t *__restrict__ profile, int64_t *__restrict__ out_index,
+                                         float *__restrict__ out_value, uint8_t *__restrict__ out_profile,
+                                         int64_t capacity) {
+    const size_t i = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t f = i < n ? flag[i] : 0u;
+    const int ex = block_exclusive_scan((int)f, nullptr);
+    if (!f) return;
+    const int64_t pos = block_off[blockIdx.x] + ex;
+    if (pos >= capacity) return;
+    const int64_t idx = index[i];
+    if (out_index) out_index[pos] = idx;
+    if (out_value) out_value[pos] = value[i];
+    if (out_profile) out_profile[pos] = profile ? profile[idx] : 0;
+}
+
+// -------------------------------------------------------------------------------------------
+
+static int compact_flags(ogn_ctx *ctx, const char *tag, const uint32_t *flags, size_t nwords, const float *src,
+                         float sign, int nx, int nxw, int64_t *out_index, float *out_value, int64_t capacity,
+                         int64_t *d_count) {
+    const int nblocks = ogn_div_up((int64_t)nwords, SCAN_BLOCK);
+    int64_t *block_tot = nullptr;
+    std::string name = std::string("scan_tot_") + tag;
+    OGN_TRY(ogn_scratch_t(ctx, name.c_str(), (size_t)nblocks + 1, &block_tot));
+    scan_block_totals_kernel<true><<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, nwords, block_tot);
+    OGN_LAUNCH_CHECK("scan_block_totals_kernel");
+    scan_block_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(block_tot, nblocks, d_count);
+    OGN_LAUNCH_CHECK("scan_block_offsets_kernel");
+    if (out_index && out_value && capacity > 0) {
+        scatter_flags_kernel<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, nwords, block_tot, src, sign, nx, nxw,
+                                                                      out_index, out_value, capacity);
+        OGN_LAUNCH_CHECK("scatter_flags_kernel");
+    }
+    return OGN_OK;
+}
+
+extern "C" int ogn_local_extrema(ogn_ctx *ctx, const float *a, const float *b, const uint8_t *mask, int nz, int ny,
+                                 int nx, int sz, int sy, int sx, float *dense_max, float *dense_min,
+                                 int64_t *max_index, float *max_value, int64_t *min_index, float *min_value,
+                                 int64_t capacity, int64_t *counts) {
+    if (!ctx) return OGN_ERR_ARG;
+    if (nz <= 0 || ny <= 0 || nx <= 0) return ogn_fail(ctx, OGN_ERR_ARG, "cube shape (%d,%d,%d) is empty", nz, ny, nx);
+    if (sz < 1 || sy < 1 || sx < 1 || !(sz & 1) || !(sy & 1) || !(sx & 1))
+        return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "window (%d,%d,%d): only odd sizes are supported", sz, sy, sx);
+    if (!a || !b) return ogn_fail(ctx, OGN_ERR_ARG, "a / b must not be NULL");
+    if (nz > 65535) return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "nz = %d exceeds the launch grid", nz);
+    OGN_CUDA(cudaSetDevice(ctx->device));
+    const size_t vol = (size_t)nz * ny * nx;
+    const int nxw = ogn_div_up(nx, 32);
+    const size_t nwords = (size_t)nz * ny * nxw;
+
+    const void *da = nullptr, *db = nullptr, *dm = nullptr;
+    OGN_TRY(ogn_input(ctx, "ext_a", a, vol * 4, &da));
+    if (b == a) db = da;
+    else OGN_TRY(ogn_input(ctx, "ext_b", b, vol * 4, &db));
+    if (mask) OGN_TRY(ogn_input(ctx, "ext_mask", mask, vol, &dm));
+
+    void *d_dmax = nullptr, *d_dmin = nullptr;
+    if (dense_max) OGN_TRY(ogn_output(ctx, "ext_dense_max", dense_max, vol * 4, &d_dmax));
+    if (dense_min) OGN_TRY(ogn_output(ctx, "ext_dense_min", dense_min, vol * 4, &d_dmin));
+    uint32_t *flag_max = nullptr, *flag_min = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, "ext_flag_max", nwords, &flag_max));
+    OGN_TRY(ogn_scratch_t(ctx, "ext_flag_min", nwords, &flag_min));
+
+    {
+        dim3 block(32, 8);
+        dim3 grid(nxw, ogn_div_up(ny, 8), nz);
+        local_extrema_kernel<<<grid, block, 0, ctx->stream>>>((const float *)da, (const float *)db,
+                                                             (const uint8_t *)dm, nz, ny, nx, sz / 2, sy / 2, sx / 2,
+                                                             (float *)d_dmax, (float *)d_dmin, flag_max, flag_min, nxw);
+        OGN_LAUNCH_CHECK("local_extrema_kernel");
+    }
+
+    const bool want_lists = max_index && max_value && min_index && min_value && capacity > 0;
+    void *d_maxi = nullptr, *d_maxv = nullptr, *d_mini = nullptr, *d_minv = nullptr;
+    if (want_lists) {
+        OGN_TRY(ogn_output(ctx, "ext_max_index", max_index, (size_t)capacity * 8, &d_maxi));
+        OGN_TRY(ogn_output(ctx, "ext_max_value", max_value, (size_t)capacity * 4, &d_maxv));
+        OGN_TRY(ogn_output(ctx, "ext_min_index", min_index, (size_t)capacity * 8, &d_mini));
+        OGN_TRY(ogn_output(ctx, "ext_min_value", min_value, (size_t)capacity * 4, &d_minv));
+    }
+    int64_t *d_counts = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, "ext_counts", (size_t)2, &d_counts));
+    OGN_TRY(compact_flags(ctx, "max", flag_max, nwords, (const float *)da, 1.f, nx, nxw, (int64_t *)d_maxi,
+                          (float *)d_maxv, want_lists ? capacity : 0, d_counts));
+    OGN_TRY(compact_flags(ctx, "min", flag_min, nwords, (const float *)db, -1.f, nx, nxw, (int64_t *)d_mini,
+                          (float *)d_minv, want_lists ? capacity : 0, d_counts + 1));
+
+    int64_t h_counts[2] = {0, 0};
+    OGN_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost, ctx->stream));
+    OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (counts) {
+        if (ogn_is_device_ptr(counts)) OGN_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToDevice, ctx->stream));
+        else { counts[0] = h_counts[0]; counts[1] = h_counts[1]; }
+    }
+    OGN_TRY(ogn_output_commit(ctx, dense_max, d_dmax, vol * 4));
+    OGN_TRY(ogn_output_commit(ctx, dense_min, d_dmin, vol * 4));
+    if (want_lists) {
+        const size_t nmax = (size_t)std::min<int64_t>(h_counts[0], capacity);
+        const size_t nmin = (size_t)std::min<int64_t>(h_counts[1], capacity);
+        OGN_TRY(ogn_output_commit(ctx, max_index, d_maxi, nmax * 8));
+        OGN_TRY(ogn_output_commit(ctx, max_value, d_maxv, nmax * 4));
+        OGN_TRY(ogn_output_commit(ctx, min_index, d_mini, nmin * 8));
+        OGN_TRY(ogn_output_commit(ctx, min_value, d_minv, nmin * 4));
+    }
+    OGN_TRY(ogn_finish_call(ctx));
+    if (want_lists && (h_counts[0] > capacity || h_counts[1] > capacity))
+        return ogn_fail(ctx, OGN_ERR_OVERFLOW, "extremum lists need %lld / %lld entries, capacity is %lld",
+                        (long long)h_counts[0], (long long)h_counts[1], (long long)capacity);
+    return OGN_OK;
+}
+
+__global__ void fill_f32_kernel2(float *p, size_t n, float v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+struct ListsDev {
+    const int64_t *maxi = nullptr, *mini = nullptr;
+    const float *maxv = nullptr, *minv = nullptr;
+    const uint8_t *seg = nullptr;
+};
+
+static int stage_lists(ogn_ctx *ctx, const int64_t *max_index, const float *max_value, int64_t nmax,
+                       const int64_t *min_index, const float *min_value, int64_t nmin, const uint8_t *segmask,
+                       size_t img, ListsDev *out) {
+    const void *d = nullptr;
+    if (nmax > 0) {
+        OGN_TRY(ogn_input(ctx, "pur_maxi", max_index, (size_t)nmax * 8, &d)); out->maxi = (const int64_t *)d;
+        OGN_TRY(ogn_input(ctx, "pur_maxv", max_value, (size_t)nmax * 4, &d)); out->maxv = (const float *)d;
+    }
+    if (nmin > 0) {
+        OGN_TRY(ogn_input(ctx, "pur_mini", min_index, (size_t)nmin * 8, &d)); out->mini = (const int64_t *)d;
+        OGN_TRY(ogn_input(ctx, "pur_minv", min_value, (size_t)nmin * 4, &d)); out->minv = (const float *)d;
+    }
+    if (segmask) {
+        OGN_TRY(ogn_input(ctx, "pur_seg", segmask, img, &d)); out->seg = (const uint8_t *)d;
+    }
+    return OGN_OK;
+}
+
+extern "C" int ogn_purity_stats(ogn_ctx *ctx, const int64_t *max_index, const float *max_value, int64_t nmax,
+                                const int64_t *min_index, const float *min_value, int64_t nmin,
+                                const uint8_t *segmask, int ny, int nx, double *stats, float *spaxel_max) {
+    if (!ctx) return OGN_ERR_ARG;
+    if (nmax < 0 || nmin < 0 || ny <= 0 || nx <= 0) return ogn_fail(ctx, OGN_ERR_ARG, "invalid sizes");
+    OGN_CUDA(cudaSetDevice(ctx->device));
+    const size_t img = (size_t)ny * nx;
+    ListsDev L;
+    OGN_TRY(stage_lists(ctx, max_index, max_value, nmax, min_index, min_value, nmin, segmask, img, &L));
+    float *d_stat = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, "pur_stat", (size_t)2, &d_stat));
+    fill_f32_kernel2<<<1, 32, 0, ctx->stream>>>(d_stat, 2, -INFINITY);
+    OGN_LAUNCH_CHECK("fill_f32_kernel");
+    void *d_sp = nullptr;
+    if (spaxel_max) {
+        OGN_TRY(ogn_output(ctx, "pur_spaxel_max", spaxel_max, img * 4, &d_sp));
+        OGN_CUDA(cudaMemsetAsync(d_sp, 0, img * 4, ctx->stream));
+    }
+    if (nmax > 0) {
+        list_stats_kernel<<<ogn_div_up(nmax, 256), 256, 0, ctx->stream>>>(L.maxi, L.maxv, nmax, nullptr, (int64_t)img,
+                                                                          d_stat, (float *)d_sp);
+        OGN_LAUNCH_CHECK("list_stats_kernel");
+    }
+    if (nmin > 0) {
+        list_stats_kernel<<<ogn_div_up(nmin, 256), 256, 0, ctx->stream>>>(L.mini, L.minv, nmin, L.seg, (int64_t)img,
+                                                                          d_stat + 1, nullptr);
+        OGN_LAUNCH_CHECK("list_stats_kernel");
+    }
+    float h_stat[2];
+    OGN_CUDA(cudaMemcpyAsync(h_stat, d_stat, sizeof(h_stat), cudaMemcpyDeviceToHost, ctx->stream));
+    OGN_TRY(ogn_output_commit(ctx, spaxel_max, d_sp, img * 4));
+    OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->host_output_pending = false;
+    if (stats) { stats[0] = h_stat[0]; stats[1] = h_stat[1]; }
+    return OGN_OK;
+}
+
+extern "C" int ogn_purity_counts(ogn_ctx *ctx, const int64_t *max_index, const float *max_value, int64_t nmax,
+                                 const int64_t *min_index, const float *min_value, int64_t nmin,
+                                 const uint8_t *segmask, int ny, int nx, const double *thresholds, int nthresh,
+                                 int64_t *n1, int64_t *n0) {
+    if (!ctx) return OGN_ERR_ARG;
+    if (nmax < 0 || nmin < 0 || ny <= 0 || nx <= 0 || nthresh < 1 || nthresh > 8192 || !thresholds || !n1 || !n0)
+        return ogn_fail(ctx, OGN_ERR_ARG, "invalid arguments (nthresh must be in 1..8192)");
+    OGN_CUDA(cudaSetDevice(ctx->device));
+    const size_t img = (size_t)ny * nx;
+    ListsDev L;
+    OGN_TRY(stage_lists(ctx, max_index, max_value, nmax, min_index, min_value, nmin, segmask, img, &L));
+    const void *d_thr = nullptr;
+    OGN_TRY(ogn_input(ctx, "pur_thr", thresholds, (size_t)nthresh * 8, &d_thr));
+    void *d_n1 = nullptr, *d_n0 = nullptr;
+    OGN_TRY(ogn_output(ctx, "pur_n1", n1, (size_t)nthresh * 8, &d_n1));
+    OGN_TRY(ogn_output(ctx, "pur_n0", n0, (size_t)nthresh * 8, &d_n0));
+    OGN_CUDA(cudaMemsetAsync(d_n1, 0, (size_t)nthresh * 8, ctx->stream));
+    OGN_CUDA(cudaMemsetAsync(d_n0, 0, (size_t)nthresh * 8, ctx->stream));
+    const size_t sm = (size_t)nthresh * sizeof(unsigned int);
+    if (nmax > 0) {
+        list_counts_kernel<<<ogn_div_up(nmax, 256), 256, sm, ctx->stream>>>(L.maxi, L.maxv, nmax, nullptr, (int64_t)img,
+                                                                            (const double *)d_thr, nthresh,
+                                                                            (unsigned long long *)d_n1);
+        OGN_LAUNCH_CHECK("list_counts_kernel");
+    }
+    if (nmin > 0) {
+        list_counts_kernel<<<ogn_div_up(nmin, 256), 256, sm, ctx->stream>>>(L.mini, L.minv, nmin, L.seg, (int64_t)img,
+                                                                            (const double *)d_thr, nthresh,
+                                                                            (unsigned long long *)d_n0);
+        OGN_LAUNCH_CHECK("list_counts_kernel");
+    }
+    OGN_TRY(ogn_output_commit(ctx, n1, d_n1, (size_t)nthresh * 8));
+    OGN_TRY(ogn_output_commit(ctx, n0, d_n0, (size_t)nthresh * 8));
+    return ogn_finish_call(ctx);
+}
+
+extern "C" int ogn_threshold_extract(ogn_ctx *ctx, const int64_t *index, const float *value, int64_t n,
+                                     double threshold, const uint8_t *profile, int64_t *out_index, float *out_value,
+                                     uint8_t *out_profile, int64_t capacity, int64_t *out_count) {
+    if (!ctx) return OGN_ERR_ARG;
+    if (n < 0 || capacity < 0) return ogn_fail(ctx, OGN_ERR_ARG, "invalid sizes");
+    OGN_CUDA(cudaSetDevice(ctx->device));
+    if (n == 0) {
+        if (out_count) *out_count = 0;
+        return OGN_OK;
+    }
+    if (profile && !ogn_is_device_ptr(profile))
+        return ogn_fail(ctx, OGN_ERR_ARG, "profile cube must be a device pointer (gather the rows on the host otherwise)");
+    const void *d_idx = nullptr, *d_val = nullptr;
+    OGN_TRY(ogn_input(ctx, "thr_index", index, (size_t)n * 8, &d_idx));
+    OGN_TRY(ogn_input(ctx, "thr_value", value, (size_t)n * 4, &d_val));
+    uint32_t *flag = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, "thr_flag", (size_t)n, &flag));
+    threshold_flag_kernel<<<ogn_div_up(n, 256), 256, 0, ctx->stream>>>((const float *)d_val, n, threshold, flag);
+    OGN_LAUNCH_CHECK("threshold_flag_kernel");
+    const int nblocks = ogn_div_up(n, SCAN_BLOCK);
+    int64_t *block_tot = nullptr, *d_count = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, "thr_scan", (size_t)nblocks + 1, &block_tot));
+    OGN_TRY(ogn_scratch_t(ctx, "thr_count", (size_t)1, &d_count));
+    scan_block_totals_kernel<false><<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(flag, (size_t)n, block_tot);
+    OGN_LAUNCH_CHECK("scan_block_totals_kernel");
+    scan_block_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(block_tot, nblocks, d_count);
+    OGN_LAUNCH_CHECK("scan_block_offsets_kernel");
+    void *d_oi = nullptr, *d_ov = nullptr, *d_op = nullptr;
+    if (capacity > 0) {
+        if (out_index) OGN_TRY(ogn_output(ctx, "thr_out_index", out_index, (size_t)capacity * 8, &d_oi));
+        if (out_value) OGN_TRY(ogn_output(ctx, "thr_out_value", out_value, (size_t)capacity * 4, &d_ov));
+        if (out_profile) OGN_TRY(ogn_output(ctx, "thr_out_profile", out_profile, (size_t)capacity, &d_op));
+        threshold_scatter_kernel<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(flag, (size_t)n, block_tot, (const int64_t *)d_idx,
+                                                                          (const float *)d_val, profile, (int64_t *)d_oi,
+                                                                          (float *)d_ov, (uint8_t *)d_op, capacity);
+        OGN_LAUNCH_CHECK("threshold_scatter_kernel");
+    }
+    int64_t h_count = 0;
+    OGN_CUDA(cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (out_count) *out_count = h_count;
+    const size_t m = (size_t)std::min<int64_t>(h_count, capacity);
+    OGN_TRY(ogn_output_commit(ctx, out_index, d_oi, m * 8));
+    OGN_TRY(ogn_output_commit(ctx, out_value, d_ov, m * 4));
+    OGN_TRY(ogn_output_commit(ctx, out_profile, d_op, m));
+    OGN_TRY(ogn_finish_call(ctx));
+    if (h_count > capacity && (out_index || out_value || out_profile))
+        return ogn_fail(ctx, OGN_ERR_OVERFLOW, "threshold list needs %lld entries, capacity is %lld",
+                        (long long)h_count, (long long)capacity);
+    return OGN_OK;
+}

@@ -1,0 +1,847 @@
+// step05 TGLR matched filter (Correlation_GLR_test, lib_origin.py:1070-1217).
+//
+//   K0  fsf_prep_kernel      per-plane zero-mean FSF weights (+ edge-class norm table)
+//   K0b den_table_kernel     single field: 1/sqrt(den_k) per (profile, edge class, z)
+//   K1  fsf_correlate_kernel per-lambda 2-D FSF correlation, TMA-staged halo tiles,
+//                            1x32 register strips, weights broadcast from smem
+//   K2  spectral_glr_kernel  per-spectrum correlation with every profile along lambda,
+//                            register ring windows fed from a shared-memory column
+//                            window, fused normalisation + max / argmax / min
+//                            (the profile-by-cube intermediate never reaches HBM)
+//
+// See DESIGN.md for the data layout and the roofline of each kernel.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "ogn_common.cuh"
+
+// ---------------------------------------------------------------------------
+// Edge classes.  With a single FSF the denominator of the GLR does not depend
+// on the data: norm_fsf[z,y,x] = sum of K_z^2 over the part of the P x P
+// footprint that falls inside the image (lib_origin.py:1039-1041 with
+// weights=None).  Along an axis of length n there are min(n, P) distinct
+// clippings ("classes"); class P/2 is the interior.
+// ---------------------------------------------------------------------------
+__host__ __device__ static inline int cls_of(int y, int n, int P) {
+    int half = P / 2;
+    if (n < P) return y;
+    if (y < half) return y;
+    if (y >= n - half) return P - (n - y);
+    return half;
+}
+__host__ __device__ static inline void cls_range(int c, int n, int P, int *lo, int *hi) {
+    int half = P / 2;
+    int y;
+    if (n < P) y = c;
+    else if (c < half) y = c;
+    else if (c == half) y = half;
+    else y = n - P + c;
+    *lo = max(0, half - y);
+    *hi = min(P - 1, half + (n - 1 - y));
+}
+
+// K0: one block per (plane, field).
+//   w32   [nf][nz][P][WP] float   K = psf - mean(psf), rows padded to WP with zeros
+//   w32sq [nf][nz][P][WP] float   K^2 (only when want_sq: weighted / multi-field path)
+//   normcls [NC][nzp] double      box sums of K^2 per edge class (single-field path)
+__global__ void fsf_prep_kernel(const double *const *__restrict__ fsf, int nz, int P, int WP,
+                                float *__restrict__ w32, float *__restrict__ w32sq,
+                                double *__restrict__ normcls, int nzp, int ny, int nx, int ncy, int ncx) {
+    extern __shared__ double sm[];
+    double *k2 = sm;           // P*P, later its 2-D inclusive prefix sum
+    double *red = sm + P * P;  // 32
+    const int z = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, n = P * P;
+    const double *psf = fsf[f] + (size_t)z * n;
+    double s = 0;
+    for (int i = tid; i < n; i += blockDim.x) s += psf[i];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid < 32) {
+        double t = tid < (blockDim.x >> 5) ? red[tid] : 0.0;
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (tid == 0) red[0] = t / n;
+    }
+    __syncthreads();
+    const double mean = red[0];
+    float *wz = w32 + ((size_t)f * nz + z) * P * WP;
+    float *wq = w32sq ? w32sq + ((size_t)f * nz + z) * P * WP : nullptr;
+    for (int i = tid; i < P * WP; i += blockDim.x) {
+        int dy = i / WP, dx = i - dy * WP;
+        double k = dx < P ? psf[dy * P + dx] - mean : 0.0;
+        wz[i] = (float)k;
+        if (wq) wq[i] = (float)(k * k);
+        if (dx < P) k2[dy * P + dx] = k * k;
+    }
+    if (!normcls) return;
+    __syncthreads();
+    if (tid < P) {  // prefix along x
+        double a = 0;
+        for (int dx = 0; dx < P; ++dx) { a += k2[tid * P + dx]; k2[tid * P + dx] = a; }
+    }
+    __syncthreads();
+    if (tid < P) {  // prefix along y
+        double a = 0;
+        for (int dy = 0; dy < P; ++dy) { a += k2[dy * P + tid]; k2[dy * P + tid] = a; }
+    }
+    __syncthreads();
+    for (int c = tid; c < ncy * ncx; c += blockDim.x) {
+        int cy = c / ncx, cx = c - cy * ncx, ly, hy, lx, hx;
+        cls_range(cy, ny, P, &ly, &hy);
+        cls_range(cx, nx, P, &lx, &hx);
+        double v = k2[hy * P + hx];
+        if (ly > 0) v -= k2[(ly - 1) * P + hx];
+        if (lx > 0) v -= k2[hy * P + lx - 1];
+        if (ly > 0 && lx > 0) v += k2[(ly - 1) * P + lx - 1];
+        normcls[(size_t)c * nzp + z] = v;
+    }
+}
+
+// K0b: rs[k][cls][z] = 1/sqrt(sum_j d_k[j]^2 normcls[cls][z + c_k - j]) (0 when the sum is <= 0,
+// the reference's "norm <= 0 -> inf", lib_origin.py:1057-1059).
+__global__ void den_table_kernel(const double *__restrict__ normcls, int nz, int nzp, int ncls,
+                                 const double *__restrict__ taps, const int *__restrict__ tap_off, int nprof,
+                                 float *__restrict__ rs) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cls = blockIdx.y, k = blockIdx.z;
+    if (z >= nzp) return;
+    float out = 0.f;
+    if (z < nz) {
+        const double *d = taps + tap_off[k];
+        const int L = tap_off[k + 1] - tap_off[k];
+        const int ck = (L - 1) / 2;
+        const double *src = normcls + (size_t)cls * nzp;
+        double den = 0;
+        for (int j = 0; j < L; ++j) {
+            int zz = z + ck - j;
+            if (zz >= 0 && zz < nz) den += d[j] * d[j] * src[zz];
+        }
+        out = den > 0 ? (float)(1.0 / sqrt(den)) : 0.f;
+    }
+    rs[((size_t)k * ncls + cls) * nzp + z] = out;
+}
+
+// ---------------------------------------------------------------------------
+// K1: per-lambda FSF correlation.
+//
+// A block owns one 64 x 64 output tile and walks a range of wavelength planes.
+// Per plane, one elected thread issues a 3-D TMA load of the (64+P-1) x PITCH
+// input tile (out-of-bounds elements are filled with zeros by the TMA unit =
+// the reference's zero padding) and a bulk copy of that plane's P x WP weights;
+// the block waits on an mbarrier.  Each of the 128 threads then computes a
+// 1 x 32 strip of outputs: per FSF row it loads 32+P-1 inputs (LDS.128,
+// conflict-free because PITCH = 4 mod 32 and the lanes of a warp are 32
+// consecutive rows) and the P weights of the row (LDS.128 broadcast) and issues
+// 32*P FFMAs from registers.
+// ---------------------------------------------------------------------------
+namespace k1 {
+constexpr int TILE = 64;     // outputs per tile side
+constexpr int STRIP = 32;    // outputs per thread
+constexpr int THREADS = TILE * (TILE / STRIP);
+
+template <int P>
+struct Geo {
+    static constexpr int WP = (P + 3) / 4 * 4;
+    static constexpr int ROWS = TILE + P - 1;
+    static constexpr int NEED = TILE + P - 1;
+    // smallest pitch >= NEED with pitch % 32 == 4 (conflict-free LDS.128 across rows)
+    static constexpr int PITCH = ((NEED - 4 + 31) / 32) * 32 + 4;
+    static constexpr int IN_N = (STRIP + P - 1 + 3) / 4 * 4;
+    static constexpr int TILE_BYTES = ROWS * PITCH * 4;
+    static constexpr int W_BYTES = P * WP * 4;
+    static constexpr int SMEM = TILE_BYTES + W_BYTES + 16;
+    static_assert(PITCH >= (TILE / STRIP - 1) * STRIP + IN_N, "pitch too small for the last strip");
+    static_assert(PITCH <= 256, "TMA box dimension limit");
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int P>
+__global__ void __launch_bounds__(THREADS, 4)
+fsf_correlate_kernel(const __grid_constant__ CUtensorMap in_map, int in_z_invariant,
+                     const float *__restrict__ weights,  // [nz][P][WP]
+                     float *__restrict__ out, int oy0, int ox0, int ony, int onx, int opitch,
+                     int nz, int zsplit, int accumulate) {
+    using G = Geo<P>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tile = reinterpret_cast<float *>(smem_raw);
+    float *wsm = reinterpret_cast<float *>(smem_raw + G::TILE_BYTES);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + G::TILE_BYTES + G::W_BYTES);
+
+    const int tid = threadIdx.x;
+    const int row = tid & (TILE - 1);   // lanes of a warp = 32 consecutive rows
+    const int strip = tid / TILE;
+    const int ty0 = blockIdx.y * TILE, tx0 = blockIdx.x * TILE;  // tile origin in output coords
+    const int zchunk = (nz + zsplit - 1) / zsplit;
+    const int zbeg = blockIdx.z * zchunk;
+    const int zend = min(nz, zbeg + zchunk);
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int oy = ty0 + row;
+    const int ox = tx0 + strip * STRIP;
+    const bool live = oy < ony && ox < opitch;
+    const float *trow = tile + row * G::PITCH + strip * STRIP;
+    uint32_t phase = 0;
+
+    for (int z = zbeg; z < zend; ++z) {
+        if (tid == 0) {
+            mbar_expect_tx(bar, G::TILE_BYTES + G::W_BYTES);
+            tma_load_3d(tile, &in_map, bar, ox0 + tx0 - P / 2, oy0 + ty0 - P / 2, in_z_invariant ? 0 : z);
+            bulk_load(wsm, weights + (size_t)z * P * G::WP, G::W_BYTES, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+
+        float acc[STRIP];
+#pragma unroll
+        for (int i = 0; i < STRIP; ++i) acc[i] = 0.f;
+
+#pragma unroll 1
+        for (int dy = 0; dy < P; ++dy) {
+            float in[G::IN_N];
+            float w[G::WP];
+            const float4 *ip = reinterpret_cast<const float4 *>(trow + dy * G::PITCH);
+            const float4 *wp = reinterpret_cast<const float4 *>(wsm + dy * G::WP);
+#pragma unroll
+            for (int i = 0; i < G::IN_N / 4; ++i) {
+                float4 v = ip[i];
+                in[4 * i] = v.x; in[4 * i + 1] = v.y; in[4 * i + 2] = v.z; in[4 * i + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < G::WP / 4; ++i) {
+                float4 v = wp[i];
+                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+#pragma unroll
+            for (int dx = 0; dx < P; ++dx)
+#pragma unroll
+                for (int i = 0; i < STRIP; ++i) acc[i] = fmaf(w[dx], in[i + dx], acc[i]);
+        }
+
+        if (live) {
+            float *op = out + ((size_t)z * ony + oy) * opitch + ox;
+#pragma unroll
+            for (int i = 0; i < STRIP / 4; ++i) {
+                float4 v = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                float4 *o4 = reinterpret_cast<float4 *>(op) + i;
+                if (accumulate) {
+                    float4 old = *o4;
+                    v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+                }
+                *o4 = v;
+            }
+        }
+        __syncthreads();  // every thread is done with the tile before the next TMA overwrites it
+    }
+}
+}  // namespace k1
+
+// Fallback for FSF sizes without a K1 instantiation: one thread per output.
+__global__ void fsf_correlate_naive_kernel(const float *__restrict__ in, int in_z_invariant, int iny, int inx,
+                                           int ipitch, const float *__restrict__ weights, int P, int WP,
+                                           float *__restrict__ out, int oy0, int ox0, int ony, int onx,
+                                           int opitch, int nz, int accumulate) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, z = blockIdx.z;
+    if (x >= onx) return;
+    const float *w = weights + (size_t)z * P * WP;
+    const float *plane = in + (in_z_invariant ? 0 : (size_t)z * iny * ipitch);
+    const int half = P / 2;
+    float acc = 0.f;
+    for (int dy = 0; dy < P; ++dy) {
+        int yy = oy0 + y + dy - half;
+        if (yy < 0 || yy >= iny) continue;
+        for (int dx = 0; dx < P; ++dx) {
+            int xx = ox0 + x + dx - half;
+            if (xx < 0 || xx >= inx) continue;
+            acc = fmaf(w[dy * WP + dx], plane[(size_t)yy * ipitch + xx], acc);
+        }
+    }
+    float *o = out + ((size_t)z * ony + y) * opitch + x;
+    *o = accumulate ? *o + acc : acc;
+}
+
+// ---------------------------------------------------------------------------
+// K2: spectral correlation with every profile + max / argmax / min.
+//
+// Block = NW warps; the 32 lanes are 32 consecutive x of one image row, warp w
+// owns the ZB consecutive wavelengths starting at (blockIdx.z*NW + w)*ZB.  The
+// block first stages the column window it needs (NW*ZB + longest profile rows
+// of 32 floats, zeros outside [0, nz)) in shared memory; every lane only ever
+// reads its own column, so the rows are bank-conflict free and no further
+// synchronisation is needed.  For each profile a thread then runs the taps in
+// chunks of U=4 over a ring of ZB+2U registers: chunk q multiplies taps
+// 4q..4q+3 (one broadcast LDS.128) into the ZB accumulators while the 4 window
+// values the next chunk needs are loaded into the free ring slots; the chunk
+// loop is unrolled by the ring period so every register index is static.
+// After the last tap the ZB values are normalised (table lookup for a single
+// FSF, per-voxel denominator otherwise) and folded into the running max /
+// first-wins argmax / min (lib_origin.py:1210-1212).
+// ---------------------------------------------------------------------------
+namespace k2 {
+constexpr int U = 4;
+constexpr int NW = 4;
+
+struct ProfDesc {
+    int tap_off;   // float offset of the reversed, zero-padded taps (multiple of 4)
+    int nchunks;   // padded length / U
+    int row_off;   // window row where this profile's taps start, relative to the block window
+    int pad;
+};
+
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_float(float *addr, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+template <int ZB, bool PERVOXEL>
+__global__ void __launch_bounds__(NW * 32, PERVOXEL ? 2 : (ZB > 24 ? 2 : 3))
+spectral_glr_kernel(const float *__restrict__ num_in, const float *__restrict__ den_in,  // [nz][ny][pitch]
+                    int nz, int ny, int nx, int pitch,
+                    const float *__restrict__ taps, const float *__restrict__ taps_sq, int ntaps_total,
+                    const ProfDesc *__restrict__ desc, int nprof, int win_rows, int woff_min,
+                    const float *__restrict__ rs, int nzp, int ncls, int ncx, int cls_ny, int cls_nx, int P,
+                    const uint8_t *__restrict__ mask,
+                    float *__restrict__ correl, float *__restrict__ correl_min, uint8_t *__restrict__ profile,
+                    float *__restrict__ maxmap, float *__restrict__ minmap) {
+    constexpr int RING = ZB + 2 * U;
+    constexpr int PERIOD = RING / U;
+    static_assert(RING % U == 0, "ring must be a multiple of the chunk");
+    extern __shared__ __align__(16) float smem[];
+    float *win = smem;                                   // [win_rows][32]
+    float *win_den = PERVOXEL ? win + win_rows * 32 : nullptr;
+    float *tap_sm = smem + (PERVOXEL ? 2 : 1) * win_rows * 32;
+    float *tap_sq_sm = PERVOXEL ? tap_sm + ntaps_total : nullptr;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + lane, y = blockIdx.y;
+    const int zb0 = blockIdx.z * (NW * ZB);
+    const int z0 = zb0 + warp * ZB;
+    const size_t plane = (size_t)ny * pitch;
+    const size_t col = (size_t)y * pitch + x;  // x < pitch always (pitch is a multiple of 32)
+
+    for (int i = threadIdx.x; i < ntaps_total; i += NW * 32) {
+        tap_sm[i] = taps[i];
+        if (PERVOXEL) tap_sq_sm[i] = taps_sq[i];
+    }
+    for (int r = warp; r < win_rows; r += NW) {
+        int z = zb0 + woff_min + r;
+        bool ok = z >= 0 && z < nz;
+        win[r * 32 + lane] = ok ? __ldg(num_in + (size_t)z * plane + col) : 0.f;
+        if (PERVOXEL) win_den[r * 32 + lane] = ok ? __ldg(den_in + (size_t)z * plane + col) : 0.f;
+    }
+    __syncthreads();
+    if (z0 >= nz) return;
+
+    float mx[ZB], mn[ZB];
+    int arg[ZB];
+#pragma unroll
+    for (int i = 0; i < ZB; ++i) { mx[i] = -INFINITY; mn[i] = INFINITY; arg[i] = 0; }
+
+    const float *rs_col = nullptr;
+    if (!PERVOXEL) {
+        int cls = cls_of(y, cls_ny, P) * ncx + cls_of(min(x, cls_nx - 1), cls_nx, P);
+        rs_col = rs + (size_t)cls * nzp + z0;
+    }
+
+#pragma unroll 1
+    for (int k = 0; k < nprof; ++k) {
+        const ProfDesc d = desc[k];
+        const float *wp = win + (warp * ZB + d.row_off) * 32 + lane;
+        const float4 *tp = reinterpret_cast<const float4 *>(tap_sm + d.tap_off);
+        float ring[RING], acc[ZB];
+#pragma unroll
+        for (int t = 0; t < ZB + U - 1; ++t) ring[t] = wp[t * 32];
+#pragma unroll
+        for (int i = 0; i < ZB; ++i) acc[i] = 0.f;
+#pragma unroll 1
+        for (int qb = 0; qb < d.nchunks; qb += PERIOD) {
+#pragma unroll
+            for (int qq = 0; qq < PERIOD; ++qq) {
+                if (qb + qq < d.nchunks) {
+                    const float4 e = tp[qq];
+#pragma unroll
+                    for (int ii = 0; ii < U; ++ii)
+                        ring[(U * qq + ZB + U - 1 + ii) % RING] = wp[(U * qq + ZB + U - 1 + ii) * 32];
+                    const float ev[U] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+                    for (int ii = 0; ii < U; ++ii)
+#pragma unroll
+                        for (int i = 0; i < ZB; ++i)
+                            acc[i] = fmaf(ev[ii], ring[(U * qq + i + ii) % RING], acc[i]);
+                }
+            }
+            wp += PERIOD * U * 32;
+            tp += PERIOD;
+        }
+
+        if (PERVOXEL) {
+            // per-voxel denominator: same ring walk over the norm window with squared taps
+            const float *dp = win_den + (warp * ZB + d.row_off) * 32 + lane;
+            const float4 *tq = reinterpret_cast<const float4 *>(tap_sq_sm + d.tap_off);
+            float den[ZB];
+#pragma unroll
+            for (int t = 0; t < ZB + U - 1; ++t) ring[t] = dp[t * 32];
+#pragma unroll
+            for (int i = 0; i < ZB; ++i) den[i] = 0.f;
+#pragma unroll 1
+            for (int qb = 0; qb < d.nchunks; qb += PERIOD) {
+#pragma unroll
+                for (int qq = 0; qq < PERIOD; ++qq) {
+                    if (qb + qq < d.nchunks) {
+                        const float4 e = tq[qq];
+#pragma unroll
+                        for (int ii = 0; ii < U; ++ii)
+                            ring[(U * qq + ZB + U - 1 + ii) % RING] = dp[(U * qq + ZB + U - 1 + ii) * 32];
+                        const float ev[U] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+                        for (int ii = 0; ii < U; ++ii)
+#pragma unroll
+                            for (int i = 0; i < ZB; ++i)
+                                den[i] = fmaf(ev[ii], ring[(U * qq + i + ii) % RING], den[i]);
+                    }
+                }
+                dp += PERIOD * U * 32;
+                tq += PERIOD;
+            }
+#pragma unroll
+            for (int i = 0; i < ZB; ++i) acc[i] = den[i] > 0.f ? acc[i] / sqrtf(den[i]) : 0.f;
+        } else {
+            const float4 *rp = reinterpret_cast<const float4 *>(rs_col + (size_t)k * ncls * nzp);
+#pragma unroll
+            for (int i = 0; i < ZB / 4; ++i) {
+                float4 r = __ldg(rp + i);
+                acc[4 * i] *= r.x; acc[4 * i + 1] *= r.y; acc[4 * i + 2] *= r.z; acc[4 * i + 3] *= r.w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < ZB; ++i) {
+            const float t = acc[i];
+            arg[i] = t > mx[i] ? k : arg[i];
+            mx[i] = fmaxf(mx[i], t);
+            mn[i] = fminf(mn[i], t);
+        }
+    }
+
+    if (x >= nx) return;
+    float cmax = -INFINITY, cmin = INFINITY;
+#pragma unroll
+    for (int i = 0; i < ZB; ++i) {
+        const int z = z0 + i;
+        if (z < nz) {
+            const size_t o = ((size_t)z * ny + y) * nx + x;
+            float c = mx[i];
+            int a = arg[i];
+            if (mask && mask[o]) { c = 0.f; a = 0; }
+            if (correl) correl[o] = c;
+            if (correl_min) correl_min[o] = mn[i];
+            if (profile) profile[o] = (uint8_t)a;
+            cmax = fmaxf(cmax, c);
+            cmin = fminf(cmin, mn[i]);
+        }
+    }
+    if (maxmap) atomic_max_float(maxmap + (size_t)y * nx + x, cmax);
+    if (minmap) atomic_min_float(minmap + (size_t)y * nx + x, cmin);
+}
+}  // namespace k2
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+__global__ void fill_f32_kernel(float *p, size_t n, float v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// dst[z][y][dpitch] = src[z][y][nx] * (w ? w[y][x] : 1), zero in the pad columns
+__global__ void pitch_copy_kernel(const float *__restrict__ src, const double *__restrict__ w,
+                                  float *__restrict__ dst, int nz, int ny, int nx, int dpitch, int src_z_invariant) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, z = blockIdx.z;
+    if (x >= dpitch) return;
+    float v = 0.f;
+    if (x < nx) {
+        v = src ? src[((size_t)(src_z_invariant ? 0 : z) * ny + y) * nx + x] : 1.f;
+        if (w) v *= (float)w[(size_t)y * nx + x];
+    }
+    dst[((size_t)z * ny + y) * dpitch + x] = v;
+}
+
+// out[z][y][nx] = in[z][y][pitch]
+__global__ void unpitch_kernel(const float *__restrict__ src, float *__restrict__ dst, int ny, int nx, int pitch) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, z = blockIdx.z;
+    if (x < nx) dst[((size_t)z * ny + y) * nx + x] = src[((size_t)z * ny + y) * pitch + x];
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static int make_tile_map(ogn_ctx *ctx, CUtensorMap *map, const float *base, int nz, int ny, int nx, int pitch,
+                         int box_x, int box_y) {
+    static PFN_encodeTiled encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return ogn_fail(ctx, OGN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)ny * pitch * 4};
+    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ogn_fail(ctx, OGN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return OGN_OK;
+}
+
+// Launch K1 (or the naive fallback) for one field: out (+)= corr(in, weights).
+//   in: device f32 [nz or 1][iny][ipitch], 16-byte aligned, ipitch % 4 == 0
+static int launch_fsf_correlate(ogn_ctx *ctx, const float *in, int in_z_invariant, int nz, int iny, int inx,
+                                int ipitch, const float *weights, int P, int WP, float *out, int ony, int onx,
+                                int opitch, int accumulate) {
+    if (P == 25) {
+        using G = k1::Geo<25>;
+        CUtensorMap map;
+        OGN_TRY(make_tile_map(ctx, &map, in, in_z_invariant ? 1 : nz, iny, inx, ipitch, G::PITCH, G::ROWS));
+        auto kern = k1::fsf_correlate_kernel<25>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            OGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
+            attr_set = true;
+        }
+        const int tx = ogn_div_up(onx, k1::TILE), ty = ogn_div_up(ony, k1::TILE);
+        // one wave of resident blocks (4 per SM); every block walks nz/zsplit planes
+        int zsplit = std::max(1, (ctx->sm_count * 4) / (tx * ty));
+        zsplit = std::min(zsplit, nz);
+        dim3 grid(tx, ty, zsplit);
+        kern<<<grid, k1::THREADS, G::SMEM, ctx->stream>>>(map, in_z_invariant, weights, out, 0, 0, ony, onx, opitch,
+                                                          nz, zsplit, accumulate);
+        OGN_LAUNCH_CHECK("fsf_correlate_kernel");
+    } else {
+        dim3 grid(ogn_div_up(onx, 128), ony, nz);
+        fsf_correlate_naive_kernel<<<grid, 128, 0, ctx->stream>>>(in, in_z_invariant, iny, inx, ipitch, weights, P, WP,
+                                                                 out, 0, 0, ony, onx, opitch, nz, accumulate);
+        OGN_LAUNCH_CHECK("fsf_correlate_naive_kernel");
+    }
+    return OGN_OK;
+}
+
+struct TglrPlan {
+    int nz, ny, nx, pitch, P, WP, nfields, nprof;
+    bool pervoxel;
+    float *w32 = nullptr, *w32sq = nullptr;
+    float *cube_fsf = nullptr, *norm_fsf = nullptr;
+};
+
+// Spatial stage on the device: fills plan.cube_fsf (and plan.norm_fsf when pervoxel).
+static int run_fsf_stage(ogn_ctx *ctx, const float *cube, const double *const *fsf_host,
+                         const double *const *weights_host, TglrPlan &pl, double **normcls_out, int nzp, int ncy,
+                         int ncx) {
+    const int nz = pl.nz, ny = pl.ny, nx = pl.nx, P = pl.P, WP = pl.WP, nf = pl.nfields;
+    const size_t fsf_bytes = (size_t)nz * P * P * sizeof(double);
+    // FSF cubes -> device, pointer table
+    std::vector<const double *> fsf_dev(nf), w_dev(nf, nullptr);
+    for (int f = 0; f < nf; ++f) {
+        char name[32];
+        snprintf(name, sizeof(name), "fsf%d", f);
+        const void *d = nullptr;
+        OGN_TRY(ogn_input(ctx, name, fsf_host[f], fsf_bytes, &d));
+        fsf_dev[f] = static_cast<const double *>(d);
+        if (weights_host) {
+            snprintf(name, sizeof(name), "wmap%d", f);
+            OGN_TRY(ogn_input(ctx, name, weights_host[f], (size_t)ny * nx * sizeof(double), &d));
+            w_dev[f] = static_cast<const double *>(d);
+        }
+    }
+    const double **fsf_tab = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, "fsf_tab", (size_t)nf, &fsf_tab));
+    OGN_CUDA(cudaMemcpyAsync(fsf_tab, fsf_dev.data(), nf * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
+    // the pageable source vector dies at return: make sure the copy has been staged
+    OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+
+    OGN_TRY(ogn_scratch_t(ctx, "w32", (size_t)nf * nz * P * WP, &pl.w32));
+    double *normcls = nullptr;
+    if (pl.pervoxel) {
+        OGN_TRY(ogn_scratch_t(ctx, "w32sq", (size_t)nf * nz * P * WP, &pl.w32sq));
+    } else {
+        OGN_TRY(ogn_scratch_t(ctx, "normcls", (size_t)ncy * ncx * nzp, &normcls));
+        OGN_CUDA(cudaMemsetAsync(normcls, 0, (size_t)ncy * ncx * nzp * sizeof(double), ctx->stream));
+    }
+    {
+        dim3 grid(nz, nf);
+        size_t sm = ((size_t)P * P + 32) * sizeof(double);
+        fsf_prep_kernel<<<grid, 256, sm, ctx->stream>>>(fsf_tab, nz, P, WP, pl.w32, pl.w32sq, normcls, nzp, ny, nx,
+                                                        ncy, ncx);
+        OGN_LAUNCH_CHECK("fsf_prep_kernel");
+    }
+    if (normcls_out) *normcls_out = normcls;
+
+    const size_t vol_p = (size_t)nz * ny * pl.pitch;
+    OGN_TRY(ogn_scratch_t(ctx, "cube_fsf", vol_p, &pl.cube_fsf));
+    if (pl.pervoxel) OGN_TRY(ogn_scratch_t(ctx, "norm_fsf", vol_p, &pl.norm_fsf));
+
+    const bool aligned = (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(cube) & 15) == 0);
+    for (int f = 0; f < nf; ++f) {
+        const float *in = cube;
+        int ipitch = nx;
+        if (w_dev[f] || !aligned) {
+            // weighted data (lib_origin.py:1030) or a TMA-incompatible layout: stage a padded copy
+            ipitch = (int)ogn_round_up(nx, 4);
+            float *tmp = nullptr;
+            OGN_TRY(ogn_scratch_t(ctx, "cube_w", (size_t)nz * ny * ipitch, &tmp));
+            dim3 grid(ogn_div_up(ipitch, 128), ny, nz);
+            pitch_copy_kernel<<<grid, 128, 0, ctx->stream>>>(cube, w_dev[f], tmp, nz, ny, nx, ipitch, 0);
+            OGN_LAUNCH_CHECK("pitch_copy_kernel");
+            in = tmp;
+        }
+        OGN_TRY(launch_fsf_correlate(ctx, in, 0, nz, ny, nx, ipitch, pl.w32 + (size_t)f * nz * P * WP, P, WP,
+                                     pl.cube_fsf, ny, nx, pl.pitch, f > 0));
+        if (pl.pervoxel) {
+            // norm_fsf += corr(w_f or ones, K^2)   (lib_origin.py:1028-1031, 1040-1041)
+            int wpitch = (int)ogn_round_up(nx, 4);
+            float *wplane = nullptr;
+            OGN_TRY(ogn_scratch_t(ctx, "wplane", (size_t)ny * wpitch, &wplane));
+            dim3 grid(ogn_div_up(wpitch, 128), ny, 1);
+            pitch_copy_kernel<<<grid, 128, 0, ctx->stream>>>(nullptr, w_dev[f], wplane, 1, ny, nx, wpitch, 1);
+            OGN_LAUNCH_CHECK("pitch_copy_kernel");
+            OGN_TRY(launch_fsf_correlate(ctx, wplane, 1, nz, ny, nx, wpitch, pl.w32sq + (size_t)f * nz * P * WP, P,
+                                         WP, pl.norm_fsf, ny, nx, pl.pitch, f > 0));
+        }
+    }
+    return OGN_OK;
+}
+
+static int check_dims(ogn_ctx *ctx, int nz, int ny, int nx, int nfields, int psize) {
+    if (!ctx) return OGN_ERR_ARG;
+    if (nz <= 0 || ny <= 0 || nx <= 0) return ogn_fail(ctx, OGN_ERR_ARG, "cube shape (%d,%d,%d) is empty", nz, ny, nx);
+    if (nfields < 1) return ogn_fail(ctx, OGN_ERR_ARG, "nfields must be >= 1");
+    if (psize < 1 || psize % 2 == 0 || psize > 63)
+        return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "FSF size %d: only odd sizes up to 63 are supported", psize);
+    if ((int64_t)ny * nx > (int64_t)INT32_MAX / 4)
+        return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "image of %dx%d spaxels is too large", ny, nx);
+    return OGN_OK;
+}
+
+extern "C" int ogn_fsf_stage(ogn_ctx *ctx, const void *cube, int cube_dtype, int nz, int ny, int nx, int nfields,
+                             const double *const *fsf, int psize, const double *const *weights, float *cube_fsf,
+                             float *norm_fsf) {
+    OGN_TRY(check_dims(ctx, nz, ny, nx, nfields, psize));
+    OGN_CUDA(cudaSetDevice(ctx->device));
+    const size_t vol = (size_t)nz * ny * nx;
+    const float *dcube = nullptr;
+    OGN_TRY(ogn_input_cube_f32(ctx, "cube", cube, cube_dtype, vol, &dcube));
+    TglrPlan pl;
+    pl.nz = nz; pl.ny = ny; pl.nx = nx; pl.pitch = (int)ogn_round_up(nx, 32);
+    pl.P = psize; pl.WP = (psize + 3) / 4 * 4; pl.nfields = nfields; pl.nprof = 0;
+    pl.pervoxel = true;
+    OGN_TRY(run_fsf_stage(ctx, dcube, fsf, weights, pl, nullptr, 0, 0, 0));
+    dim3 grid(ogn_div_up(nx, 128), ny, nz);
+    if (cube_fsf) {
+        void *d = nullptr;
+        OGN_TRY(ogn_output(ctx, "out_cube_fsf", cube_fsf, vol * 4, &d));
+        unpitch_kernel<<<grid, 128, 0, ctx->stream>>>(pl.cube_fsf, (float *)d, ny, nx, pl.pitch);
+        OGN_LAUNCH_CHECK("unpitch_kernel");
+        OGN_TRY(ogn_output_commit(ctx, cube_fsf, d, vol * 4));
+    }
+    if (norm_fsf) {
+        void *d = nullptr;
+        OGN_TRY(ogn_output(ctx, "out_norm_fsf", norm_fsf, vol * 4, &d));
+        unpitch_kernel<<<grid, 128, 0, ctx->stream>>>(pl.norm_fsf, (float *)d, ny, nx, pl.pitch);
+        OGN_LAUNCH_CHECK("unpitch_kernel");
+        OGN_TRY(ogn_output_commit(ctx, norm_fsf, d, vol * 4));
+    }
+    return ogn_finish_call(ctx);
+}
+
+template <int ZB, bool PV>
+static int launch_spectral(ogn_ctx *ctx, const TglrPlan &pl, const float *taps, const float *taps_sq,
+                           int ntaps_total, const k2::ProfDesc *desc, int win_rows, int woff_min, const float *rs,
+                           int nzp, int ncls, int ncx, const uint8_t *mask, float *correl, float *correl_min,
+                           uint8_t *profile, float *maxmap, float *minmap) {
+    auto kern = k2::spectral_glr_kernel<ZB, PV>;
+    const size_t smem = ((size_t)(PV ? 2 : 1) * win_rows * 32 + (size_t)(PV ? 2 : 1) * ntaps_total) * sizeof(float);
+    if (smem > 200 * 1024)
+        return ogn_fail(ctx, OGN_ERR_UNSUPPORTED,
+                        "profile dictionary needs %zu bytes of shared memory per block (limit 200 KiB)", smem);
+    OGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int nzb = ogn_div_up(pl.nz, ZB);
+    dim3 grid(pl.pitch / 32, pl.ny, ogn_div_up(nzb, k2::NW));
+    if (grid.y > 65535 || grid.z > 65535)
+        return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "cube too large for the K2 launch grid");
+    kern<<<grid, k2::NW * 32, smem, ctx->stream>>>(pl.cube_fsf, pl.norm_fsf, pl.nz, pl.ny, pl.nx, pl.pitch, taps,
+                                                   taps_sq, ntaps_total, desc, pl.nprof, win_rows, woff_min, rs, nzp,
+                                                   ncls, ncx, pl.ny, pl.nx, pl.P, mask, correl, correl_min, profile,
+                                                   maxmap, minmap);
+    OGN_LAUNCH_CHECK("spectral_glr_kernel");
+    return OGN_OK;
+}
+
+extern "C" int ogn_tglr(ogn_ctx *ctx, const void *cube, int cube_dtype, int nz, int ny, int nx, int nfields,
+                        const double *const *fsf, int psize, const double *const *weights, const double *taps,
+                        const int *tap_offsets, int nprof, const uint8_t *mask, float *correl, float *correl_min,
+                        uint8_t *profile, float *maxmap, float *minmap) {
+    OGN_TRY(check_dims(ctx, nz, ny, nx, nfields, psize));
+    if (nprof < 1 || nprof > 255)
+        return ogn_fail(ctx, OGN_ERR_ARG, "nprof = %d: the profile index is a uint8 (lib_origin.py:1197), 1..255", nprof);
+    if (!fsf || !taps || !tap_offsets) return ogn_fail(ctx, OGN_ERR_ARG, "fsf / taps / tap_offsets must not be NULL");
+    OGN_CUDA(cudaSetDevice(ctx->device));
+    constexpr int ZB = 32;
+    const size_t vol = (size_t)nz * ny * nx;
+    const size_t img = (size_t)ny * nx;
+
+    TglrPlan pl;
+    pl.nz = nz; pl.ny = ny; pl.nx = nx; pl.pitch = (int)ogn_round_up(nx, 32);
+    pl.P = psize; pl.WP = (psize + 3) / 4 * 4; pl.nfields = nfields; pl.nprof = nprof;
+    pl.pervoxel = weights != nullptr || nfields > 1;
+
+    // ---- profiles: reversed, zero-padded to a multiple of U, float32 ----------------
+    const int ntaps_in = tap_offsets[nprof];
+    std::vector<k2::ProfDesc> desc(nprof);
+    std::vector<float> tp, tpsq;
+    int woff_min = 0, reach = 0;
+    for (int k = 0; k < nprof; ++k) {
+        const int L = tap_offsets[k + 1] - tap_offsets[k];
+        if (L < 1) return ogn_fail(ctx, OGN_ERR_ARG, "profile %d is empty", k);
+        const int ck = (L - 1) / 2;           // 'same' window start, lib_origin.py:1179
+        const int woff = ck - (L - 1);        // first window sample relative to the output index
+        woff_min = std::min(woff_min, woff);
+        const int LP = (int)ogn_round_up(L, k2::U);
+        desc[k].tap_off = (int)tp.size();
+        desc[k].nchunks = LP / k2::U;
+        desc[k].row_off = woff;               // made relative to woff_min below
+        desc[k].pad = 0;
+        for (int i = 0; i < LP; ++i) {
+            double v = i < L ? taps[tap_offsets[k] + (L - 1 - i)] : 0.0;
+            tp.push_back((float)v);
+            tpsq.push_back((float)(v * v));
+        }
+    }
+    for (int k = 0; k < nprof; ++k) {
+        desc[k].row_off -= woff_min;
+        reach = std::max(reach, desc[k].row_off + desc[k].nchunks * k2::U);
+    }
+    const int win_rows = k2::NW * ZB + reach + 2 * k2::U;
+    const int ntaps_total = (int)tp.size();
+
+    float *d_taps = nullptr, *d_taps_sq = nullptr;
+    k2::ProfDesc *d_desc = nullptr;
+    double *d_taps64 = nullptr;
+    int *d_tapoff = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, "taps32", (size_t)ntaps_total, &d_taps));
+    OGN_TRY(ogn_scratch_t(ctx, "taps32sq", (size_t)ntaps_total, &d_taps_sq));
+    OGN_TRY(ogn_scratch_t(ctx, "prof_desc", (size_t)nprof, &d_desc));
+    OGN_TRY(ogn_scratch_t(ctx, "taps64", (size_t)ntaps_in, &d_taps64));
+    OGN_TRY(ogn_scratch_t(ctx, "tap_off", (size_t)nprof + 1, &d_tapoff));
+    OGN_CUDA(cudaMemcpyAsync(d_taps, tp.data(), ntaps_total * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    OGN_CUDA(cudaMemcpyAsync(d_taps_sq, tpsq.data(), ntaps_total * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    OGN_CUDA(cudaMemcpyAsync(d_desc, desc.data(), nprof * sizeof(k2::ProfDesc), cudaMemcpyHostToDevice, ctx->stream));
+    OGN_CUDA(cudaMemcpyAsync(d_taps64, taps, ntaps_in * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    OGN_CUDA(cudaMemcpyAsync(d_tapoff, tap_offsets, (nprof + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    OGN_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors above go out of scope
+
+    // ---- inputs ----------------------------------------------------------------------
+    const float *dcube = nullptr;
+    OGN_TRY(ogn_input_cube_f32(ctx, "cube", cube, cube_dtype, vol, &dcube));
+    const uint8_t *dmask = nullptr;
+    if (mask) {
+        const void *d = nullptr;
+        OGN_TRY(ogn_input(ctx, "mask", mask, vol, &d));
+        dmask = static_cast<const uint8_t *>(d);
+    }
+
+    // ---- K0 + K1 ---------------------------------------------------------------------
+    const int nzp = (int)ogn_round_up(nz, ZB) + ZB;
+    const int ncy = std::min(ny, psize), ncx = std::min(nx, psize);
+    double *normcls = nullptr;
+    OGN_TRY(run_fsf_stage(ctx, dcube, fsf, weights, pl, &normcls, nzp, ncy, ncx));
+
+    float *rs = nullptr;
+    if (!pl.pervoxel) {
+        OGN_TRY(ogn_scratch_t(ctx, "rs", (size_t)nprof * ncy * ncx * nzp, &rs));
+        dim3 grid(ogn_div_up(nzp, 128), ncy * ncx, nprof);
+        den_table_kernel<<<grid, 128, 0, ctx->stream>>>(normcls, nz, nzp, ncy * ncx, d_taps64, d_tapoff, nprof, rs);
+        OGN_LAUNCH_CHECK("den_table_kernel");
+    }
+
+    // ---- K2 ----------------------------------------------------------------------------
+    void *d_correl = nullptr, *d_cmin = nullptr, *d_prof = nullptr, *d_maxmap = nullptr, *d_minmap = nullptr;
+    if (correl) OGN_TRY(ogn_output(ctx, "out_correl", correl, vol * 4, &d_correl));
+    if (correl_min) OGN_TRY(ogn_output(ctx, "out_correl_min", correl_min, vol * 4, &d_cmin));
+    if (profile) OGN_TRY(ogn_output(ctx, "out_profile", profile, vol, &d_prof));
+    if (maxmap) {
+        OGN_TRY(ogn_output(ctx, "out_maxmap", maxmap, img * 4, &d_maxmap));
+        fill_f32_kernel<<<ogn_div_up(img, 256), 256, 0, ctx->stream>>>((float *)d_maxmap, img, -INFINITY);
+        OGN_LAUNCH_CHECK("fill_f32_kernel");
+    }
+    if (minmap) {
+        OGN_TRY(ogn_output(ctx, "out_minmap", minmap, img * 4, &d_minmap));
+        fill_f32_kernel<<<ogn_div_up(img, 256), 256, 0, ctx->stream>>>((float *)d_minmap, img, INFINITY);
+        OGN_LAUNCH_CHECK("fill_f32_kernel");
+    }
+    if (pl.pervoxel)
+        OGN_TRY((launch_spectral<16, true>(ctx, pl, d_taps, d_taps_sq, ntaps_total, d_desc,
+                                            k2::NW * 16 + reach + 2 * k2::U, woff_min, nullptr, nzp, 0, 0, dmask,
+                                            (float *)d_correl, (float *)d_cmin, (uint8_t *)d_prof,
+                                            (float *)d_maxmap, (float *)d_minmap)));
+    else
+        OGN_TRY((launch_spectral<ZB, false>(ctx, pl, d_taps, d_taps_sq, ntaps_total, d_desc, win_rows, woff_min, rs,
+                                             nzp, ncy * ncx, ncx, dmask, (float *)d_correl, (float *)d_cmin,
+                                             (uint8_t *)d_prof, (float *)d_maxmap, (float *)d_minmap)));
+
+    OGN_TRY(ogn_output_commit(ctx, correl, d_correl, vol * 4));
+    OGN_TRY(ogn_output_commit(ctx, correl_min, d_cmin, vol * 4));
+    OGN_TRY(ogn_output_commit(ctx, profile, d_prof, vol));
+    OGN_TRY(ogn_output_commit(ctx, maxmap, d_maxmap, img * 4));
+    OGN_TRY(ogn_output_commit(ctx, minmap, d_minmap, img * 4));
+    return ogn_finish_call(ctx);
+}

@@ -1,0 +1,559 @@
+"""Host-side mirror of the reference's numerical library for the hot path.
+
+Same function names, argument order and error behaviour as
+``muse_origin/lib_origin.py`` for the functions the step layer imports by name
+(``steps.py:19-41``): ``DCTMAT``, ``dct_residual``, ``O2test``,
+``Correlation_GLR_test``, ``compute_local_max``, ``Compute_threshold_purity``.
+All arithmetic runs in ``libogn.so`` (hand-written CUDA for sm_100a); without
+it, or without a B200, every call raises — there is no CPU fallback.
+
+Inputs may be numpy arrays (host) or torch CUDA tensors (device; used in
+place).  Results come back as numpy arrays for numpy inputs and as torch
+tensors on the same device for tensor inputs.  Floating-point cubes are
+float32 (the kernels compute in FP32, the DCT fit in FP64); pass
+``out_dtype=np.float64`` where the reference's float64 container is needed.
+"""
+
+import numpy as np
+
+from . import _lib
+from ._lib import OGN_F32, OGN_F64, OgnError, default_context, ptr
+
+__all__ = ['DCTMAT', 'dct_residual', 'O2test', 'Correlation_GLR_test', 'compute_local_max',
+           'Compute_threshold_purity', 'prepare_profiles', 'tglr', 'local_extrema', 'LocalExtrema',
+           'purity_counts', 'threshold_rows', 'preprocess', 'PurityTable']
+
+
+# --------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------
+
+def _is_torch(x):
+    return _lib._is_torch(x)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _dtype_code(x):
+    if _is_torch(x):
+        torch = _torch()
+        if x.dtype == torch.float32:
+            return OGN_F32
+        if x.dtype == torch.float64:
+            return OGN_F64
+        raise TypeError('cube tensors must be float32 or float64')
+    if x.dtype == np.float32:
+        return OGN_F32
+    if x.dtype == np.float64:
+        return OGN_F64
+    raise TypeError('cube arrays must be float32 or float64')
+
+
+def _as_float_cube(x):
+    """C-contiguous float32/float64 view of a cube (numpy or torch)."""
+    if _is_torch(x):
+        torch = _torch()
+        if x.dtype not in (torch.float32, torch.float64):
+            x = x.to(torch.float32)
+        return x.contiguous()
+    x = np.asarray(x)
+    if x.dtype not in (np.float32, np.float64):
+        x = x.astype(np.float64)
+    return np.ascontiguousarray(x)
+
+
+def _as_u8(x, like=None):
+    if x is None:
+        return None
+    if _is_torch(x):
+        torch = _torch()
+        return (x if x.dtype == torch.uint8 else x.to(torch.uint8)).contiguous()
+    x = np.asarray(x)
+    if x.dtype == np.bool_:
+        return np.ascontiguousarray(x).view(np.uint8)
+    return np.ascontiguousarray(x != 0).view(np.uint8)
+
+
+def _empty_like_kind(ref, shape, dtype):
+    """Uninitialised output living where ``ref`` lives."""
+    if _is_torch(ref) and ref.is_cuda:
+        torch = _torch()
+        tdt = {np.float32: torch.float32, np.float64: torch.float64, np.uint8: torch.uint8,
+               np.int64: torch.int64}[np.dtype(dtype).type]
+        return torch.empty(tuple(shape), dtype=tdt, device=ref.device)
+    return np.empty(shape, dtype=dtype)
+
+
+def _ctx_for(x, ctx):
+    if ctx is not None:
+        return ctx
+    if _is_torch(x) and x.is_cuda:
+        return default_context(x.device.index)
+    return default_context()
+
+
+def _f64_host(x):
+    if _is_torch(x):
+        x = x.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+
+
+class _PtrArray:
+    """ctypes array of raw addresses (``const double *const *``), keeping the
+    referenced arrays alive."""
+
+    def __init__(self, arrays):
+        import ctypes
+        self.keep = list(arrays)
+        self.arr = (ctypes.c_void_p * len(self.keep))(*[a.ctypes.data for a in self.keep])
+
+    @property
+    def address(self):
+        import ctypes
+        return ctypes.addressof(self.arr)
+
+
+# --------------------------------------------------------------------------
+# step01
+# --------------------------------------------------------------------------
+
+def DCTMAT(nl, order):
+    """DCT synthesis matrix, ``nl x (order+1)`` (reference lib_origin.py:127-146).
+    Host numpy: it is a 3681 x 11 table; the kernels rebuild it on their side."""
+    yy, xx = np.mgrid[:nl, :order + 1]
+    d0 = np.sqrt(2 / nl) * np.cos((yy + 0.5) * (np.pi / nl) * xx)
+    d0[:, 0] *= 1 / np.sqrt(2)
+    return d0
+
+
+def dct_residual(w_raw, order, var, approx, mask, out_dtype=np.float64, ctx=None):
+    """Continuum estimated by a (variance-weighted) projection on the first
+    ``order+1`` DCT atoms (reference lib_origin.py:150-240).  Returns the
+    continuum, like the reference."""
+    raw = _as_float_cube(w_raw)
+    if raw.ndim != 3:
+        raise ValueError('w_raw must be a (nz, ny, nx) cube')
+    code = _dtype_code(raw)
+    v = None
+    if var is not None:
+        v = _as_float_cube(var)
+        if _dtype_code(v) != code:
+            v = v.to(raw.dtype) if _is_torch(v) else v.astype(raw.dtype)
+    m = _as_u8(mask)
+    ctx = _ctx_for(raw, ctx)
+    nz, ny, nx = raw.shape
+    cont = _empty_like_kind(raw, raw.shape, out_dtype)
+    ctx.check(ctx.lib.ogn_dct_residual(ctx.handle, ptr(raw), ptr(v), code, ptr(m), nz, ny, nx, int(order),
+                                       int(bool(approx)), ptr(cont), OGN_F64 if np.dtype(out_dtype) == np.float64 else OGN_F32))
+    return cont
+
+
+def O2test(arr):
+    """Second-order test per spaxel, ``mean_z arr^2`` (reference
+    lib_origin.py:957-974).  The fused step01 path (:func:`preprocess`) returns
+    this map as a by-product; this stand-alone form is a 2-D reduction of an
+    array the caller already holds."""
+    if _is_torch(arr):
+        return (arr.double() ** 2).mean(dim=0)
+    return np.mean(np.asarray(arr, dtype=np.float64) ** 2, axis=0)
+
+
+def preprocess(cube_raw, var, mask, dct_order=10, dct_approx=False, allreduce=None, ctx=None):
+    """Array part of ``Preprocessing.run`` (reference steps.py:431-465, :472,
+    :480) in two device phases.  ``allreduce(sum, cnt)`` (optional) combines
+    the per-wavelength partial sums across ranks in place (float64 arrays of
+    length nz) before the mean is taken."""
+    raw = _as_float_cube(cube_raw)
+    code = _dtype_code(raw)
+    v = _as_float_cube(var)
+    if _dtype_code(v) != code:
+        v = v.to(raw.dtype) if _is_torch(v) else v.astype(raw.dtype)
+    m = _as_u8(mask)
+    ctx = _ctx_for(raw, ctx)
+    nz, ny, nx = raw.shape
+    lsum = np.zeros(nz)
+    lcnt = np.zeros(nz)
+    ctx.check(ctx.lib.ogn_preprocess_begin(ctx.handle, ptr(raw), ptr(v), code, ptr(m), nz, ny, nx, int(dct_order),
+                                           int(bool(dct_approx)), ptr(lsum), ptr(lcnt)))
+    if allreduce is not None:
+        allreduce(lsum, lcnt)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        mean = lsum / lcnt                      # NaN for fully masked planes, as np.nanmean
+    out = dict(
+        cube_std=_empty_like_kind(raw, raw.shape, np.float32),
+        cont_dct=_empty_like_kind(raw, raw.shape, np.float32),
+        ima_std=np.empty((ny, nx)), ima_dct=np.empty((ny, nx)),
+        cont_sumsq=np.empty((ny, nx)), o2map=np.empty((ny, nx)),
+    )
+    ctx.check(ctx.lib.ogn_preprocess_finish(ctx.handle, ptr(mean), ptr(out['cube_std']), ptr(out['cont_dct']),
+                                            ptr(out['ima_std']), ptr(out['ima_dct']), ptr(out['cont_sumsq']),
+                                            ptr(out['o2map'])))
+    out['mean_lambda'] = mean
+    return out
+
+
+# --------------------------------------------------------------------------
+# step05
+# --------------------------------------------------------------------------
+
+def prepare_profiles(profiles, pcut=None, pmeansub=True):
+    """Cut at ``pcut``, L2-normalise, subtract the mean (reference
+    lib_origin.py:1155-1165); float64 on the host, K short vectors."""
+    out = []
+    for prof in profiles:
+        prof = np.array(prof, dtype=np.float64).ravel()
+        if pcut is not None:
+            lpeak = int(prof.argmax())
+            sel = np.where(prof >= pcut)[0]
+            lw = int(np.max(np.abs(sel[[0, -1]] - lpeak)))
+            prof = prof[lpeak - lw:lpeak + lw + 1]
+        prof = prof / np.linalg.norm(prof)
+        if pmeansub:
+            prof = prof - prof.mean()
+        out.append(prof)
+    return out
+
+
+def _pack_profiles(prof_cut):
+    offs = np.zeros(len(prof_cut) + 1, dtype=np.int32)
+    offs[1:] = np.cumsum([len(p) for p in prof_cut])
+    return np.ascontiguousarray(np.concatenate(prof_cut)), offs
+
+
+def tglr(cube, fsf, weights, profiles, mask=None, pcut=None, pmeansub=True, want=('correl', 'profile', 'correl_min',
+                                                                                  'maxmap', 'minmap'), ctx=None):
+    """``Correlation_GLR_test`` fused with the masking / maxmap / minmap glue
+    of ``ComputeTGLR.run`` (reference steps.py:781-793).  Returns a dict with
+    the requested products."""
+    cube = _as_float_cube(cube)
+    if cube.ndim != 3:
+        raise ValueError('cube must be (nz, ny, nx)')
+    nz, ny, nx = cube.shape
+    if weights is None:                         # one FSF (lib_origin.py:1112-1114)
+        fsfs, wmaps = [fsf], None
+    else:
+        fsfs, wmaps = list(fsf), list(weights)
+        if len(fsfs) != len(wmaps):
+            raise ValueError('fsf and weights must have the same length')
+    fsfs = [_f64_host(f) for f in fsfs]
+    for f in fsfs:
+        if f.ndim != 3 or f.shape[0] != nz or f.shape[1] != f.shape[2]:
+            raise ValueError('each FSF must be (nz, P, P), got %r' % (f.shape,))
+    psize = fsfs[0].shape[1]
+    fsf_ptrs = _PtrArray(fsfs)
+    w_ptrs = None
+    if wmaps is not None:
+        wmaps = [_f64_host(w) for w in wmaps]
+        for w in wmaps:
+            if w.shape != (ny, nx):
+                raise ValueError('weight maps must be (ny, nx)')
+        w_ptrs = _PtrArray(wmaps)
+    prof_cut = prepare_profiles(profiles, pcut, pmeansub)
+    taps, offs = _pack_profiles(prof_cut)
+    m = _as_u8(mask)
+    ctx = _ctx_for(cube, ctx)
+    out = {}
+    if 'correl' in want:
+        out['correl'] = _empty_like_kind(cube, cube.shape, np.float32)
+    if 'correl_min' in want:
+        out['correl_min'] = _empty_like_kind(cube, cube.shape, np.float32)
+    if 'profile' in want:
+        out['profile'] = _empty_like_kind(cube, cube.shape, np.uint8)
+    if 'maxmap' in want:
+        out['maxmap'] = _empty_like_kind(cube, (ny, nx), np.float32)
+    if 'minmap' in want:
+        out['minmap'] = _empty_like_kind(cube, (ny, nx), np.float32)
+    ctx.check(ctx.lib.ogn_tglr(
+        ctx.handle, ptr(cube), _dtype_code(cube), nz, ny, nx, len(fsfs), fsf_ptrs.address, psize,
+        w_ptrs.address if w_ptrs else None, ptr(taps), ptr(offs), len(prof_cut), ptr(m),
+        ptr(out.get('correl')), ptr(out.get('correl_min')), ptr(out.get('profile')),
+        ptr(out.get('maxmap')), ptr(out.get('minmap'))))
+    return out
+
+
+def Correlation_GLR_test(cube, fsf, weights, profiles, nthreads=1, pcut=None, pmeansub=True, out_dtype=np.float32,
+                         ctx=None):
+    """GLR test cubes for the given FSF(s) and profile dictionary (reference
+    lib_origin.py:1070-1217): returns ``(correl, profile, correl_min)``.
+    ``nthreads`` is accepted for signature compatibility and ignored (the
+    reference only uses it to chunk its FFTs; results do not depend on it)."""
+    res = tglr(cube, fsf, weights, profiles, None, pcut, pmeansub, want=('correl', 'profile', 'correl_min'), ctx=ctx)
+    correl, correl_min = res['correl'], res['correl_min']
+    if np.dtype(out_dtype) == np.float64:
+        correl = correl.double() if _is_torch(correl) else correl.astype(np.float64)
+        correl_min = correl_min.double() if _is_torch(correl_min) else correl_min.astype(np.float64)
+    return correl, res['profile'], correl_min
+
+
+def fsf_stage(cube, fsf, weights, ctx=None):
+    """The two intermediates of the spatial stage (reference ``_convolve_fsf``,
+    lib_origin.py:1027-1043, summed over fields): ``(cube_fsf, norm_fsf)``."""
+    cube = _as_float_cube(cube)
+    nz, ny, nx = cube.shape
+    if weights is None:
+        fsfs, wmaps = [fsf], None
+    else:
+        fsfs, wmaps = list(fsf), list(weights)
+    fsfs = [_f64_host(f) for f in fsfs]
+    fsf_ptrs = _PtrArray(fsfs)
+    w_ptrs = _PtrArray([_f64_host(w) for w in wmaps]) if wmaps is not None else None
+    ctx = _ctx_for(cube, ctx)
+    a = _empty_like_kind(cube, cube.shape, np.float32)
+    b = _empty_like_kind(cube, cube.shape, np.float32)
+    ctx.check(ctx.lib.ogn_fsf_stage(ctx.handle, ptr(cube), _dtype_code(cube), nz, ny, nx, len(fsfs),
+                                    fsf_ptrs.address, fsfs[0].shape[1], w_ptrs.address if w_ptrs else None,
+                                    ptr(a), ptr(b)))
+    return a, b
+
+
+# --------------------------------------------------------------------------
+# local extrema
+# --------------------------------------------------------------------------
+
+class LocalExtrema:
+    """Compact form of the two cubes ``compute_local_max`` returns: the kept
+    voxels as ``(linear index, value)`` lists sorted in C order (the order of
+    ``np.where``), for the maxima of ``correl`` and of ``-correl_min``."""
+
+    def __init__(self, shape, max_index, max_value, min_index, min_value):
+        self.shape = tuple(int(s) for s in shape)
+        self.max_index, self.max_value = max_index, max_value
+        self.min_index, self.min_value = min_index, min_value
+
+    @property
+    def counts(self):
+        return len(self.max_index), len(self.min_index)
+
+    def _host(self, x):
+        return x.detach().cpu().numpy() if _is_torch(x) else x
+
+    def dense(self, which='max', dtype=np.float32):
+        """Materialise ``cube_local_max`` / ``cube_local_min`` on the host."""
+        idx = self._host(self.max_index if which == 'max' else self.min_index)
+        val = self._host(self.max_value if which == 'max' else self.min_value)
+        out = np.zeros(int(np.prod(self.shape)), dtype=dtype)
+        out[idx] = val
+        return out.reshape(self.shape)
+
+    def coords(self, which='max'):
+        idx = self._host(self.max_index if which == 'max' else self.min_index)
+        return np.unravel_index(idx, self.shape)
+
+
+def local_extrema(correl, correl_min, mask, size=3, dense=False, capacity=None, ctx=None):
+    """3-D local maxima of ``correl`` and of ``-correl_min`` outside the mask
+    (reference lib_origin.py:1220-1256).  Returns ``(LocalExtrema, dense_max,
+    dense_min)``; the dense cubes are None unless ``dense``."""
+    if np.isscalar(size):
+        size = (size, size, size)
+    size = tuple(int(s) for s in size)
+    if any(s < 1 or s % 2 == 0 for s in size):
+        raise ValueError('only odd window sizes are supported, got %r' % (size,))
+    a = _as_float_cube(correl)
+    if _dtype_code(a) != OGN_F32:
+        a = a.float() if _is_torch(a) else a.astype(np.float32)
+    if correl_min is correl:
+        b = a
+    else:
+        b = _as_float_cube(correl_min)
+        if _dtype_code(b) != OGN_F32:
+            b = b.float() if _is_torch(b) else b.astype(np.float32)
+    if a.shape != b.shape or a.ndim != 3:
+        raise ValueError('correl and correl_min must be cubes of the same shape')
+    m = _as_u8(mask)
+    ctx = _ctx_for(a, ctx)
+    nz, ny, nx = a.shape
+    vol = nz * ny * nx
+    dmax = _empty_like_kind(a, a.shape, np.float32) if dense else None
+    dmin = _empty_like_kind(a, a.shape, np.float32) if dense else None
+    if capacity is None:
+        capacity = max(4096, vol // 40)
+    counts = np.zeros(2, dtype=np.int64)
+    while True:
+        mi = _empty_like_kind(a, (capacity,), np.int64)
+        mv = _empty_like_kind(a, (capacity,), np.float32)
+        ni = _empty_like_kind(a, (capacity,), np.int64)
+        nv = _empty_like_kind(a, (capacity,), np.float32)
+        rc = ctx.check(ctx.lib.ogn_local_extrema(ctx.handle, ptr(a), ptr(b), ptr(m), nz, ny, nx, size[0], size[1],
+                                                 size[2], ptr(dmax), ptr(dmin), ptr(mi), ptr(mv), ptr(ni), ptr(nv),
+                                                 capacity, ptr(counts)), allow_overflow=True)
+        if rc == 0:
+            break
+        capacity = int(counts.max())
+    n1, n0 = int(counts[0]), int(counts[1])
+    ext = LocalExtrema(a.shape, mi[:n1], mv[:n1], ni[:n0], nv[:n0])
+    return ext, dmax, dmin
+
+
+def compute_local_max(correl, correl_min, mask, size=3, ctx=None):
+    """Drop-in for the reference's ``compute_local_max`` (lib_origin.py:1220-1256):
+    returns the dense ``(local_max, local_min)`` cubes (float32)."""
+    _, dmax, dmin = local_extrema(correl, correl_min, mask, size, dense=True, ctx=ctx)
+    return dmax, dmin
+
+
+# --------------------------------------------------------------------------
+# step06 / step07
+# --------------------------------------------------------------------------
+
+class PurityTable(dict):
+    """Columns ``Tval_r, Pval_r, Det_m, Det_M`` of the purity table (the
+    reference returns an astropy Table, lib_origin.py:1454-1460; astropy is not
+    a dependency of the hot path, :meth:`to_astropy` converts when present)."""
+
+    colnames = ('Tval_r', 'Pval_r', 'Det_m', 'Det_M')
+
+    def to_astropy(self):
+        from astropy.table import Table
+        tab = Table([self[c] for c in self.colnames], names=self.colnames)
+        tab['Tval_r'].format = '.2f'
+        tab['Pval_r'].format = '.2f'
+        return tab
+
+    def __len__(self):
+        return len(self['Tval_r'])
+
+
+def _lists_from_dense(cube):
+    flat = np.asarray(cube).reshape(-1)
+    idx = np.flatnonzero(flat)
+    return idx.astype(np.int64), flat[idx].astype(np.float32)
+
+
+def _as_extrema(cube_local_max, cube_local_min):
+    if isinstance(cube_local_max, LocalExtrema):
+        return cube_local_max
+    if _is_torch(cube_local_max):
+        cube_local_max = cube_local_max.detach().cpu().numpy()
+        cube_local_min = cube_local_min.detach().cpu().numpy()
+    mi, mv = _lists_from_dense(cube_local_max)
+    ni, nv = _lists_from_dense(cube_local_min)
+    return LocalExtrema(np.shape(cube_local_max), mi, mv, ni, nv)
+
+
+def purity_stats(ext, segmask, ctx=None):
+    """``(max of maxima, max of background minima, per-spaxel max map)``
+    from the compact lists (reference lib_origin.py:1437-1438 inputs)."""
+    ctx = _ctx_for(ext.max_value, ctx)
+    nz, ny, nx = ext.shape
+    stats = np.zeros(2)
+    spmax = np.empty((ny, nx), dtype=np.float32)
+    seg = _as_u8(segmask)
+    n1, n0 = ext.counts
+    ctx.check(ctx.lib.ogn_purity_stats(ctx.handle, ptr(ext.max_index), ptr(ext.max_value), n1, ptr(ext.min_index),
+                                       ptr(ext.min_value), n0, ptr(seg), ny, nx, ptr(stats), ptr(spmax)))
+    return float(stats[0]), float(stats[1]), spmax
+
+
+def purity_counts(ext, segmask, thresholds, ctx=None):
+    """``n1[t] = #{maxima > t}``, ``n0[t] = #{background minima > t}`` (int64;
+    the loop at reference lib_origin.py:1443-1449)."""
+    ctx = _ctx_for(ext.max_value, ctx)
+    nz, ny, nx = ext.shape
+    thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+    n1 = np.zeros(len(thr), dtype=np.int64)
+    n0 = np.zeros(len(thr), dtype=np.int64)
+    seg = _as_u8(segmask)
+    c1, c0 = ext.counts
+    ctx.check(ctx.lib.ogn_purity_counts(ctx.handle, ptr(ext.max_index), ptr(ext.max_value), c1, ptr(ext.min_index),
+                                        ptr(ext.min_value), c0, ptr(seg), ny, nx, ptr(thr), len(thr), ptr(n1),
+                                        ptr(n0)))
+    return n1, n0
+
+
+def Compute_threshold_purity(purity, cube_local_max, cube_local_min, segmap=None, threshlist=None, allreduce=None,
+                             ctx=None):
+    """Threshold for a target purity (reference lib_origin.py:1391-1479).
+
+    ``cube_local_max`` may be the dense cube, as in the reference, or a
+    :class:`LocalExtrema` (then ``cube_local_min`` is ignored).  Returns
+    ``(threshold, table)``.  ``allreduce`` (multi-GPU) is an object with
+    ``max(scalars) -> scalars``, ``max_image(img)`` and ``sum(int64 array)``
+    that combines tile-local statistics across ranks; the spatial size used for
+    L1/L0 is then the global one it reports via ``allreduce.sum``.
+    """
+    ext = _as_extrema(cube_local_max, cube_local_min)
+    nz, ny, nx = ext.shape
+    vol = nz * ny * nx
+    l1 = ny * nx                                           # lib_origin.py:1424
+    segmask = None
+    if segmap is not None:
+        segmap = segmap.detach().cpu().numpy() if _is_torch(segmap) else np.asarray(segmap)
+        segmask = segmap != 0                              # complement of :1428
+        l0 = int(np.count_nonzero(~segmask))
+    else:
+        l0 = l1
+    if allreduce is not None:
+        l1, l0 = (int(v) for v in allreduce.sum(np.array([l1, l0], dtype=np.int64)))
+    n_max, n_min = ext.counts
+    if threshlist is None:
+        mx_max, mx_min, spmax = purity_stats(ext, segmask, ctx)
+        # the dense cubes hold 0 wherever a voxel is not an extremum (:1247, :1254)
+        if n_max < vol:
+            mx_max = max(mx_max, 0.0)
+        if n_min < vol or segmask is not None:
+            mx_min = max(mx_min, 0.0)
+        if allreduce is not None:
+            mx_max, mx_min = allreduce.max([mx_max, mx_min])
+            spmax = allreduce.gather_image(spmax)
+        threshmax = min(mx_min, mx_max)                    # :1437
+        threshmin = float(np.median(spmax.astype(np.float64))) * 1.1   # :1438
+        threshlist = np.linspace(threshmin, threshmax, 50)  # :1439
+    else:
+        threshlist = np.asarray(threshlist, dtype=np.float64)
+    n1, n0 = purity_counts(ext, segmask, threshlist, ctx)
+    # zeros of the dense cubes count for negative thresholds
+    neg = threshlist < 0
+    if neg.any():
+        n1 = n1 + neg * (vol - n_max)
+        n0 = n0 + neg * (vol - n_min)
+    if allreduce is not None:
+        n1 = allreduce.sum(n1)
+        n0 = allreduce.sum(n0)
+    n0 = n0 * (l1 / l0)                                    # :1451
+    with np.errstate(divide='ignore', invalid='ignore'):
+        est_purity = 1 - n0 / n1                           # :1453
+    order = np.argsort(threshlist, kind='stable')          # res.sort('Tval_r'), :1460
+    table = PurityTable(Tval_r=np.asarray(threshlist, dtype=np.float64)[order], Pval_r=est_purity[order],
+                        Det_m=n0.astype(int)[order], Det_M=n1[order])
+    if est_purity[-1] < purity:                            # :1463
+        threshold = np.inf
+    else:
+        threshold = np.interp(purity, table['Pval_r'], table['Tval_r'])   # :1469
+    return float(threshold), table
+
+
+def threshold_rows(ext, threshold, profile=None, which='max', ctx=None):
+    """Rows of the raw detection catalogue (reference steps.py:956-964 for
+    ``which='max'``, :966-974 on the std cube, :935-939 for ``'min'``): entries
+    above ``threshold`` in C order -> dict ``x0, y0, z0, value[, profile]``."""
+    idx = ext.max_index if which == 'max' else ext.min_index
+    val = ext.max_value if which == 'max' else ext.min_value
+    n = len(idx)
+    ctx = _ctx_for(val, ctx)
+    dev_profile = profile if (profile is not None and _is_torch(profile) and profile.is_cuda) else None
+    cap = max(1024, n // 64)
+    count = np.zeros(1, dtype=np.int64)
+    while True:
+        oi = np.empty(cap, dtype=np.int64)
+        ov = np.empty(cap, dtype=np.float32)
+        op = np.empty(cap, dtype=np.uint8) if dev_profile is not None else None
+        rc = ctx.check(ctx.lib.ogn_threshold_extract(ctx.handle, ptr(idx), ptr(val), n, float(threshold),
+                                                     ptr(dev_profile), ptr(oi), ptr(ov), ptr(op), cap, ptr(count)),
+                       allow_overflow=True)
+        if rc == 0:
+            break
+        cap = int(count[0])
+    m = int(count[0])
+    oi, ov = oi[:m], ov[:m]
+    z, y, x = np.unravel_index(oi, ext.shape)
+    rows = dict(x0=x, y0=y, z0=z, value=ov)
+    if profile is not None:
+        if dev_profile is not None:
+            rows['profile'] = op[:m]
+        else:
+            rows['profile'] = np.asarray(profile)[z, y, x]
+    return rows

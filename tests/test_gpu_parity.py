@@ -1,0 +1,375 @@
+"""Parity of the CUDA path (through the C ABI / host mirror) against the
+reference-generated golden fixtures and the float64 oracle.
+
+Tolerances (BASELINE.json north_star): ``correl`` and
+``correl_min`` within ``1e-5 * max(|ref|, rms(ref))``; argmax profile, extremum
+lists and catalogue rows identical except where competing values differ by
+less than that tolerance (the number of such ties is asserted to be small and
+each one is verified to be a genuine near-tie); integer / index work bit-exact.
+"""
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, tol_report, unpack_mask
+from oracle import origin_oracle as orc
+from origin_b200 import dictionaries, synthetic
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def lo():
+    from origin_b200 import lib_origin
+    return lib_origin
+
+
+def assert_close(got, ref, what, rtol=RTOL):
+    rep = tol_report(got, ref, rtol)
+    assert rep['ok'], '%s: max_abs=%.3g worst=%.3g x bound (rms %.3g)' % (what, rep['max_abs'], rep['worst'], rep['rms'])
+    return rep
+
+
+def check_profile(got, ref_profile, tk, what, max_frac=1e-3):
+    """argmax must match except at genuine near-ties of the reference's T_k."""
+    mism = np.argwhere(got != ref_profile)
+    if len(mism) == 0:
+        return 0
+    rms = float(np.sqrt(np.mean(tk.max(axis=0) ** 2)))
+    for idx in mism:
+        col = tk[(slice(None),) + tuple(idx)]
+        top = np.sort(col)[::-1]
+        gap = top[0] - col[got[tuple(idx)]]
+        assert gap <= RTOL * max(abs(top[0]), rms), '%s: profile mismatch at %s is not a tie (gap %.3g)' % (what, idx, gap)
+    assert len(mism) <= max(2, max_frac * got.size), '%s: %d argmax ties' % (what, len(mism))
+    return len(mism)
+
+
+def oracle_tk(cube, fsf, weights, profiles, pcut, pmeansub):
+    cf, nf = orc.fsf_correlate(cube, fsf, weights)
+    prof = orc.prepare_profiles(profiles, pcut, pmeansub)
+    return orc.spectral_glr_direct(cf, nf, prof)[3]
+
+
+# --------------------------------------------------------------------------
+# step05
+# --------------------------------------------------------------------------
+
+def test_fsf_stage_matches_oracle(lo):
+    g = load_golden('tglr_single')
+    cf, nf = lo.fsf_stage(g['cube'], g['fsf'], None)
+    rcf, rnf = orc.fsf_correlate_direct(g['cube'], g['fsf'])
+    assert_close(cf, rcf, 'cube_fsf')
+    assert_close(nf, rnf, 'norm_fsf', rtol=2e-6)
+
+
+def test_tglr_single_field_golden(lo):
+    g = load_golden('tglr_single')
+    mask = unpack_mask(g['mask'], g['shape'])
+    profs = dictionaries.dico_3fwhm()[0]
+    correl, profile, correl_min = lo.Correlation_GLR_test(g['cube'], g['fsf'], None, profs, pcut=1e-8)
+    assert correl.dtype == np.float32 and profile.dtype == np.uint8
+    assert_close(correl, g['correl_unmasked'], 'correl')
+    assert_close(correl_min, g['cube_correl_min'], 'correl_min')
+    tk = oracle_tk(g['cube'], g['fsf'], None, profs, 1e-8, True)
+    check_profile(profile, g['profile_unmasked'], tk, 'profile')
+    # fused step glue: mask, maxmap, minmap (steps.py:781-793)
+    out = lo.tglr(g['cube'], g['fsf'], None, profs, mask=mask, pcut=1e-8)
+    assert_close(out['correl'], g['cube_correl'], 'masked correl')
+    assert np.all(out['correl'][mask] == 0) and np.all(out['profile'][mask] == 0)
+    assert_close(out['correl_min'], g['cube_correl_min'], 'correl_min (unmasked by design)')
+    assert_close(out['maxmap'], g['maxmap'], 'maxmap')
+    assert_close(out['minmap'], g['minmap'], 'minmap')
+    np.testing.assert_array_equal(out['maxmap'], out['correl'].max(axis=0))
+    np.testing.assert_array_equal(out['minmap'], out['correl_min'].min(axis=0))
+
+
+@pytest.mark.parametrize('name,pcut,pmeansub,full', [
+    ('tglr_2_12', 1e-8, True, True), ('tglr_nocut', None, False, False),
+    ('tglr_tiny', 1e-8, True, False)])
+def test_tglr_variants_golden(lo, name, pcut, pmeansub, full):
+    g = load_golden(name)
+    profs = dictionaries.dico_fwhm_2_12()[0] if full else dictionaries.dico_3fwhm()[0]
+    correl, profile, correl_min = lo.Correlation_GLR_test(g['cube'], g['fsf'], None, profs, pcut=pcut,
+                                                          pmeansub=pmeansub)
+    assert_close(correl, g['correl'], name + ' correl')
+    assert_close(correl_min, g['correl_min'], name + ' correl_min')
+    tk = oracle_tk(g['cube'], g['fsf'], None, profs, pcut, pmeansub)
+    check_profile(profile, g['profile'], tk, name + ' profile', max_frac=3e-3)
+
+
+def test_tglr_multifield_golden(lo):
+    g = load_golden('tglr_multifield')
+    profs = dictionaries.dico_3fwhm()[0]
+    fsf, w = [g['fsf0'], g['fsf1']], [g['w0'], g['w1']]
+    correl, profile, correl_min = lo.Correlation_GLR_test(g['cube'], fsf, w, profs, pcut=1e-8)
+    # SURVEY.md note N1: where no field covers the footprint the reference holds FFT round-off;
+    # compare where the 25x25 footprint sees data (x >= 6 + 12)
+    sel = np.zeros(g['cube'].shape[1:], dtype=bool)
+    sel[:, 18:] = True
+    assert_close(correl[:, sel], g['correl'][:, sel], 'multifield correl')
+    assert_close(correl_min[:, sel], g['correl_min'][:, sel], 'multifield correl_min')
+    tk = oracle_tk(g['cube'], fsf, w, profs, 1e-8, True)
+    check_profile(profile[:, sel], g['profile'][:, sel], tk[:, :, sel], 'multifield profile')
+
+
+def test_tglr_float64_input_and_odd_width(lo):
+    # nx not a multiple of 4 (TMA needs a padded copy) and a float64 cube (reference dtype)
+    shape = (50, 31, 37)
+    fsf = synthetic.moffat_fsf(shape[0])
+    cube, _ = synthetic.faint_cube(shape, fsf, n_src=3, seed=11)
+    profs = dictionaries.dico_3fwhm()[0]
+    ref = orc.correlation_glr_test(cube, fsf, None, profs, pcut=1e-8)
+    for arr in (cube, cube.astype(np.float64)):
+        correl, profile, correl_min = lo.Correlation_GLR_test(arr, fsf, None, profs, pcut=1e-8)
+        assert_close(correl, ref[0], 'correl')
+        assert_close(correl_min, ref[2], 'correl_min')
+        assert np.mean(profile == ref[1]) > 0.999
+
+
+def test_tglr_small_fsf_fallback(lo):
+    # FSF size without a TMA-tiled instantiation (9x9) goes through the generic kernel
+    shape = (40, 20, 24)
+    fsf = synthetic.moffat_fsf(shape[0], size=9)
+    cube, _ = synthetic.faint_cube(shape, fsf, n_src=2, seed=12)
+    profs = dictionaries.dico_3fwhm()[0]
+    ref = orc.correlation_glr_test(cube, fsf, None, profs, pcut=1e-8)
+    correl, profile, correl_min = lo.Correlation_GLR_test(cube, fsf, None, profs, pcut=1e-8)
+    assert_close(correl, ref[0], 'correl')
+    assert_close(correl_min, ref[2], 'correl_min')
+
+
+def test_tglr_device_tensors(lo):
+    import torch
+    g = load_golden('tglr_single')
+    profs = dictionaries.dico_3fwhm()[0]
+    cube = torch.from_numpy(g['cube']).cuda()
+    out = lo.tglr(cube, g['fsf'], None, profs, pcut=1e-8)
+    torch.cuda.synchronize()
+    assert out['correl'].is_cuda
+    assert_close(out['correl'].cpu().numpy(), g['correl_unmasked'], 'device correl')
+
+
+def test_tglr_errors(lo):
+    from origin_b200._lib import OgnError
+    profs = dictionaries.dico_3fwhm()[0]
+    cube = np.zeros((8, 6, 6), np.float32)
+    with pytest.raises(ValueError):
+        lo.Correlation_GLR_test(cube, np.zeros((7, 5, 5)), None, profs)          # wrong nz
+    with pytest.raises(OgnError):
+        lo.Correlation_GLR_test(cube, np.zeros((8, 4, 4)), None, profs)          # even FSF
+    with pytest.raises(OgnError):
+        lo.Correlation_GLR_test(cube, np.ones((8, 5, 5)), None, profs * 100)     # > 255 profiles
+
+
+# --------------------------------------------------------------------------
+# local extrema, purity, thresholding
+# --------------------------------------------------------------------------
+
+def test_local_extrema_bit_exact_on_reference_inputs(lo):
+    g = load_golden('tglr_single')
+    mask = unpack_mask(g['mask'], g['shape'])
+    a = g['cube_correl'].astype(np.float32)
+    b = g['cube_correl_min'].astype(np.float32)
+    rmax, rmin = orc.compute_local_max(a, b, mask, 3)
+    dmax, dmin = lo.compute_local_max(a, b, mask, 3)
+    np.testing.assert_array_equal(dmax, rmax.astype(np.float32))
+    np.testing.assert_array_equal(dmin, rmin.astype(np.float32))
+    ext, _, _ = lo.local_extrema(a, b, mask, 3)
+    np.testing.assert_array_equal(ext.max_index, np.flatnonzero(rmax))
+    np.testing.assert_array_equal(ext.min_index, np.flatnonzero(rmin))
+    assert np.all(np.diff(ext.max_index) > 0) and np.all(np.diff(ext.min_index) > 0)
+    np.testing.assert_array_equal(ext.dense('max'), dmax)
+    np.testing.assert_array_equal(ext.dense('min'), dmin)
+    # overflow path: tiny capacity is grown transparently
+    ext2, _, _ = lo.local_extrema(a, b, mask, 3, capacity=8)
+    np.testing.assert_array_equal(ext2.max_index, ext.max_index)
+    np.testing.assert_array_equal(ext2.min_value, ext.min_value)
+
+
+@pytest.mark.parametrize('size', [(1, 3, 3), 5, (3, 1, 5)])
+def test_local_extrema_other_windows(lo, size):
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((20, 17, 45)).astype(np.float32)
+    b = rng.standard_normal((20, 17, 45)).astype(np.float32)
+    a[3:6, 2:5, 10:20] = 1.5                                   # plateau: every tied voxel is kept
+    mask = rng.random(a.shape) < 0.05
+    rmax, rmin = orc.compute_local_max(a, b, mask, size)
+    dmax, dmin = lo.compute_local_max(a, b, mask, size)
+    np.testing.assert_array_equal(dmax, rmax.astype(np.float32))
+    np.testing.assert_array_equal(dmin, rmin.astype(np.float32))
+
+
+def test_local_extrema_same_array_and_ragged_width(lo):
+    rng = np.random.default_rng(6)
+    a = rng.standard_normal((9, 5, 33)).astype(np.float32)    # nx = 33: two ballot words per row
+    mask = np.zeros(a.shape, bool)
+    rmax, rmin = orc.compute_local_max(a, a, mask, 3)
+    dmax, dmin = lo.compute_local_max(a, a, mask, 3)
+    np.testing.assert_array_equal(dmax, rmax.astype(np.float32))
+    np.testing.assert_array_equal(dmin, rmin.astype(np.float32))
+
+
+def test_purity_threshold_golden(lo):
+    g = load_golden('purity')
+    t = load_golden('tglr_single')
+    lmax, lmin = t['cube_local_max'], t['cube_local_min']
+    for tag, purity, seg, tl in (('a', 0.8, g['segmap'], None), ('b', 0.9, None, None),
+                                 ('c', 0.5, g['segmap'], g['threshlist_c'])):
+        thr, tab = lo.Compute_threshold_purity(purity, lmax, lmin, seg, tl)
+        # the lists are float32-rounded values of the float64 cubes: thresholds agree to 1e-6
+        np.testing.assert_allclose(tab['Tval_r'], g[tag + '_Tval_r'], rtol=2e-6)
+        dm = np.abs(tab['Det_M'] - g[tag + '_Det_M'])
+        dn = np.abs(tab['Det_m'] - g[tag + '_Det_m'])
+        assert dm.max() <= 1 and dn.max() <= 1, (tag, dm.max(), dn.max())
+        ref_thr = float(g['thr_' + tag])
+        if np.isfinite(ref_thr):
+            assert abs(thr - ref_thr) <= 2e-3 * abs(ref_thr), (tag, thr, ref_thr)
+        else:
+            assert np.isinf(thr)
+
+
+def test_purity_counts_exact(lo):
+    rng = np.random.default_rng(7)
+    shape = (30, 12, 14)
+    lmax = np.where(rng.random(shape) < 0.02, rng.gamma(2.0, 2.0, shape), 0).astype(np.float32)
+    lmin = np.where(rng.random(shape) < 0.02, rng.gamma(2.0, 1.5, shape), 0).astype(np.float32)
+    seg = (rng.random(shape[1:]) < 0.3).astype(np.int16) * 4
+    thr, tab = lo.Compute_threshold_purity(0.7, lmax, lmin, seg)
+    rthr, rtab = orc.threshold_purity(0.7, lmax, lmin, seg)
+    np.testing.assert_allclose(tab['Tval_r'], rtab['Tval_r'], rtol=1e-12)
+    np.testing.assert_array_equal(tab['Det_M'], rtab['Det_M'])
+    np.testing.assert_array_equal(tab['Det_m'], rtab['Det_m'])
+    assert thr == pytest.approx(rthr, rel=1e-12) or (np.isinf(thr) and np.isinf(rthr))
+    # explicit list with negative thresholds (zeros of the dense cube count)
+    tl = np.array([-1.0, 0.5, 3.0])
+    thr, tab = lo.Compute_threshold_purity(0.1, lmax, lmin, None, tl)
+    rthr, rtab = orc.threshold_purity(0.1, lmax, lmin, None, tl)
+    np.testing.assert_array_equal(tab['Det_M'], rtab['Det_M'])
+    np.testing.assert_array_equal(tab['Det_m'], rtab['Det_m'])
+
+
+def test_threshold_rows_order_and_values(lo):
+    rng = np.random.default_rng(8)
+    shape = (25, 11, 40)
+    a = rng.standard_normal(shape).astype(np.float32)
+    prof = rng.integers(0, 3, shape).astype(np.uint8)
+    mask = np.zeros(shape, bool)
+    ext, dmax, _ = lo.local_extrema(a, a, mask, 3, dense=True)
+    rows = lo.threshold_rows(ext, 1.2, prof)
+    ref = orc.detection_rows(dmax, prof, 1.2)
+    for k in ('x0', 'y0', 'z0', 'profile'):
+        np.testing.assert_array_equal(rows[k], ref[k])
+    np.testing.assert_array_equal(rows['value'], ref['value'])
+    rows = lo.threshold_rows(ext, 1e9, prof)
+    assert len(rows['x0']) == 0
+
+
+# --------------------------------------------------------------------------
+# step01
+# --------------------------------------------------------------------------
+
+def test_dct_residual_golden(lo):
+    g = load_golden('dct')
+    mask = unpack_mask(g['mask'], g['shape'])
+    scale = np.abs(g['cont_weighted']).max()
+    for key, order, approx in (('cont_weighted', 10, False), ('cont_approx', 10, True), ('cont_order4', 4, False)):
+        cont = lo.dct_residual(g['raw'], order, g['var'], approx, mask)
+        assert cont.dtype == np.float64
+        assert np.abs(cont - g[key]).max() <= 1e-9 * scale, key
+
+
+def test_preprocess_golden(lo):
+    g = load_golden('dct')
+    mask = unpack_mask(g['mask'], g['shape'])
+    out = lo.preprocess(g['raw'], g['var'], mask, 10, False)
+    assert_close(out['cube_std'], g['cube_std'], 'cube_std')
+    assert_close(out['cont_dct'], g['cont_dct'], 'cont_dct')
+    for key in ('ima_std', 'ima_dct', 'cont_sumsq', 'o2map'):
+        assert_close(out[key], g[key], key)
+    ext, _, _ = lo.local_extrema(out['cube_std'], out['cube_std'], mask, 3)
+    ref_idx = np.flatnonzero(g['cube_std_local_max'])
+    only = np.setxor1d(ext.max_index, ref_idx)
+    assert len(only) <= 2, 'std local maxima differ at %d voxels' % len(only)
+
+
+# --------------------------------------------------------------------------
+# chain: step01 -> step05 -> step06 -> step07 on one cube, vs the reference
+# --------------------------------------------------------------------------
+
+def test_chain_catalogue_matches_reference(lo):
+    g = load_golden('chain')
+    shape = tuple(int(s) for s in g['shape'])
+    mask = unpack_mask(g['mask'], shape)
+    profs = dictionaries.dico_3fwhm()[0]
+    s1 = lo.preprocess(g['raw'], g['var'], mask, 10, False)
+    assert_close(s1['cube_std'][100], g['cube_std_plane'], 'cube_std plane', rtol=2e-5)
+    out = lo.tglr(s1['cube_std'], g['fsf'], None, profs, mask=mask, pcut=1e-8)
+    assert_close(out['correl'][100], g['correl_plane'], 'correl plane', rtol=2e-5)
+    assert_close(out['maxmap'], g['maxmap'], 'maxmap', rtol=2e-5)
+    ext, _, _ = lo.local_extrema(out['correl'], out['correl_min'], mask, 3)
+    n1, n0 = ext.counts
+    assert abs(n1 - int(g['n_local_max'])) <= 3 and abs(n0 - int(g['n_local_min'])) <= 3
+    thr, tab = lo.Compute_threshold_purity(0.8, ext, None, g['segmap'])
+    np.testing.assert_allclose(tab['Tval_r'], g['tab_Tval_r'], rtol=1e-4)
+    assert np.abs(tab['Det_M'] - g['tab_Det_M']).max() <= 1
+    rows = lo.threshold_rows(ext, float(g['use_thr']), out['profile'])
+    np.testing.assert_array_equal(rows['z0'], g['cat_z'])
+    np.testing.assert_array_equal(rows['y0'], g['cat_y'])
+    np.testing.assert_array_equal(rows['x0'], g['cat_x'])
+    np.testing.assert_array_equal(rows['profile'], g['cat_profile'])
+    np.testing.assert_allclose(rows['value'], g['cat_tglr'], rtol=1e-4)
+    ext_std, _, _ = lo.local_extrema(s1['cube_std'], s1['cube_std'], mask, 3)
+    rows = lo.threshold_rows(ext_std, float(g['use_std']))
+    np.testing.assert_array_equal(rows['z0'], g['std_z'])
+    np.testing.assert_array_equal(rows['x0'], g['std_x'])
+
+
+# --------------------------------------------------------------------------
+# larger cubes
+# --------------------------------------------------------------------------
+
+def test_tglr_full_lambda_axis_vs_oracle(lo):
+    # the BASELINE wavelength axis on a small field; the oracle needs ~10 s
+    shape = (3681, 40, 48)
+    fsf = synthetic.moffat_fsf(shape[0])
+    cube, cat = synthetic.faint_cube(shape, fsf, n_src=8, seed=21)
+    profs = dictionaries.dico_3fwhm()[0]
+    ref = orc.correlation_glr_test(cube, fsf, None, profs, nthreads=4, pcut=1e-8)
+    correl, profile, correl_min = lo.Correlation_GLR_test(cube, fsf, None, profs, pcut=1e-8)
+    assert_close(correl, ref[0], 'correl')
+    assert_close(correl_min, ref[2], 'correl_min')
+    ties = int(np.count_nonzero(profile != ref[1]))
+    assert ties <= 1e-4 * profile.size, ties
+    # injected emitters are recovered as the global maxima of their neighbourhood
+    z, y, x = (int(v) for v in cat[np.argmax(cat[:, 4])][:3])
+    zz = slice(max(0, z - 3), z + 4)
+    assert correl[zz, max(0, y - 2):y + 3, max(0, x - 2):x + 3].max() > 8
+
+
+def test_tglr_tile_consistency_and_spot_oracle(lo):
+    """Size-independent properties on a bigger field: (1) a sub-tile cut with
+    a 12-pixel halo reproduces the full-cube result bit for bit in its
+    interior (the multi-GPU decomposition relies on it); (2) sampled voxels
+    match the direct-space float64 oracle."""
+    shape = (600, 96, 160)
+    fsf = synthetic.moffat_fsf(shape[0])
+    cube, _ = synthetic.faint_cube(shape, fsf, n_src=10, seed=22)
+    profs = dictionaries.dico_fwhm_2_12()[0]
+    full = lo.tglr(cube, fsf, None, profs, pcut=1e-8, want=('correl', 'correl_min', 'profile'))
+    y0, y1, x0, x1 = 20, 70, 40, 120
+    sub = np.ascontiguousarray(cube[:, y0 - 12:y1 + 12, x0 - 12:x1 + 12])
+    part = lo.tglr(sub, fsf, None, profs, pcut=1e-8, want=('correl', 'correl_min', 'profile'))
+    for k in ('correl', 'correl_min', 'profile'):
+        np.testing.assert_array_equal(part[k][:, 12:-12, 12:-12], full[k][:, y0:y1, x0:x1], err_msg=k)
+    rng = np.random.default_rng(3)
+    pts = [(int(rng.integers(0, shape[0])), int(rng.integers(0, shape[1])), int(rng.integers(0, shape[2])))
+           for _ in range(40)] + [(0, 0, 0), (599, 95, 159), (300, 0, 80), (10, 50, 159)]
+    prof_cut = orc.prepare_profiles(profs, 1e-8, True)
+    tk = orc.spot_tglr(cube, fsf, prof_cut, pts)
+    rms = float(np.sqrt(np.mean(full['correl'].astype(np.float64) ** 2)))
+    for (z, y, x), t in zip(pts, tk):
+        assert abs(full['correl'][z, y, x] - t.max()) <= RTOL * max(abs(t.max()), rms)
+        assert abs(full['correl_min'][z, y, x] - t.min()) <= RTOL * max(abs(t.min()), rms)
