@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""Benchmark of ORIGIN's detection hot path on B200: step05 TGLR (+ local extrema + step06
+purity counts) in Gvoxel.profiles/s on a synthetic MUSE-shaped cube.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--shape NZ NY NX] [--dico 3FWHM|2_12]
+
+Prints ONE JSON line (see DESIGN.md "Measurement" for every field).
+
+* ``value``  device-resident: inputs already in HBM, CUDA events around K steps.
+* ``e2e``    the same step through the public host API (``lib_origin.step05`` ->
+             ``ogn_step05``) with pinned HOST buffers: every step copies the cube and
+             mask host->device and every product device->host inside the timed region.
+* ``roofline`` dominant kernel (K1, per-lambda FSF correlation): algorithmic FLOPs /
+             CUDA-event duration on the launching stream, against the FP32 FFMA peak
+             measured on this device by ``tools/fma_peak`` in the same run.
+* ``cpu_baseline`` the float64 oracle port of the reference algorithm
+             (``oracle/origin_oracle.py``) timed on the host cores on a bounded spatial
+             tile of the same workload (rank 0, N=1 only).
+* ``--impl reference``: that CPU port alone, in the same JSON shape.
+
+N > 1 (launched by torchrun): the cube is split into spatial tiles with (P//2 + 1)-pixel
+halos, one per rank (strong scaling of the fixed cube); the step adds the NCCL allreduce
+of the per-threshold purity counts and the gather of the owned correl tiles to rank 0.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PSF_SIZE = 25
+SHAPE = (3681, 320, 320)
+CPU_TILE = (64, 96)          # spatial sample of the workload for the CPU baseline
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--shape', type=int, nargs=3, default=list(SHAPE))
+    ap.add_argument('--dico', default='3FWHM', choices=['3FWHM', '2_12'])
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    return ap.parse_args()
+
+
+def dictionary(name):
+    from origin_b200 import dictionaries
+    return dictionaries.dico_3fwhm()[0] if name == '3FWHM' else dictionaries.dico_fwhm_2_12()[0]
+
+
+def sum_taps(profs, pcut=1e-8):
+    from origin_b200.lib_origin import prepare_profiles
+    return sum(len(p) for p in prepare_profiles(profs, pcut, True))
+
+
+# ------------------------------------------------------------------------------------------
+# CPU leg (cpu_baseline and --impl reference): the oracle port on a bounded tile
+# ------------------------------------------------------------------------------------------
+
+def cpu_step(cube, fsf, profs, mask, workers):
+    from oracle import origin_oracle as orc
+    out = orc.tglr_step(cube, fsf, None, profs, mask, 3, workers, 1e-8, True)
+    orc.threshold_purity(0.9, out['cube_local_max'], out['cube_local_min'])
+    return out
+
+
+def cpu_inputs(nz, seed=0):
+    from origin_b200 import synthetic
+    ty, tx = CPU_TILE
+    fsf = synthetic.moffat_fsf(nz)
+    cube, _ = synthetic.faint_cube((nz, ty, tx), fsf, n_src=4, seed=seed)
+    mask = synthetic.footprint_mask((nz, ty, tx), seed=seed)
+    return cube, fsf, mask
+
+
+def run_cpu(nz, profs, steps, warmup):
+    cores = os.cpu_count() or 1
+    cube, fsf, mask = cpu_inputs(nz)
+    for _ in range(warmup):
+        cpu_step(cube, fsf, profs, mask, cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(cube, fsf, profs, mask, cores)
+    dt = (time.perf_counter() - t0) / steps
+    units = cube.size * len(profs) / 1e9
+    return dict(value=units / dt, seconds_per_step=dt, cores=cores,
+                sample='%dx%dx%d tile of the cube, all %d profiles, float64, scipy.fft workers=%d'
+                       % (cube.shape + (len(profs), cores)))
+
+
+def main_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    profs = dictionary(args.dico)
+    nz = args.shape[0]
+    res = run_cpu(nz, profs, max(1, min(args.steps, 10)), min(args.warmup, 3))
+    line = dict(
+        metric='step05 TGLR throughput', value=res['value'], unit='Gvoxel.profiles/s', impl='reference',
+        n_gpus=args.gpus, steps=max(1, min(args.steps, 10)), warmup=min(args.warmup, 3),
+        ms_per_step=res['seconds_per_step'] * 1e3, higher_is_better=True, scaling='strong', vs_baseline=None,
+        dtype='f64', data='synthetic',
+        config=dict(workload='step05 TGLR + local extrema + step06 purity counts, %dx%dx%d cube, Dico_%s'
+                             % (tuple(args.shape) + (args.dico,)), psf_size=PSF_SIZE),
+        cpu_baseline=dict(value=res['value'], unit='Gvoxel.profiles/s', cores=res['cores'], kind='port',
+                          sample=res['sample']),
+        e2e=dict(value=res['value'], unit='Gvoxel.profiles/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        note='oracle port of the reference algorithm (the Python reference cannot travel to the GPU box); '
+             'each step is a bounded spatial tile of the workload',
+    )
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU leg
+# ------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def fma_peak():
+    exe = os.path.join(ROOT, 'tools', 'fma_peak')
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout.strip().splitlines()[-1]
+        return json.loads(out)
+    except Exception as exc:  # noqa: BLE001
+        return dict(error=str(exc))
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return json.load(f)
+    except OSError:
+        return {}
+
+
+def ncu_summary():
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_summary.json')) as f:
+            return json.load(f)
+    except OSError:
+        return {}
+
+
+def main_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from origin_b200 import _lib, lib_origin, synthetic, tiles
+    from origin_b200 import distributed as ogd
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the ported path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    ctx = _lib.default_context(local_rank)
+
+    nz, ny, nx = args.shape
+    profs = dictionary(args.dico)
+    nprof = len(profs)
+    fsf_host = synthetic.moffat_fsf(nz, PSF_SIZE)
+    fsf = torch.from_numpy(fsf_host).to(dev)
+    halo = PSF_SIZE // 2 + 1
+    all_tiles = tiles.plan_tiles(ny, nx, world, halo)
+    tile = all_tiles[rank]
+
+    # synthetic global cube, identical on every rank (same device generator seed), then the rank's tile
+    gen = torch.Generator(device=dev).manual_seed(0)
+    cube_g = torch.randn((nz, ny, nx), device=dev, dtype=torch.float32, generator=gen)
+    yy = torch.arange(ny, device=dev, dtype=torch.float32)[:, None]
+    xx = torch.arange(nx, device=dev, dtype=torch.float32)[None, :]
+    cy, cx, th = (ny - 1) / 2, (nx - 1) / 2, float(np.deg2rad(3.0))
+    u = (xx - cx) * np.cos(th) + (yy - cy) * np.sin(th)
+    v = -(xx - cx) * np.sin(th) + (yy - cy) * np.cos(th)
+    foot = (u.abs() > 0.49 * nx) | (v.abs() > 0.49 * ny)                      # ~5 % of the spaxels
+    mask_g = (torch.rand((nz, ny, nx), device=dev, generator=gen) < 1e-3) | foot[None]
+    n_src = max(1, int(round(200 * nz * ny * nx / (3681 * 320 * 320))))
+    rng = np.random.default_rng(0)
+    for _ in range(n_src):                                                        # injected line emitters
+        z0, y0, x0 = int(rng.integers(20, nz - 20)), int(rng.integers(13, ny - 13)), int(rng.integers(13, nx - 13))
+        sig = rng.uniform(2.0, 12.0) / 2.3548
+        hw = int(np.ceil(4 * sig))
+        zz = np.arange(max(0, z0 - hw), min(nz, z0 + hw + 1))
+        line = np.exp(-0.5 * ((zz - z0) / sig) ** 2)
+        spat = fsf_host[z0]
+        amp = rng.uniform(5.0, 30.0) / np.sqrt((spat ** 2).sum() * (line ** 2).sum())
+        patch = torch.from_numpy((amp * line[:, None, None] * spat[None]).astype(np.float32)).to(dev)
+        cube_g[zz[0]:zz[-1] + 1, y0 - 12:y0 + 13, x0 - 12:x0 + 13] += patch
+    py, px = tile.padded
+    cube = cube_g[:, py, px].contiguous()
+    mask = mask_g[:, py, px].to(torch.uint8).contiguous()
+    del cube_g, mask_g
+    tz, ty_, tx_ = cube.shape
+    vol_tile = tz * ty_ * tx_
+    cap = max(4096, vol_tile // 40)
+    out_dev = dict(correl=torch.empty_like(cube), correl_min=torch.empty_like(cube),
+                   profile=torch.empty(cube.shape, dtype=torch.uint8, device=dev),
+                   maxmap=torch.empty((ty_, tx_), device=dev), minmap=torch.empty((ty_, tx_), device=dev),
+                   max_index=torch.empty(cap, dtype=torch.int64, device=dev),
+                   max_value=torch.empty(cap, device=dev),
+                   min_index=torch.empty(cap, dtype=torch.int64, device=dev),
+                   min_value=torch.empty(cap, device=dev))
+    reducer = ogd.Reducer() if world > 1 else None
+    thresholds = np.linspace(4.0, 12.0, 50)
+    state = {}
+
+    def step():
+        res = lib_origin.step05(cube, fsf, None, profs, mask, 3, 1e-8, True, out=out_dev, ctx=ctx)
+        ext = res['extrema']
+        if world > 1:
+            ext = ogd.owned_extrema(ext, tile, (nz, ny, nx))
+        else:
+            ext = lib_origin.LocalExtrema((nz, ny, nx), ext.max_index, ext.max_value, ext.min_index, ext.min_value)
+        n1, n0 = lib_origin.purity_counts(ext, None, thresholds, ctx)            # step06 counting loop
+        if world > 1:
+            both = reducer.sum(np.concatenate([n1, n0]))                          # NCCL allreduce of the histograms
+            n1, n0 = both[:50], both[50:]
+            state['correl_full'] = ogd.gather_owned(res['correl'], tile, all_tiles, (nz, ny, nx))
+        state['n1'], state['n0'], state['ext'] = n1, n0, ext
+        return res
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    ctx.timing(True)
+    ctx.timing_report()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    stages = {}
+    for name, ms in ctx.timing_report():
+        stages.setdefault(name, []).append(ms)
+    ctx.timing(False)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms_step = ms_total / args.steps
+    units = nz * ny * nx * nprof / 1e9
+    value = units / (ms_step * 1e-3)
+
+    # ---- end to end through the host API with pinned host buffers --------------------------
+    e2e = None
+    if not args.no_e2e:
+        cube_h = _lib.pinned_empty(cube.shape, np.float32)
+        mask_h = _lib.pinned_empty(cube.shape, np.uint8)
+        cube_h[...] = cube.cpu().numpy()
+        mask_h[...] = mask.cpu().numpy()
+        out_h = dict(correl=_lib.pinned_empty(cube.shape, np.float32), correl_min=_lib.pinned_empty(cube.shape, np.float32),
+                     profile=_lib.pinned_empty(cube.shape, np.uint8), maxmap=_lib.pinned_empty((ty_, tx_), np.float32),
+                     minmap=_lib.pinned_empty((ty_, tx_), np.float32),
+                     max_index=_lib.pinned_empty((cap,), np.int64), max_value=_lib.pinned_empty((cap,), np.float32),
+                     min_index=_lib.pinned_empty((cap,), np.int64), min_value=_lib.pinned_empty((cap,), np.float32))
+
+        def step_e2e():
+            res = lib_origin.step05(cube_h, fsf_host, None, profs, mask_h, 3, 1e-8, True, out=out_h, ctx=ctx)
+            ext = res['extrema']
+            n1, n0 = lib_origin.purity_counts(lib_origin.LocalExtrema(cube.shape, ext.max_index, ext.max_value,
+                                                                       ext.min_index, ext.min_value), None,
+                                              thresholds, ctx)
+            if world > 1:
+                reducer.sum(np.concatenate([n1, n0]))
+            return res
+
+        step_e2e()
+        sync_all()
+        n_e2e = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n_e2e):
+            res = step_e2e()
+        e1.record()
+        sync_all()
+        wall = (time.perf_counter() - t0) * 1e3 / n_e2e
+        ms_e2e = max(e0.elapsed_time(e1) / n_e2e, wall)
+        if world > 1:
+            t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
+        n1c, n0c = res['extrema'].counts
+        h2d = cube_h.nbytes + mask_h.nbytes + fsf_host.nbytes
+        d2h = (out_h['correl'].nbytes + out_h['correl_min'].nbytes + out_h['profile'].nbytes
+               + out_h['maxmap'].nbytes + out_h['minmap'].nbytes + 12 * (n1c + n0c) + 16)
+        e2e = dict(value=units / (ms_e2e * 1e-3), unit='Gvoxel.profiles/s', ms_per_step=ms_e2e,
+                   h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                   api='origin_b200.lib_origin.step05 -> ogn_step05 (pinned host numpy in/out) + purity_counts')
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------
+    peak = fma_peak() if world == 1 else {}
+    mp = measured_peaks()
+    k1_ms = float(np.mean(stages.get('k1_fsf_correlate', [np.nan])))
+    k2_ms = float(np.mean(stages.get('k2_spectral_glr', [np.nan])))
+    k3_ms = float(np.mean(stages.get('k3_local_extrema', [np.nan])))
+    k1_flops = 2.0 * PSF_SIZE * PSF_SIZE * vol_tile
+    k2_flops = 2.0 * sum_taps(profs) * vol_tile
+    fp32_peak = peak.get('fp32_tflops')
+    summ = ncu_summary()
+    roofline = dict(
+        bound='fp32', kernel='k1::fsf_correlate_kernel<25>', achieved=k1_flops / (k1_ms * 1e-3) / 1e12,
+        peak=fp32_peak, unit='TFLOP/s', frac=(k1_flops / (k1_ms * 1e-3) / 1e12 / fp32_peak) if fp32_peak else None,
+        traffic=summ.get('k1_dram_bytes_per_launch'),
+        peak_source='FP32 FFMA peak measured on this device in this run by tools/fma_peak '
+                    '(MEASURED_PEAKS.json has no FP32 figure; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)',
+        algorithmic='2*P^2 = %d flop/voxel x %d voxels per launch' % (2 * PSF_SIZE ** 2, vol_tile),
+        ms_per_launch=k1_ms,
+        note='the schema value "tensor" does not apply: the path is FP32-FMA bound (SURVEY.md 8d), '
+             'tensor cores cannot meet the 1e-5 parity bound',
+    )
+    hbm_peak = mp.get('hbm_gbs')
+    kernels = dict(
+        k1_fsf_correlate=dict(ms=k1_ms, tflops=k1_flops / (k1_ms * 1e-3) / 1e12, bound='fp32'),
+        k2_spectral_glr=dict(ms=k2_ms, tflops=k2_flops / (k2_ms * 1e-3) / 1e12, bound='fp32'),
+        k3_local_extrema=dict(ms=k3_ms, gbs=9.0 * vol_tile / (k3_ms * 1e-3) / 1e9, bound='hbm',
+                              frac_of_measured_hbm=(9.0 * vol_tile / (k3_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None),
+        other_ms={k: float(np.mean(v)) for k, v in stages.items()
+                  if k not in ('k1_fsf_correlate', 'k2_spectral_glr', 'k3_local_extrema')},
+    )
+    total_flops = (2.0 * PSF_SIZE ** 2 + 2.0 * sum_taps(profs)) * nz * ny * nx
+    line = dict(
+        metric='step05 TGLR throughput', value=value, unit='Gvoxel.profiles/s', n_gpus=world, steps=args.steps,
+        warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling='strong', vs_baseline=None,
+        dtype='f32', data='synthetic',
+        config=dict(workload='step05 TGLR + local extrema + step06 purity counts, %dx%dx%d float32 cube, Dico_%s '
+                             '(%d profiles), single field, mask ~5%% footprint + 0.1%% voxels'
+                             % (nz, ny, nx, args.dico, nprof),
+                    psf_size=PSF_SIZE, parallelism='spatial tiles %s with %d-px halos' % (
+                        'x'.join(str(v) for v in tiles.grid_shape(world, ny, nx)), halo),
+                    l2='inputs (%.1f GB per rank) exceed the 126 MB L2; no flush needed' % (cube.numel() * 4 / 1e9),
+                    timed_region='CUDA events on the launching stream around %d steps, barrier + synchronize on both '
+                                 'sides, max over ranks' % args.steps),
+        e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline, kernels=kernels,
+        step_fp32_tflops=total_flops / (ms_step * 1e-3) / 1e12,
+        step_fp32_frac=(total_flops / (ms_step * 1e-3) / 1e12 / fp32_peak) if fp32_peak else None,
+        fma_peak=peak, n_local_extrema=[int(v) for v in state['ext'].counts],
+    )
+    if world == 1 and not args.no_cpu:
+        cb = run_cpu(nz, profs, 1, 0)
+        line['cpu_baseline'] = dict(value=cb['value'], unit='Gvoxel.profiles/s', cores=cb['cores'], kind='port',
+                                    sample=cb['sample'], seconds_for_sample=cb['seconds_per_step'])
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        main_reference(a)
+    else:
+        main_gpu(a)

@@ -70,6 +70,11 @@ OGN_API int ogn_version(void);
 OGN_API int ogn_synchronize(ogn_ctx *ctx);
 /* Number of kernels this context has launched so far (bench bookkeeping). */
 OGN_API int64_t ogn_launch_count(const ogn_ctx *ctx);
+/* Per-stage CUDA-event timing on the context's stream (off by default).
+ * ogn_timing_report synchronises, writes "stage:ms;stage:ms;..." for every
+ * stage timed since the previous report into buf, and clears the list. */
+OGN_API int ogn_timing_enable(ogn_ctx *ctx, int on);
+OGN_API int ogn_timing_report(ogn_ctx *ctx, char *buf, size_t size);
 /* Release the context's scratch memory (it is re-grown on demand). */
 OGN_API int ogn_trim(ogn_ctx *ctx);
 /* Pinned host memory for fast staging (optional; any host pointer works). */
@@ -142,6 +147,25 @@ OGN_API int ogn_local_extrema(ogn_ctx *ctx,
                       int64_t *max_index, float *max_value,
                       int64_t *min_index, float *min_value,
                       int64_t capacity, int64_t *counts);
+
+/* The whole array part of ComputeTGLR.run (steps.py:768-802) in one call:
+ * ogn_tglr followed by ogn_local_extrema on the masked correl / correl_min,
+ * with the intermediates staying on the device.  Arguments are those of the
+ * two functions; correl and correl_min may be NULL when only the extremum
+ * lists are wanted.  Returns OGN_ERR_OVERFLOW like ogn_local_extrema (all
+ * other outputs are complete in that case). */
+OGN_API int ogn_step05(ogn_ctx *ctx,
+               const void *cube, int cube_dtype, int nz, int ny, int nx,
+               int nfields, const double *const *fsf, int psize,
+               const double *const *weights,
+               const double *taps, const int *tap_offsets, int nprof,
+               const uint8_t *mask, int sz, int sy, int sx,
+               float *correl, float *correl_min, uint8_t *profile,
+               float *maxmap, float *minmap,
+               float *dense_max, float *dense_min,
+               int64_t *max_index, float *max_value,
+               int64_t *min_index, float *min_value,
+               int64_t capacity, int64_t *counts);
 
 /* ---- step06: purity threshold counts ------------------------------------ */
 

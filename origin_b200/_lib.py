@@ -27,12 +27,18 @@ SIGNATURES = {
     'ogn_synchronize': (c_int, [c_void_p]),
     'ogn_launch_count': (c_int64, [c_void_p]),
     'ogn_trim': (c_int, [c_void_p]),
+    'ogn_timing_enable': (c_int, [c_void_p, c_int]),
+    'ogn_timing_report': (c_int, [c_void_p, ctypes.c_char_p, ctypes.c_size_t]),
     'ogn_host_alloc': (c_int, [ctypes.c_size_t, ctypes.POINTER(c_void_p)]),
     'ogn_host_free': (c_int, [c_void_p]),
     'ogn_tglr': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                          c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ogn_fsf_stage': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                               c_void_p, c_void_p]),
+    'ogn_step05': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                           c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                           c_void_p]),
     'ogn_local_extrema': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     'ogn_purity_stats': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
@@ -120,6 +126,21 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.ogn_launch_count(self.handle))
+
+    def timing(self, on=True):
+        """Switch per-stage CUDA-event timing on or off."""
+        self.check(self.lib.ogn_timing_enable(self.handle, int(bool(on))))
+
+    def timing_report(self):
+        """``[(stage, ms), ...]`` for the stages timed since the last report."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        self.check(self.lib.ogn_timing_report(self.handle, buf, len(buf)))
+        out = []
+        for item in buf.value.decode().split(';'):
+            if item:
+                name, ms = item.rsplit(':', 1)
+                out.append((name, float(ms)))
+        return out
 
     def trim(self):
         self.check(self.lib.ogn_trim(self.handle))

@@ -83,6 +83,34 @@ extern "C" int ogn_synchronize(ogn_ctx *ctx) {
     return OGN_OK;
 }
 
+extern "C" int ogn_timing_enable(ogn_ctx *ctx, int on) {
+    if (!ctx) return OGN_ERR_ARG;
+    ctx->timing = on != 0;
+    return OGN_OK;
+}
+
+// "name:ms;name:ms;..." for every timed stage since the last report; clears the list.
+extern "C" int ogn_timing_report(ogn_ctx *ctx, char *buf, size_t size) {
+    if (!ctx || !buf || size == 0) return OGN_ERR_ARG;
+    OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::string out;
+    for (auto &e : ctx->timings) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.start, e.stop) == cudaSuccess) {
+            char tmp[160];
+            snprintf(tmp, sizeof(tmp), "%s:%.6f;", e.name.c_str(), ms);
+            out += tmp;
+        } else {
+            cudaGetLastError();
+        }
+        cudaEventDestroy(e.start);
+        cudaEventDestroy(e.stop);
+    }
+    ctx->timings.clear();
+    snprintf(buf, size, "%s", out.c_str());
+    return OGN_OK;
+}
+
 extern "C" int64_t ogn_launch_count(const ogn_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int ogn_host_alloc(size_t bytes, void **out) {

@@ -27,7 +27,14 @@ struct ogn_prep_state {
     double *cont = nullptr;         // device: continuum (f64)
 };
 
+struct ogn_timing_entry {
+    std::string name;
+    cudaEvent_t start = nullptr, stop = nullptr;
+};
+
 struct ogn_ctx {
+    bool timing = false;
+    std::vector<ogn_timing_entry> timings;
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -40,6 +47,24 @@ struct ogn_ctx {
 };
 
 int ogn_fail(ogn_ctx *ctx, int code, const char *fmt, ...);
+
+// Scoped CUDA-event timer on the context's stream (active only after ogn_timing_enable).
+struct ogn_timer {
+    ogn_ctx *ctx;
+    int slot = -1;
+    ogn_timer(ogn_ctx *c, const char *name) : ctx(c) {
+        if (!ctx->timing) return;
+        ogn_timing_entry e;
+        e.name = name;
+        if (cudaEventCreate(&e.start) != cudaSuccess || cudaEventCreate(&e.stop) != cudaSuccess) return;
+        cudaEventRecord(e.start, ctx->stream);
+        ctx->timings.push_back(e);
+        slot = (int)ctx->timings.size() - 1;
+    }
+    ~ogn_timer() {
+        if (slot >= 0) cudaEventRecord(ctx->timings[slot].stop, ctx->stream);
+    }
+};
 
 #define OGN_CUDA(call)                                                                       \
     do {                                                                                     \

@@ -56,6 +56,106 @@ __global__ void local_extrema_kernel(const float *__restrict__ a, const float *_
     }
 }
 
+// 3 x 3 x 3 window (the default, steps.py:427,756): a block owns a 32 x 16 spatial tile and
+// walks a run of wavelength planes with 18 warps, one per tile row including the two halo
+// rows.  Per plane every thread loads its own voxel of both arrays (one coalesced 128-byte
+// row per warp; lanes 0 and 31 also fetch the neighbouring tile's column), takes the 3-wide
+// max / min along x with two shuffles, the 3-wide max / min along y through a
+// double-buffered shared-memory tile (one barrier per plane), and keeps the plane extrema
+// of z-1, z, z+1 in registers, so each voxel is read once per array from L2/HBM.  The loads
+// of plane p+1 are issued before plane p is reduced (software pipeline).
+constexpr int EX_TY = 16;
+constexpr int EX_CZ = 64;
+
+struct ExPlane {
+    float va, ea, vb, eb;  // own voxel and (lanes 0 / 31) the neighbouring tile's voxel
+    uint8_t m;
+};
+
+__global__ void __launch_bounds__(32 * (EX_TY + 2))
+local_extrema3_kernel(const float *__restrict__ a, const float *__restrict__ b, const uint8_t *__restrict__ mask,
+                      int nz, int ny, int nx, float *__restrict__ dense_max, float *__restrict__ dense_min,
+                      uint32_t *__restrict__ flag_max, uint32_t *__restrict__ flag_min, int nxw) {
+    __shared__ float sa[2][EX_TY + 2][32];
+    __shared__ float sb[2][EX_TY + 2][32];
+    const int lane = threadIdx.x, row = threadIdx.y;  // row 0 and EX_TY+1 are halo rows
+    const int x0 = blockIdx.x * 32, x = x0 + lane;
+    const int y = blockIdx.y * EX_TY + row - 1;
+    const int zc0 = blockIdx.z * EX_CZ, zc1 = min(nz, zc0 + EX_CZ);
+    const bool row_ok = y >= 0 && y < ny;
+    const bool c_ok = row_ok && x < nx;
+    const int xe = lane == 0 ? x0 - 1 : x0 + 32;
+    const bool e_ok = row_ok && ((lane == 0 && x0 > 0) || (lane == 31 && x0 + 32 < nx));
+    const bool out_row = row >= 1 && row <= EX_TY && y < ny;
+    const size_t plane = (size_t)ny * nx;
+    const size_t oc = (size_t)(row_ok ? y : 0) * nx + (x < nx ? x : 0);
+    const size_t oe = (size_t)(row_ok ? y : 0) * nx + (e_ok ? xe : 0);
+
+    auto load_plane = [&](int p) {
+        ExPlane pl;
+        const bool pok = p >= 0 && p < nz;
+        const size_t base = (size_t)(pok ? p : 0) * plane;
+        pl.va = (pok && c_ok) ? __ldg(a + base + oc) : -INFINITY;
+        pl.ea = (pok && e_ok) ? __ldg(a + base + oe) : -INFINITY;
+        pl.vb = (pok && c_ok) ? __ldg(b + base + oc) : INFINITY;
+        pl.eb = (pok && e_ok) ? __ldg(b + base + oe) : INFINITY;
+        pl.m = (mask && pok && c_ok) ? mask[base + oc] : (uint8_t)0;
+        return pl;
+    };
+
+    float pa_prev = -INFINITY, pa_cur = -INFINITY, ca_cur = 0.f;
+    float pb_prev = INFINITY, pb_cur = INFINITY, cb_cur = 0.f;
+    uint8_t m_cur = 0;
+    ExPlane cur = load_plane(zc0 - 1);
+#pragma unroll 2
+    for (int p = zc0 - 1; p <= zc1; ++p) {
+        const ExPlane nxt = load_plane(p + 1 <= zc1 ? p + 1 : -1);
+        const int buf = (p - zc0 + 1) & 1;
+        {
+            float l = __shfl_up_sync(0xffffffffu, cur.va, 1), r = __shfl_down_sync(0xffffffffu, cur.va, 1);
+            if (lane == 0) l = cur.ea;
+            if (lane == 31) r = cur.ea;
+            sa[buf][row][lane] = fmaxf(cur.va, fmaxf(l, r));
+            l = __shfl_up_sync(0xffffffffu, cur.vb, 1);
+            r = __shfl_down_sync(0xffffffffu, cur.vb, 1);
+            if (lane == 0) l = cur.eb;
+            if (lane == 31) r = cur.eb;
+            sb[buf][row][lane] = fminf(cur.vb, fminf(l, r));
+        }
+        __syncthreads();
+        const int q = p - 1;
+        if (out_row) {  // warp-uniform
+            const float m9a = fmaxf(sa[buf][row - 1][lane], fmaxf(sa[buf][row][lane], sa[buf][row + 1][lane]));
+            const float m9b = fminf(sb[buf][row - 1][lane], fminf(sb[buf][row][lane], sb[buf][row + 1][lane]));
+            if (q >= zc0 && q < zc1) {
+                bool keep_a = false, keep_b = false;
+                if (x < nx) {
+                    keep_a = !m_cur && ca_cur == fmaxf(pa_prev, fmaxf(pa_cur, m9a));
+                    keep_b = !m_cur && cb_cur == fminf(pb_prev, fminf(pb_cur, m9b));
+                    if (dense_max || dense_min) {
+                        const size_t idx = (size_t)q * plane + oc;
+                        if (dense_max) dense_max[idx] = keep_a ? ca_cur : 0.f;
+                        if (dense_min) dense_min[idx] = keep_b ? -cb_cur : 0.f;
+                    }
+                }
+                const uint32_t wa = __ballot_sync(0xffffffffu, keep_a);
+                const uint32_t wb = __ballot_sync(0xffffffffu, keep_b);
+                if (lane == 0) {
+                    const size_t w = ((size_t)q * ny + y) * nxw + blockIdx.x;
+                    flag_max[w] = wa;
+                    flag_min[w] = wb;
+                }
+            }
+            pa_prev = pa_cur; pa_cur = m9a;
+            pb_prev = pb_cur; pb_cur = m9b;
+        }
+        ca_cur = cur.va;
+        cb_cur = cur.vb;
+        m_cur = cur.m;
+        cur = nxt;
+    }
+}
+
 // ---- exclusive scan of popcounts (3 phases, 1024 words per block) ------------------------
 constexpr int SCAN_BLOCK = 1024;
 
@@ -255,14 +355,25 @@ extern "C" int ogn_local_extrema(ogn_ctx *ctx, const float *a, const float *b, c
     OGN_TRY(ogn_scratch_t(ctx, "ext_flag_max", nwords, &flag_max));
     OGN_TRY(ogn_scratch_t(ctx, "ext_flag_min", nwords, &flag_min));
 
-    {
+    ogn_timer *t_k3 = new ogn_timer(ctx, "k3_local_extrema");
+    if (sz == 3 && sy == 3 && sx == 3) {
+        dim3 block(32, EX_TY + 2);
+        dim3 grid(nxw, ogn_div_up(ny, EX_TY), ogn_div_up(nz, EX_CZ));
+        local_extrema3_kernel<<<grid, block, 0, ctx->stream>>>((const float *)da, (const float *)db,
+                                                              (const uint8_t *)dm, nz, ny, nx, (float *)d_dmax,
+                                                              (float *)d_dmin, flag_max, flag_min, nxw);
+        delete t_k3;
+        OGN_LAUNCH_CHECK("local_extrema3_kernel");
+    } else {
         dim3 block(32, 8);
         dim3 grid(nxw, ogn_div_up(ny, 8), nz);
         local_extrema_kernel<<<grid, block, 0, ctx->stream>>>((const float *)da, (const float *)db,
                                                              (const uint8_t *)dm, nz, ny, nx, sz / 2, sy / 2, sx / 2,
                                                              (float *)d_dmax, (float *)d_dmin, flag_max, flag_min, nxw);
+        delete t_k3;
         OGN_LAUNCH_CHECK("local_extrema_kernel");
     }
+    ogn_timer t_compact(ctx, "k3_compaction");
 
     const bool want_lists = max_index && max_value && min_index && min_value && capacity > 0;
     void *d_maxi = nullptr, *d_maxv = nullptr, *d_mini = nullptr, *d_minv = nullptr;

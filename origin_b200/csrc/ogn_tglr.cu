@@ -136,26 +136,7 @@ __global__ void den_table_kernel(const double *__restrict__ normcls, int nz, int
 // consecutive rows) and the P weights of the row (LDS.128 broadcast) and issues
 // 32*P FFMAs from registers.
 // ---------------------------------------------------------------------------
-namespace k1 {
-constexpr int TILE = 64;     // outputs per tile side
-constexpr int STRIP = 32;    // outputs per thread
-constexpr int THREADS = TILE * (TILE / STRIP);
-
-template <int P>
-struct Geo {
-    static constexpr int WP = (P + 3) / 4 * 4;
-    static constexpr int ROWS = TILE + P - 1;
-    static constexpr int NEED = TILE + P - 1;
-    // smallest pitch >= NEED with pitch % 32 == 4 (conflict-free LDS.128 across rows)
-    static constexpr int PITCH = ((NEED - 4 + 31) / 32) * 32 + 4;
-    static constexpr int IN_N = (STRIP + P - 1 + 3) / 4 * 4;
-    static constexpr int TILE_BYTES = ROWS * PITCH * 4;
-    static constexpr int W_BYTES = P * WP * 4;
-    static constexpr int SMEM = TILE_BYTES + W_BYTES + 16;
-    static_assert(PITCH >= (TILE / STRIP - 1) * STRIP + IN_N, "pitch too small for the last strip");
-    static_assert(PITCH <= 256, "TMA box dimension limit");
-};
-
+namespace tma {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -188,6 +169,29 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+
+}  // namespace tma
+
+namespace k1 {
+using namespace tma;
+constexpr int TILE = 64;     // outputs per tile side
+constexpr int STRIP = 32;    // outputs per thread
+constexpr int THREADS = TILE * (TILE / STRIP);
+
+template <int P>
+struct Geo {
+    static constexpr int WP = (P + 3) / 4 * 4;
+    static constexpr int ROWS = TILE + P - 1;
+    static constexpr int NEED = TILE + P - 1;
+    // smallest pitch >= NEED with pitch % 32 == 4 (conflict-free LDS.128 across rows)
+    static constexpr int PITCH = ((NEED - 4 + 31) / 32) * 32 + 4;
+    static constexpr int IN_N = (STRIP + P - 1 + 3) / 4 * 4;
+    static constexpr int TILE_BYTES = ROWS * PITCH * 4;
+    static constexpr int W_BYTES = P * WP * 4;
+    static constexpr int SMEM = TILE_BYTES + W_BYTES + 16;
+    static_assert(PITCH >= (TILE / STRIP - 1) * STRIP + IN_N, "pitch too small for the last strip");
+    static_assert(PITCH <= 256, "TMA box dimension limit");
+};
 
 template <int P>
 __global__ void __launch_bounds__(THREADS, 4)
@@ -303,23 +307,29 @@ __global__ void fsf_correlate_naive_kernel(const float *__restrict__ in, int in_
 // ---------------------------------------------------------------------------
 // K2: spectral correlation with every profile + max / argmax / min.
 //
-// Block = NW warps; the 32 lanes are 32 consecutive x of one image row, warp w
-// owns the ZB consecutive wavelengths starting at (blockIdx.z*NW + w)*ZB.  The
-// block first stages the column window it needs (NW*ZB + longest profile rows
-// of 32 floats, zeros outside [0, nz)) in shared memory; every lane only ever
-// reads its own column, so the rows are bank-conflict free and no further
-// synchronisation is needed.  For each profile a thread then runs the taps in
-// chunks of U=4 over a ring of ZB+2U registers: chunk q multiplies taps
-// 4q..4q+3 (one broadcast LDS.128) into the ZB accumulators while the 4 window
-// values the next chunk needs are loaded into the free ring slots; the chunk
-// loop is unrolled by the ring period so every register index is static.
-// After the last tap the ZB values are normalised (table lookup for a single
-// FSF, per-voxel denominator otherwise) and folded into the running max /
-// first-wins argmax / min (lib_origin.py:1210-1212).
+// Block = NW warps; the 32 lanes are 32 consecutive x of one image row.  A block
+// walks wavelength chunks of NW*ZB planes (warp w owns the ZB planes starting at
+// chunk*NW*ZB + w*ZB).  For every chunk one elected thread issues 3-D TMA loads
+// of the column window the chunk needs — box {32 x, 1 y, rows z}, rows = NW*ZB +
+// longest profile; wavelengths outside [0, nz) and columns beyond nx are
+// zero-filled by the TMA unit, which is the reference's zero padding of the
+// linear convolution — into one of two shared-memory buffers, so the load of
+// chunk i+1 overlaps the arithmetic of chunk i.  Every lane only reads its own
+// column: rows are bank-conflict free.
+// For each profile a thread runs the taps in chunks of U=4 over a ring of
+// ZB+2U registers: chunk q multiplies taps 4q..4q+3 (one broadcast LDS.128)
+// into the ZB accumulators while the 4 window values the next chunk needs are
+// loaded into the free ring slots; the chunk loop is unrolled by the ring
+// period so every register index is static.  After the last tap the ZB values
+// are normalised (table lookup for a single FSF, per-voxel denominator
+// otherwise) and folded into the running max / first-wins argmax / min
+// (lib_origin.py:1210-1212).
 // ---------------------------------------------------------------------------
 namespace k2 {
+using namespace tma;
 constexpr int U = 4;
 constexpr int NW = 4;
+constexpr int MAX_BOX_ROWS = 256;
 
 struct ProfDesc {
     int tap_off;   // float offset of the reversed, zero-padded taps (multiple of 4)
@@ -337,154 +347,237 @@ __device__ __forceinline__ void atomic_min_float(float *addr, float v) {
     else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
 }
 
-template <int ZB, bool PERVOXEL>
-__global__ void __launch_bounds__(NW * 32, PERVOXEL ? 2 : (ZB > 24 ? 2 : 3))
-spectral_glr_kernel(const float *__restrict__ num_in, const float *__restrict__ den_in,  // [nz][ny][pitch]
-                    int nz, int ny, int nx, int pitch,
-                    const float *__restrict__ taps, const float *__restrict__ taps_sq, int ntaps_total,
-                    const ProfDesc *__restrict__ desc, int nprof, int win_rows, int woff_min,
-                    const float *__restrict__ rs, int nzp, int ncls, int ncx, int cls_ny, int cls_nx, int P,
-                    const uint8_t *__restrict__ mask,
-                    float *__restrict__ correl, float *__restrict__ correl_min, uint8_t *__restrict__ profile,
-                    float *__restrict__ maxmap, float *__restrict__ minmap) {
+// acc[i] += sum_j taps[j] * window[i + j] for one profile, window rows 32 floats apart
+template <int ZB>
+__device__ __forceinline__ void ring_correlate(const float *__restrict__ wp, const float4 *__restrict__ tp,
+                                               int nchunks, float (&acc)[ZB]) {
     constexpr int RING = ZB + 2 * U;
     constexpr int PERIOD = RING / U;
     static_assert(RING % U == 0, "ring must be a multiple of the chunk");
-    extern __shared__ __align__(16) float smem[];
-    float *win = smem;                                   // [win_rows][32]
-    float *win_den = PERVOXEL ? win + win_rows * 32 : nullptr;
-    float *tap_sm = smem + (PERVOXEL ? 2 : 1) * win_rows * 32;
-    float *tap_sq_sm = PERVOXEL ? tap_sm + ntaps_total : nullptr;
+    float ring[RING];
+#pragma unroll
+    for (int t = 0; t < ZB + U - 1; ++t) ring[t] = wp[t * 32];
+#pragma unroll
+    for (int i = 0; i < ZB; ++i) acc[i] = 0.f;
+    float4 e = tp[0];
+#pragma unroll 1
+    for (int qb = 0; qb < nchunks; qb += PERIOD) {
+#pragma unroll
+        for (int qq = 0; qq < PERIOD; ++qq) {
+            if (qb + qq < nchunks) {
+                // taps and window samples of the NEXT chunk are requested before this chunk's FFMAs
+                const float4 e_next = tp[qq + 1];  // one float4 past the profile is readable padding
+#pragma unroll
+                for (int ii = 0; ii < U; ++ii)
+                    ring[(U * qq + ZB + U - 1 + ii) % RING] = wp[(U * qq + ZB + U - 1 + ii) * 32];
+                const float ev[U] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+                for (int ii = 0; ii < U; ++ii)
+#pragma unroll
+                    for (int i = 0; i < ZB; ++i) acc[i] = fmaf(ev[ii], ring[(U * qq + i + ii) % RING], acc[i]);
+                e = e_next;
+            }
+        }
+        wp += PERIOD * U * 32;
+        tp += PERIOD;
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
+    const uint32_t d = smem_u32(dst);
+    const int bytes = valid ? 16 : 0;  // src-size 0: nothing is read, the 16 bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int ZB, bool PERVOXEL>
+__global__ void __launch_bounds__(NW * 32, PERVOXEL ? 2 : (ZB > 24 ? 2 : 3))
+spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_constant__ CUtensorMap den_map,
+                    int nz, int ny, int nx,
+                    const float *__restrict__ taps, const float *__restrict__ taps_sq, int ntaps_total,
+                    const ProfDesc *__restrict__ desc, int nprof, int box_rows, int nbox, int woff_min,
+                    const float *__restrict__ rs, int nzp, int ncls, int ncx, int P, int stage_rs, int stage_mask,
+                    const uint8_t *__restrict__ mask,
+                    float *__restrict__ correl, float *__restrict__ correl_min, uint8_t *__restrict__ profile,
+                    float *__restrict__ maxmap, float *__restrict__ minmap) {
+    // shared memory: [2 stages of window rows][taps (+ squares)][mbarriers]
+    //                [2 stages x NW warps of mask rows][2 stages x NW warps of rs rows]
+    extern __shared__ __align__(128) float smem[];
+    const int win_rows = box_rows * nbox;
+    constexpr int NSTAGE = 2;
+    const int stage_floats = (PERVOXEL ? 2 : 1) * win_rows * 32;
+    const int tap_floats = (PERVOXEL ? 2 : 1) * (ntaps_total + 4);
+    float *tap_sm = smem + NSTAGE * stage_floats;
+    float *tap_sq_sm = PERVOXEL ? tap_sm + ntaps_total + 4 : nullptr;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tap_sm + tap_floats);
+    uint8_t *mask_sm = reinterpret_cast<uint8_t *>(bars + 2);                         // [2][NW][ZB][32]
+    float *rs_sm = reinterpret_cast<float *>(mask_sm + (stage_mask ? 2 * NW * ZB * 32 : 0));  // [2][NW][nprof][ZB]
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = blockIdx.x * 32 + lane, y = blockIdx.y;
-    const int zb0 = blockIdx.z * (NW * ZB);
-    const int z0 = zb0 + warp * ZB;
-    const size_t plane = (size_t)ny * pitch;
-    const size_t col = (size_t)y * pitch + x;  // x < pitch always (pitch is a multiple of 32)
+    const int x0 = blockIdx.x * 32, x = x0 + lane, y = blockIdx.y;
+    const int nchunk = (nz + NW * ZB - 1) / (NW * ZB);
+    const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
 
-    for (int i = threadIdx.x; i < ntaps_total; i += NW * 32) {
-        tap_sm[i] = taps[i];
-        if (PERVOXEL) tap_sq_sm[i] = taps_sq[i];
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    for (int r = warp; r < win_rows; r += NW) {
-        int z = zb0 + woff_min + r;
-        bool ok = z >= 0 && z < nz;
-        win[r * 32 + lane] = ok ? __ldg(num_in + (size_t)z * plane + col) : 0.f;
-        if (PERVOXEL) win_den[r * 32 + lane] = ok ? __ldg(den_in + (size_t)z * plane + col) : 0.f;
+    for (int i = threadIdx.x; i < ntaps_total + 4; i += NW * 32) {
+        tap_sm[i] = i < ntaps_total ? taps[i] : 0.f;
+        if (PERVOXEL) tap_sq_sm[i] = i < ntaps_total ? taps_sq[i] : 0.f;
     }
     __syncthreads();
-    if (z0 >= nz) return;
 
-    float mx[ZB], mn[ZB];
-    int arg[ZB];
-#pragma unroll
-    for (int i = 0; i < ZB; ++i) { mx[i] = -INFINITY; mn[i] = INFINITY; arg[i] = 0; }
-
-    const float *rs_col = nullptr;
+    int cls_base = 0;
+    bool rs_staged = false;
     if (!PERVOXEL) {
-        int cls = cls_of(y, cls_ny, P) * ncx + cls_of(min(x, cls_nx - 1), cls_nx, P);
-        rs_col = rs + (size_t)cls * nzp + z0;
+        cls_base = cls_of(y, ny, P) * ncx + cls_of(min(x, nx - 1), nx, P);
+        // the warp shares one denominator row when all its lanes are interior in x
+        rs_staged = stage_rs && nx >= P && x0 >= P / 2 && x0 + 31 < nx - P / 2;
     }
 
-#pragma unroll 1
-    for (int k = 0; k < nprof; ++k) {
-        const ProfDesc d = desc[k];
-        const float *wp = win + (warp * ZB + d.row_off) * 32 + lane;
-        const float4 *tp = reinterpret_cast<const float4 *>(tap_sm + d.tap_off);
-        float ring[RING], acc[ZB];
+    // TMA window of one chunk (elected thread)
+    auto issue_window = [&](int chunk, int stage) {
+        float *dst = smem + stage * stage_floats;
+        mbar_expect_tx(&bars[stage], stage_bytes);
+        const int zbase = chunk * (NW * ZB) + woff_min;
+        for (int b = 0; b < nbox; ++b) {
+            tma_load_3d(dst + b * box_rows * 32, &num_map, &bars[stage], x0, y, zbase + b * box_rows);
+            if (PERVOXEL)
+                tma_load_3d(dst + (win_rows + b * box_rows) * 32, &den_map, &bars[stage], x0, y, zbase + b * box_rows);
+        }
+    };
+    // per-warp side inputs of one chunk: its ZB mask rows and its nprof denominator rows (cp.async)
+    auto issue_side = [&](int chunk, int stage) {
+        const int z0 = chunk * (NW * ZB) + warp * ZB;
+        if (stage_mask && mask) {
+            uint8_t *dst = mask_sm + ((stage * NW + warp) * ZB) * 32;
 #pragma unroll
-        for (int t = 0; t < ZB + U - 1; ++t) ring[t] = wp[t * 32];
-#pragma unroll
-        for (int i = 0; i < ZB; ++i) acc[i] = 0.f;
-#pragma unroll 1
-        for (int qb = 0; qb < d.nchunks; qb += PERIOD) {
-#pragma unroll
-            for (int qq = 0; qq < PERIOD; ++qq) {
-                if (qb + qq < d.nchunks) {
-                    const float4 e = tp[qq];
-#pragma unroll
-                    for (int ii = 0; ii < U; ++ii)
-                        ring[(U * qq + ZB + U - 1 + ii) % RING] = wp[(U * qq + ZB + U - 1 + ii) * 32];
-                    const float ev[U] = {e.x, e.y, e.z, e.w};
-#pragma unroll
-                    for (int ii = 0; ii < U; ++ii)
-#pragma unroll
-                        for (int i = 0; i < ZB; ++i)
-                            acc[i] = fmaf(ev[ii], ring[(U * qq + i + ii) % RING], acc[i]);
+            for (int j = 0; j < (ZB * 2 + 31) / 32; ++j) {
+                const int c = lane + 32 * j, row = c >> 1, half = c & 1;
+                if (row < ZB) {
+                    const bool ok = z0 + row < nz && x0 + 16 * half < nx;
+                    const uint8_t *src = ok ? mask + ((size_t)(z0 + row) * ny + y) * nx + x0 + 16 * half : mask;
+                    cp_async16(dst + row * 32 + 16 * half, src, ok);
                 }
             }
-            wp += PERIOD * U * 32;
-            tp += PERIOD;
         }
+        if (rs_staged && z0 < nz) {
+            float *dst = rs_sm + (size_t)(stage * NW + warp) * nprof * ZB;
+            const float *src = rs + (size_t)cls_base * nzp + z0;
+            for (int c = lane; c < nprof * (ZB / 4); c += 32) {
+                const int k = c / (ZB / 4), part = c - k * (ZB / 4);
+                cp_async16(dst + k * ZB + 4 * part, src + (size_t)k * ncls * nzp + 4 * part, true);
+            }
+        }
+    };
 
-        if (PERVOXEL) {
-            // per-voxel denominator: same ring walk over the norm window with squared taps
-            const float *dp = win_den + (warp * ZB + d.row_off) * 32 + lane;
-            const float4 *tq = reinterpret_cast<const float4 *>(tap_sq_sm + d.tap_off);
-            float den[ZB];
+    int chunk = blockIdx.z;
+    if (chunk < nchunk) {
+        if (threadIdx.x == 0) issue_window(chunk, 0);
+        issue_side(chunk, 0);
+    }
+
+    uint32_t phase_bits = 0;
+    for (int it = 0; chunk < nchunk; chunk += gridDim.z, ++it) {
+        const int stage = it & 1;
+        const int next = chunk + gridDim.z;
+        cp_async_wait_all();  // this chunk's side inputs (issued one iteration ago) have landed
+        __syncwarp();
+        if (next < nchunk) {
+            if (threadIdx.x == 0) issue_window(next, stage ^ 1);
+            issue_side(next, stage ^ 1);
+        }
+        mbar_wait(&bars[stage], (phase_bits >> stage) & 1u);
+        phase_bits ^= 1u << stage;
+
+        const float *win = smem + stage * stage_floats;
+        const float *win_den = win + win_rows * 32;
+        const int z0 = chunk * (NW * ZB) + warp * ZB;
+        if (z0 < nz) {
+            float mx[ZB], mn[ZB];
+            int arg[ZB];
 #pragma unroll
-            for (int t = 0; t < ZB + U - 1; ++t) ring[t] = dp[t * 32];
-#pragma unroll
-            for (int i = 0; i < ZB; ++i) den[i] = 0.f;
+            for (int i = 0; i < ZB; ++i) { mx[i] = -INFINITY; mn[i] = INFINITY; arg[i] = 0; }
+            const float *rs_col = PERVOXEL ? nullptr : rs + (size_t)cls_base * nzp + z0;
+            const float *rs_warp = rs_sm + (size_t)(stage * NW + warp) * nprof * ZB;
+
 #pragma unroll 1
-            for (int qb = 0; qb < d.nchunks; qb += PERIOD) {
+            for (int k = 0; k < nprof; ++k) {
+                const ProfDesc d = desc[k];
+                float acc[ZB];
+                ring_correlate<ZB>(win + (warp * ZB + d.row_off) * 32 + lane,
+                                   reinterpret_cast<const float4 *>(tap_sm + d.tap_off), d.nchunks, acc);
+                if (PERVOXEL) {
+                    float den[ZB];
+                    ring_correlate<ZB>(win_den + (warp * ZB + d.row_off) * 32 + lane,
+                                       reinterpret_cast<const float4 *>(tap_sq_sm + d.tap_off), d.nchunks, den);
 #pragma unroll
-                for (int qq = 0; qq < PERIOD; ++qq) {
-                    if (qb + qq < d.nchunks) {
-                        const float4 e = tq[qq];
+                    for (int i = 0; i < ZB; ++i) acc[i] = den[i] > 0.f ? acc[i] / sqrtf(den[i]) : 0.f;
+                } else if (rs_staged) {
+                    const float4 *rp = reinterpret_cast<const float4 *>(rs_warp + k * ZB);  // broadcast LDS.128
 #pragma unroll
-                        for (int ii = 0; ii < U; ++ii)
-                            ring[(U * qq + ZB + U - 1 + ii) % RING] = dp[(U * qq + ZB + U - 1 + ii) * 32];
-                        const float ev[U] = {e.x, e.y, e.z, e.w};
+                    for (int i = 0; i < ZB / 4; ++i) {
+                        const float4 r = rp[i];
+                        acc[4 * i] *= r.x; acc[4 * i + 1] *= r.y; acc[4 * i + 2] *= r.z; acc[4 * i + 3] *= r.w;
+                    }
+                } else {
+                    const float4 *rp = reinterpret_cast<const float4 *>(rs_col + (size_t)k * ncls * nzp);
 #pragma unroll
-                        for (int ii = 0; ii < U; ++ii)
-#pragma unroll
-                            for (int i = 0; i < ZB; ++i)
-                                den[i] = fmaf(ev[ii], ring[(U * qq + i + ii) % RING], den[i]);
+                    for (int i = 0; i < ZB / 4; ++i) {
+                        const float4 r = __ldg(rp + i);
+                        acc[4 * i] *= r.x; acc[4 * i + 1] *= r.y; acc[4 * i + 2] *= r.z; acc[4 * i + 3] *= r.w;
                     }
                 }
-                dp += PERIOD * U * 32;
-                tq += PERIOD;
+#pragma unroll
+                for (int i = 0; i < ZB; ++i) {
+                    const float t = acc[i];
+                    arg[i] = t > mx[i] ? k : arg[i];
+                    mx[i] = fmaxf(mx[i], t);
+                    mn[i] = fminf(mn[i], t);
+                }
             }
-#pragma unroll
-            for (int i = 0; i < ZB; ++i) acc[i] = den[i] > 0.f ? acc[i] / sqrtf(den[i]) : 0.f;
-        } else {
-            const float4 *rp = reinterpret_cast<const float4 *>(rs_col + (size_t)k * ncls * nzp);
-#pragma unroll
-            for (int i = 0; i < ZB / 4; ++i) {
-                float4 r = __ldg(rp + i);
-                acc[4 * i] *= r.x; acc[4 * i + 1] *= r.y; acc[4 * i + 2] *= r.z; acc[4 * i + 3] *= r.w;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < ZB; ++i) {
-            const float t = acc[i];
-            arg[i] = t > mx[i] ? k : arg[i];
-            mx[i] = fmaxf(mx[i], t);
-            mn[i] = fminf(mn[i], t);
-        }
-    }
 
-    if (x >= nx) return;
-    float cmax = -INFINITY, cmin = INFINITY;
+            if (x < nx) {
+                // mask bits of this thread's ZB voxels
+                uint32_t mbits = 0;
+                if (mask) {
+                    if (stage_mask) {
+                        const uint8_t *mrow = mask_sm + ((stage * NW + warp) * ZB) * 32 + lane;
 #pragma unroll
-    for (int i = 0; i < ZB; ++i) {
-        const int z = z0 + i;
-        if (z < nz) {
-            const size_t o = ((size_t)z * ny + y) * nx + x;
-            float c = mx[i];
-            int a = arg[i];
-            if (mask && mask[o]) { c = 0.f; a = 0; }
-            if (correl) correl[o] = c;
-            if (correl_min) correl_min[o] = mn[i];
-            if (profile) profile[o] = (uint8_t)a;
-            cmax = fmaxf(cmax, c);
-            cmin = fminf(cmin, mn[i]);
+                        for (int i = 0; i < ZB; ++i) mbits |= (mrow[i * 32] ? 1u : 0u) << i;
+                    } else {
+                        uint8_t mv[ZB];
+#pragma unroll
+                        for (int i = 0; i < ZB; ++i)
+                            mv[i] = (z0 + i < nz) ? mask[((size_t)(z0 + i) * ny + y) * nx + x] : (uint8_t)0;
+#pragma unroll
+                        for (int i = 0; i < ZB; ++i) mbits |= (mv[i] ? 1u : 0u) << i;
+                    }
+                }
+                float cmax = -INFINITY, cmin = INFINITY;
+#pragma unroll
+                for (int i = 0; i < ZB; ++i) {
+                    const int z = z0 + i;
+                    if (z < nz) {
+                        const size_t o = ((size_t)z * ny + y) * nx + x;
+                        const bool masked = (mbits >> i) & 1u;
+                        const float c = masked ? 0.f : mx[i];
+                        if (correl) correl[o] = c;
+                        if (correl_min) correl_min[o] = mn[i];
+                        if (profile) profile[o] = masked ? (uint8_t)0 : (uint8_t)arg[i];
+                        cmax = fmaxf(cmax, c);
+                        cmin = fminf(cmin, mn[i]);
+                    }
+                }
+                if (maxmap) atomic_max_float(maxmap + (size_t)y * nx + x, cmax);
+                if (minmap) atomic_min_float(minmap + (size_t)y * nx + x, cmin);
+            }
         }
+        __syncthreads();  // the stage is free again before the next iteration refills it
     }
-    if (maxmap) atomic_max_float(maxmap + (size_t)y * nx + x, cmax);
-    if (minmap) atomic_min_float(minmap + (size_t)y * nx + x, cmin);
 }
 }  // namespace k2
 
@@ -523,7 +616,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     CUtensorMapFloatOOBfill);
 
 static int make_tile_map(ogn_ctx *ctx, CUtensorMap *map, const float *base, int nz, int ny, int nx, int pitch,
-                         int box_x, int box_y) {
+                         int box_x, int box_y, int box_z = 1) {
     static PFN_encodeTiled encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -535,7 +628,7 @@ static int make_tile_map(ogn_ctx *ctx, CUtensorMap *map, const float *base, int 
     }
     cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
     cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)ny * pitch * 4};
-    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, (cuuint32_t)box_z};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -618,6 +711,7 @@ static int run_fsf_stage(ogn_ctx *ctx, const float *cube, const double *const *f
         OGN_CUDA(cudaMemsetAsync(normcls, 0, (size_t)ncy * ncx * nzp * sizeof(double), ctx->stream));
     }
     {
+        ogn_timer t_(ctx, "fsf_prep");
         dim3 grid(nz, nf);
         size_t sm = ((size_t)P * P + 32) * sizeof(double);
         fsf_prep_kernel<<<grid, 256, sm, ctx->stream>>>(fsf_tab, nz, P, WP, pl.w32, pl.w32sq, normcls, nzp, ny, nx,
@@ -631,6 +725,7 @@ static int run_fsf_stage(ogn_ctx *ctx, const float *cube, const double *const *f
     if (pl.pervoxel) OGN_TRY(ogn_scratch_t(ctx, "norm_fsf", vol_p, &pl.norm_fsf));
 
     const bool aligned = (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(cube) & 15) == 0);
+    ogn_timer t_k1(ctx, "k1_fsf_correlate");
     for (int f = 0; f < nf; ++f) {
         const float *in = cube;
         int ipitch = nx;
@@ -705,23 +800,40 @@ extern "C" int ogn_fsf_stage(ogn_ctx *ctx, const void *cube, int cube_dtype, int
 
 template <int ZB, bool PV>
 static int launch_spectral(ogn_ctx *ctx, const TglrPlan &pl, const float *taps, const float *taps_sq,
-                           int ntaps_total, const k2::ProfDesc *desc, int win_rows, int woff_min, const float *rs,
+                           int ntaps_total, const k2::ProfDesc *desc, int reach, int woff_min, const float *rs,
                            int nzp, int ncls, int ncx, const uint8_t *mask, float *correl, float *correl_min,
                            uint8_t *profile, float *maxmap, float *minmap) {
     auto kern = k2::spectral_glr_kernel<ZB, PV>;
-    const size_t smem = ((size_t)(PV ? 2 : 1) * win_rows * 32 + (size_t)(PV ? 2 : 1) * ntaps_total) * sizeof(float);
-    if (smem > 200 * 1024)
+    // window rows per chunk: the chunk itself, the longest profile, and the ring's read-ahead
+    const int need_rows = k2::NW * ZB + reach + 2 * k2::U;
+    const int nbox = ogn_div_up(need_rows, k2::MAX_BOX_ROWS);
+    const int box_rows = ogn_div_up(need_rows, nbox);
+    const int win_rows = nbox * box_rows;
+    size_t smem = ((size_t)2 * (PV ? 2 : 1) * win_rows * 32 + (size_t)(PV ? 2 : 1) * (ntaps_total + 4)) * sizeof(float) + 16;
+    if (smem > 110 * 1024)
         return ogn_fail(ctx, OGN_ERR_UNSUPPORTED,
-                        "profile dictionary needs %zu bytes of shared memory per block (limit 200 KiB)", smem);
+                        "profile dictionary needs %zu bytes of shared memory per block (limit 110 KiB)", smem);
+    // optional per-warp staging of the mask rows (needs 16-byte aligned rows) and of the denominator rows
+    const int stage_mask = mask && pl.nx % 16 == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0;
+    if (stage_mask) smem += (size_t)2 * k2::NW * ZB * 32;
+    const size_t rs_bytes = (size_t)2 * k2::NW * pl.nprof * ZB * sizeof(float);
+    const int stage_rs = !PV && smem + rs_bytes <= 110 * 1024;
+    if (stage_rs) smem += rs_bytes;
     OGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int nzb = ogn_div_up(pl.nz, ZB);
-    dim3 grid(pl.pitch / 32, pl.ny, ogn_div_up(nzb, k2::NW));
-    if (grid.y > 65535 || grid.z > 65535)
-        return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "cube too large for the K2 launch grid");
-    kern<<<grid, k2::NW * 32, smem, ctx->stream>>>(pl.cube_fsf, pl.norm_fsf, pl.nz, pl.ny, pl.nx, pl.pitch, taps,
-                                                   taps_sq, ntaps_total, desc, pl.nprof, win_rows, woff_min, rs, nzp,
-                                                   ncls, ncx, pl.ny, pl.nx, pl.P, mask, correl, correl_min, profile,
-                                                   maxmap, minmap);
+    CUtensorMap num_map, den_map;
+    OGN_TRY(make_tile_map(ctx, &num_map, pl.cube_fsf, pl.nz, pl.ny, pl.nx, pl.pitch, 32, 1, box_rows));
+    if (PV) OGN_TRY(make_tile_map(ctx, &den_map, pl.norm_fsf, pl.nz, pl.ny, pl.nx, pl.pitch, 32, 1, box_rows));
+    else den_map = num_map;
+    const int nchunk = ogn_div_up(pl.nz, k2::NW * ZB);
+    const int cols = (pl.pitch / 32) * pl.ny;
+    // enough blocks for ~8 waves of 2 resident blocks per SM, at most one block per chunk
+    int zsplit = ogn_div_up((int64_t)ctx->sm_count * 2 * 8, cols);
+    zsplit = std::max(1, std::min(zsplit, nchunk));
+    dim3 grid(pl.pitch / 32, pl.ny, zsplit);
+    if (grid.y > 65535) return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "cube too large for the K2 launch grid");
+    kern<<<grid, k2::NW * 32, smem, ctx->stream>>>(num_map, den_map, pl.nz, pl.ny, pl.nx, taps, taps_sq, ntaps_total,
+                                                   desc, pl.nprof, box_rows, nbox, woff_min, rs, nzp, ncls, ncx, pl.P,
+                                                   stage_rs, stage_mask, mask, correl, correl_min, profile, maxmap, minmap);
     OGN_LAUNCH_CHECK("spectral_glr_kernel");
     return OGN_OK;
 }
@@ -770,7 +882,6 @@ extern "C" int ogn_tglr(ogn_ctx *ctx, const void *cube, int cube_dtype, int nz, 
         desc[k].row_off -= woff_min;
         reach = std::max(reach, desc[k].row_off + desc[k].nchunks * k2::U);
     }
-    const int win_rows = k2::NW * ZB + reach + 2 * k2::U;
     const int ntaps_total = (int)tp.size();
 
     float *d_taps = nullptr, *d_taps_sq = nullptr;
@@ -808,6 +919,7 @@ extern "C" int ogn_tglr(ogn_ctx *ctx, const void *cube, int cube_dtype, int nz, 
     float *rs = nullptr;
     if (!pl.pervoxel) {
         OGN_TRY(ogn_scratch_t(ctx, "rs", (size_t)nprof * ncy * ncx * nzp, &rs));
+        ogn_timer t_(ctx, "den_table");
         dim3 grid(ogn_div_up(nzp, 128), ncy * ncx, nprof);
         den_table_kernel<<<grid, 128, 0, ctx->stream>>>(normcls, nz, nzp, ncy * ncx, d_taps64, d_tapoff, nprof, rs);
         OGN_LAUNCH_CHECK("den_table_kernel");
@@ -828,15 +940,19 @@ extern "C" int ogn_tglr(ogn_ctx *ctx, const void *cube, int cube_dtype, int nz, 
         fill_f32_kernel<<<ogn_div_up(img, 256), 256, 0, ctx->stream>>>((float *)d_minmap, img, INFINITY);
         OGN_LAUNCH_CHECK("fill_f32_kernel");
     }
+    ogn_timer *t_k2 = new ogn_timer(ctx, "k2_spectral_glr");
+    int rc_k2;
     if (pl.pervoxel)
-        OGN_TRY((launch_spectral<16, true>(ctx, pl, d_taps, d_taps_sq, ntaps_total, d_desc,
-                                            k2::NW * 16 + reach + 2 * k2::U, woff_min, nullptr, nzp, 0, 0, dmask,
+        rc_k2 = (launch_spectral<16, true>(ctx, pl, d_taps, d_taps_sq, ntaps_total, d_desc, reach, woff_min, nullptr,
+                                            nzp, 0, 0, dmask,
                                             (float *)d_correl, (float *)d_cmin, (uint8_t *)d_prof,
-                                            (float *)d_maxmap, (float *)d_minmap)));
+                                            (float *)d_maxmap, (float *)d_minmap));
     else
-        OGN_TRY((launch_spectral<ZB, false>(ctx, pl, d_taps, d_taps_sq, ntaps_total, d_desc, win_rows, woff_min, rs,
+        rc_k2 = (launch_spectral<ZB, false>(ctx, pl, d_taps, d_taps_sq, ntaps_total, d_desc, reach, woff_min, rs,
                                              nzp, ncy * ncx, ncx, dmask, (float *)d_correl, (float *)d_cmin,
-                                             (uint8_t *)d_prof, (float *)d_maxmap, (float *)d_minmap)));
+                                             (uint8_t *)d_prof, (float *)d_maxmap, (float *)d_minmap));
+    delete t_k2;
+    OGN_TRY(rc_k2);
 
     OGN_TRY(ogn_output_commit(ctx, correl, d_correl, vol * 4));
     OGN_TRY(ogn_output_commit(ctx, correl_min, d_cmin, vol * 4));

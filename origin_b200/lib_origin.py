@@ -21,7 +21,7 @@ from ._lib import OGN_F32, OGN_F64, OgnError, default_context, ptr
 
 __all__ = ['DCTMAT', 'dct_residual', 'O2test', 'Correlation_GLR_test', 'compute_local_max',
            'Compute_threshold_purity', 'prepare_profiles', 'tglr', 'local_extrema', 'LocalExtrema',
-           'purity_counts', 'threshold_rows', 'preprocess', 'PurityTable']
+           'purity_counts', 'threshold_rows', 'preprocess', 'PurityTable', 'step05', 'fsf_stage']
 
 
 # --------------------------------------------------------------------------
@@ -101,6 +101,13 @@ def _f64_host(x):
     return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
 
 
+def _f64_any(x):
+    """float64 C-contiguous array on the host, or tensor left on its CUDA device."""
+    if _is_torch(x) and x.is_cuda:
+        return x.double().contiguous()
+    return _f64_host(x)
+
+
 class _PtrArray:
     """ctypes array of raw addresses (``const double *const *``), keeping the
     referenced arrays alive."""
@@ -108,7 +115,7 @@ class _PtrArray:
     def __init__(self, arrays):
         import ctypes
         self.keep = list(arrays)
-        self.arr = (ctypes.c_void_p * len(self.keep))(*[a.ctypes.data for a in self.keep])
+        self.arr = (ctypes.c_void_p * len(self.keep))(*[ptr(a) for a in self.keep])
 
     @property
     def address(self):
@@ -228,32 +235,9 @@ def tglr(cube, fsf, weights, profiles, mask=None, pcut=None, pmeansub=True, want
     """``Correlation_GLR_test`` fused with the masking / maxmap / minmap glue
     of ``ComputeTGLR.run`` (reference steps.py:781-793).  Returns a dict with
     the requested products."""
-    cube = _as_float_cube(cube)
-    if cube.ndim != 3:
-        raise ValueError('cube must be (nz, ny, nx)')
+    cube, fsfs, fsf_ptrs, w_ptrs, taps, offs, nprof, m = _tglr_args(cube, fsf, weights, profiles, mask, pcut, pmeansub)
     nz, ny, nx = cube.shape
-    if weights is None:                         # one FSF (lib_origin.py:1112-1114)
-        fsfs, wmaps = [fsf], None
-    else:
-        fsfs, wmaps = list(fsf), list(weights)
-        if len(fsfs) != len(wmaps):
-            raise ValueError('fsf and weights must have the same length')
-    fsfs = [_f64_host(f) for f in fsfs]
-    for f in fsfs:
-        if f.ndim != 3 or f.shape[0] != nz or f.shape[1] != f.shape[2]:
-            raise ValueError('each FSF must be (nz, P, P), got %r' % (f.shape,))
     psize = fsfs[0].shape[1]
-    fsf_ptrs = _PtrArray(fsfs)
-    w_ptrs = None
-    if wmaps is not None:
-        wmaps = [_f64_host(w) for w in wmaps]
-        for w in wmaps:
-            if w.shape != (ny, nx):
-                raise ValueError('weight maps must be (ny, nx)')
-        w_ptrs = _PtrArray(wmaps)
-    prof_cut = prepare_profiles(profiles, pcut, pmeansub)
-    taps, offs = _pack_profiles(prof_cut)
-    m = _as_u8(mask)
     ctx = _ctx_for(cube, ctx)
     out = {}
     if 'correl' in want:
@@ -268,10 +252,98 @@ def tglr(cube, fsf, weights, profiles, mask=None, pcut=None, pmeansub=True, want
         out['minmap'] = _empty_like_kind(cube, (ny, nx), np.float32)
     ctx.check(ctx.lib.ogn_tglr(
         ctx.handle, ptr(cube), _dtype_code(cube), nz, ny, nx, len(fsfs), fsf_ptrs.address, psize,
-        w_ptrs.address if w_ptrs else None, ptr(taps), ptr(offs), len(prof_cut), ptr(m),
+        w_ptrs.address if w_ptrs else None, ptr(taps), ptr(offs), nprof, ptr(m),
         ptr(out.get('correl')), ptr(out.get('correl_min')), ptr(out.get('profile')),
         ptr(out.get('maxmap')), ptr(out.get('minmap'))))
     return out
+
+
+def _tglr_args(cube, fsf, weights, profiles, mask, pcut, pmeansub):
+    """Validated, C-ready arguments shared by :func:`tglr` and :func:`step05`."""
+    cube = _as_float_cube(cube)
+    if cube.ndim != 3:
+        raise ValueError('cube must be (nz, ny, nx)')
+    nz, ny, nx = cube.shape
+    if weights is None:                         # one FSF (lib_origin.py:1112-1114)
+        fsfs, wmaps = [fsf], None
+    else:
+        fsfs, wmaps = list(fsf), list(weights)
+        if len(fsfs) != len(wmaps):
+            raise ValueError('fsf and weights must have the same length')
+    fsfs = [_f64_any(f) for f in fsfs]
+    for f in fsfs:
+        if f.ndim != 3 or f.shape[0] != nz or f.shape[1] != f.shape[2]:
+            raise ValueError('each FSF must be (nz, P, P), got %r' % (tuple(f.shape),))
+    fsf_ptrs = _PtrArray(fsfs)
+    w_ptrs = None
+    if wmaps is not None:
+        wmaps = [_f64_any(w) for w in wmaps]
+        for w in wmaps:
+            if tuple(w.shape) != (ny, nx):
+                raise ValueError('weight maps must be (ny, nx)')
+        w_ptrs = _PtrArray(wmaps)
+    prof_cut = prepare_profiles(profiles, pcut, pmeansub)
+    taps, offs = _pack_profiles(prof_cut)
+    return cube, fsfs, fsf_ptrs, w_ptrs, taps, offs, len(prof_cut), _as_u8(mask)
+
+
+def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True, out=None, dense=False,
+           capacity=None, want=('correl', 'profile', 'correl_min', 'maxmap', 'minmap'), ctx=None):
+    """The array part of ``ComputeTGLR.run`` (reference steps.py:768-802) in one
+    device pass: TGLR, masking, maxmap / minmap and the local extrema.
+
+    ``out`` may hold preallocated arrays (e.g. pinned host buffers from
+    :func:`origin_b200._lib.pinned_empty`) for ``correl, correl_min, profile,
+    maxmap, minmap, max_index, max_value, min_index, min_value``.
+    Returns a dict with the products in ``want`` plus ``extrema``
+    (:class:`LocalExtrema`) and, when ``dense``, ``cube_local_max`` /
+    ``cube_local_min``.
+    """
+    cube, fsfs, fsf_ptrs, w_ptrs, taps, offs, nprof, m = _tglr_args(cube, fsf, weights, profiles, mask, pcut, pmeansub)
+    if np.isscalar(size):
+        size = (size, size, size)
+    size = tuple(int(s) for s in size)
+    if any(s < 1 or s % 2 == 0 for s in size):
+        raise ValueError('only odd window sizes are supported, got %r' % (size,))
+    nz, ny, nx = cube.shape
+    vol = nz * ny * nx
+    ctx = _ctx_for(cube, ctx)
+    out = dict(out or {})
+    res = {}
+    shapes = dict(correl=(cube.shape, np.float32), correl_min=(cube.shape, np.float32), profile=(cube.shape, np.uint8),
+                  maxmap=((ny, nx), np.float32), minmap=((ny, nx), np.float32))
+    for key, (shape, dt) in shapes.items():
+        if key in want:
+            res[key] = out.get(key)
+            if res[key] is None:
+                res[key] = _empty_like_kind(cube, shape, dt)
+    if dense:
+        res['cube_local_max'] = _empty_like_kind(cube, cube.shape, np.float32)
+        res['cube_local_min'] = _empty_like_kind(cube, cube.shape, np.float32)
+    if capacity is None:
+        capacity = len(out['max_index']) if out.get('max_index') is not None else max(4096, vol // 40)
+    counts = np.zeros(2, dtype=np.int64)
+    while True:
+        lists = {}
+        for key, dt in (('max_index', np.int64), ('max_value', np.float32), ('min_index', np.int64),
+                        ('min_value', np.float32)):
+            buf = out.get(key)
+            lists[key] = buf if buf is not None and len(buf) >= capacity else _empty_like_kind(cube, (capacity,), dt)
+        rc = ctx.check(ctx.lib.ogn_step05(
+            ctx.handle, ptr(cube), _dtype_code(cube), nz, ny, nx, len(fsfs), fsf_ptrs.address, fsfs[0].shape[1],
+            w_ptrs.address if w_ptrs else None, ptr(taps), ptr(offs), nprof, ptr(m), size[0], size[1], size[2],
+            ptr(res.get('correl')), ptr(res.get('correl_min')), ptr(res.get('profile')), ptr(res.get('maxmap')),
+            ptr(res.get('minmap')), ptr(res.get('cube_local_max')), ptr(res.get('cube_local_min')),
+            ptr(lists['max_index']), ptr(lists['max_value']), ptr(lists['min_index']), ptr(lists['min_value']),
+            capacity, ptr(counts)), allow_overflow=True)
+        if rc == 0:
+            break
+        capacity = int(counts.max())
+        out = {k: v for k, v in out.items() if k not in lists}
+    n1, n0 = int(counts[0]), int(counts[1])
+    res['extrema'] = LocalExtrema(cube.shape, lists['max_index'][:n1], lists['max_value'][:n1],
+                                  lists['min_index'][:n0], lists['min_value'][:n0])
+    return res
 
 
 def Correlation_GLR_test(cube, fsf, weights, profiles, nthreads=1, pcut=None, pmeansub=True, out_dtype=np.float32,
@@ -464,18 +536,36 @@ def purity_counts(ext, segmask, thresholds, ctx=None):
     return n1, n0
 
 
+class _DeviceCounter:
+    """Default backend of :func:`Compute_threshold_purity`: the K4 kernels."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def stats(self, ext, segmask):
+        return purity_stats(ext, segmask, self.ctx)
+
+    def counts(self, ext, segmask, thresholds):
+        return purity_counts(ext, segmask, thresholds, self.ctx)
+
+
 def Compute_threshold_purity(purity, cube_local_max, cube_local_min, segmap=None, threshlist=None, allreduce=None,
-                             ctx=None):
+                             ctx=None, _backend=None):
     """Threshold for a target purity (reference lib_origin.py:1391-1479).
 
     ``cube_local_max`` may be the dense cube, as in the reference, or a
     :class:`LocalExtrema` (then ``cube_local_min`` is ignored).  Returns
-    ``(threshold, table)``.  ``allreduce`` (multi-GPU) is an object with
-    ``max(scalars) -> scalars``, ``max_image(img)`` and ``sum(int64 array)``
-    that combines tile-local statistics across ranks; the spatial size used for
-    L1/L0 is then the global one it reports via ``allreduce.sum``.
+    ``(threshold, table)``.
+
+    Multi-GPU: every rank passes the extrema of the voxels it owns (global
+    shape, global linear indices) and the global ``segmap``; ``allreduce`` is
+    an object with ``sum(int64 array)``, ``max(float64 array)`` and
+    ``max_image(float32 image)`` (see :mod:`origin_b200.distributed`) that
+    combines the tile-local statistics and the per-threshold counts — the
+    purity "histograms" — across ranks, so every rank returns the same result.
     """
     ext = _as_extrema(cube_local_max, cube_local_min)
+    backend = _backend or _DeviceCounter(ctx)
     nz, ny, nx = ext.shape
     vol = nz * ny * nx
     l1 = ny * nx                                           # lib_origin.py:1424
@@ -483,36 +573,36 @@ def Compute_threshold_purity(purity, cube_local_max, cube_local_min, segmap=None
     if segmap is not None:
         segmap = segmap.detach().cpu().numpy() if _is_torch(segmap) else np.asarray(segmap)
         segmask = segmap != 0                              # complement of :1428
-        l0 = int(np.count_nonzero(~segmask))
+        l0 = int(np.count_nonzero(~segmask))               # :1431
     else:
         l0 = l1
-    if allreduce is not None:
-        l1, l0 = (int(v) for v in allreduce.sum(np.array([l1, l0], dtype=np.int64)))
     n_max, n_min = ext.counts
+    if allreduce is not None:
+        n_max, n_min = (int(v) for v in allreduce.sum(np.array([n_max, n_min], dtype=np.int64)))
     if threshlist is None:
-        mx_max, mx_min, spmax = purity_stats(ext, segmask, ctx)
+        mx_max, mx_min, spmax = backend.stats(ext, segmask)
+        if allreduce is not None:
+            mx_max, mx_min = (float(v) for v in allreduce.max(np.array([mx_max, mx_min], dtype=np.float64)))
+            spmax = allreduce.max_image(spmax)
         # the dense cubes hold 0 wherever a voxel is not an extremum (:1247, :1254)
         if n_max < vol:
             mx_max = max(mx_max, 0.0)
         if n_min < vol or segmask is not None:
             mx_min = max(mx_min, 0.0)
-        if allreduce is not None:
-            mx_max, mx_min = allreduce.max([mx_max, mx_min])
-            spmax = allreduce.gather_image(spmax)
         threshmax = min(mx_min, mx_max)                    # :1437
-        threshmin = float(np.median(spmax.astype(np.float64))) * 1.1   # :1438
+        threshmin = float(np.median(np.asarray(spmax, dtype=np.float64))) * 1.1   # :1438
         threshlist = np.linspace(threshmin, threshmax, 50)  # :1439
     else:
         threshlist = np.asarray(threshlist, dtype=np.float64)
-    n1, n0 = purity_counts(ext, segmask, threshlist, ctx)
+    n1, n0 = backend.counts(ext, segmask, threshlist)
+    if allreduce is not None:
+        both = allreduce.sum(np.concatenate([n1, n0]).astype(np.int64))
+        n1, n0 = both[:len(n1)], both[len(n1):]
     # zeros of the dense cubes count for negative thresholds
     neg = threshlist < 0
     if neg.any():
         n1 = n1 + neg * (vol - n_max)
         n0 = n0 + neg * (vol - n_min)
-    if allreduce is not None:
-        n1 = allreduce.sum(n1)
-        n0 = allreduce.sum(n0)
     n0 = n0 * (l1 / l0)                                    # :1451
     with np.errstate(divide='ignore', invalid='ignore'):
         est_purity = 1 - n0 / n1                           # :1453

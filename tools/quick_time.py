@@ -15,6 +15,8 @@ fsf = synthetic.moffat_fsf(shape[0])
 g = torch.Generator(device='cuda').manual_seed(0)
 cube = torch.randn(shape, device='cuda', dtype=torch.float32, generator=g)
 mask = (torch.rand(shape, device='cuda', generator=g) < 0.01).to(torch.uint8)
+ctx = lib_origin.default_context()
+ctx.timing(True)
 for name, profs in (('3FWHM', dictionaries.dico_3fwhm()[0]), ('2_12', dictionaries.dico_fwhm_2_12()[0])):
     for r in range(reps):
         torch.cuda.synchronize()
@@ -28,3 +30,4 @@ for name, profs in (('3FWHM', dictionaries.dico_3fwhm()[0]), ('2_12', dictionari
         v = shape[0] * shape[1] * shape[2] * len(profs)
         print('%s rep %d: tglr %.2f ms  extrema %.2f ms  -> %.1f Gvoxel.profiles/s (tglr only)  lists %s' % (
             name, r, e0.elapsed_time(e1), e1.elapsed_time(e2), v / e0.elapsed_time(e1) / 1e6, ext.counts), flush=True)
+        print('   stages:', ' '.join('%s=%.3f' % kv for kv in ctx.timing_report()), flush=True)
