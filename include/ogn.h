@@ -225,7 +225,9 @@ OGN_API int ogn_dct_residual(ogn_ctx *ctx,
  *
  * begin : continuum fit, data = raw - cont kept on the device, and the
  *         per-wavelength partial sums lambda_sum[nz] / lambda_cnt[nz] (float64,
- *         host or device) of the unmasked data of THIS cube (tile).
+ *         host or device) of the unmasked data of THIS cube (tile).  `owned`
+ *         is NULL or {y0, y1, x0, x1}: only spaxels of that window of the
+ *         given cube enter the sums (a tile's halo belongs to its neighbours).
  * finish: given the global per-wavelength mean, standardise and reduce:
  *         cube_std [nz][ny][nx] f32, cont_dct [nz][ny][nx] f32 (= cont/sqrt(var)),
  *         ima_std, ima_dct, cont_sumsq (= sum_z cont_dct^2), o2map
@@ -234,7 +236,7 @@ OGN_API int ogn_dct_residual(ogn_ctx *ctx,
 OGN_API int ogn_preprocess_begin(ogn_ctx *ctx,
                          const void *raw, const void *var, int in_dtype,
                          const uint8_t *mask, int nz, int ny, int nx,
-                         int order, int approx,
+                         int order, int approx, const int *owned,
                          double *lambda_sum, double *lambda_cnt);
 OGN_API int ogn_preprocess_finish(ogn_ctx *ctx, const double *lambda_mean,
                           float *cube_std, float *cont_dct,

@@ -50,7 +50,7 @@ SIGNATURES = {
     'ogn_dct_residual': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_int]),
     'ogn_preprocess_begin': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
-                                     c_int, c_void_p, c_void_p]),
+                                     c_int, c_void_p, c_void_p, c_void_p]),
     'ogn_preprocess_finish': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
 }

