@@ -262,12 +262,9 @@ def main_gpu(args):
     state = {}
 
     def step():
-        res = lib_origin.step05(cube, fsf, None, profs, mask, 3, 1e-8, True, out=out_dev, ctx=ctx)
-        ext = res['extrema']
-        if world > 1:
-            ext = ogd.owned_extrema(ext, tile, (nz, ny, nx))
-        else:
-            ext = lib_origin.LocalExtrema((nz, ny, nx), ext.max_index, ext.max_value, ext.min_index, ext.min_value)
+        res = lib_origin.step05(cube, fsf, None, profs, mask, 3, 1e-8, True, out=out_dev, ctx=ctx,
+                                tile=(tile, (ny, nx)) if world > 1 else None)
+        ext = res['extrema']                                                      # owned voxels, global indices
         n1, n0 = lib_origin.purity_counts(ext, None, thresholds, ctx)            # step06 counting loop
         if world > 1:
             both = reducer.sum(np.concatenate([n1, n0]))                          # NCCL allreduce of the histograms

@@ -167,6 +167,29 @@ OGN_API int ogn_step05(ogn_ctx *ctx,
                int64_t *min_index, float *min_value,
                int64_t capacity, int64_t *counts);
 
+/* ogn_step05 on one spatial tile of a larger field (multi-GPU runs).  `cube` is
+ * the [nz][ny][nx] sub-cube cut from the field with its halo;
+ *   tile = {gny, gnx, gy0, gx0, oy0, oy1, ox0, ox1}
+ * says that spaxel (0,0) of the sub-cube is spaxel (gy0,gx0) of the gny x gnx
+ * field and that the rank owns rows [oy0,oy1) and columns [ox0,ox1) of the
+ * sub-cube.  Sub-cube edges that are not field edges must lie at least
+ * psize/2 + 1 pixels outside the owned window.  Only the owned window grown by
+ * the extremum radius is computed; the products are sub-cube shaped and valid
+ * on that window; the extremum lists hold the owned voxels with linear indices
+ * of the WHOLE field ([nz][gny][gnx]), so per-rank lists concatenate. */
+OGN_API int ogn_step05_tile(ogn_ctx *ctx,
+                    const void *cube, int cube_dtype, int nz, int ny, int nx,
+                    const int *tile,
+                    int nfields, const double *const *fsf, int psize,
+                    const double *const *weights,
+                    const double *taps, const int *tap_offsets, int nprof,
+                    const uint8_t *mask, int sz, int sy, int sx,
+                    float *correl, float *correl_min, uint8_t *profile,
+                    float *maxmap, float *minmap,
+                    int64_t *max_index, float *max_value,
+                    int64_t *min_index, float *min_value,
+                    int64_t capacity, int64_t *counts);
+
 /* ---- step06: purity threshold counts ------------------------------------ */
 
 /* Statistics Compute_threshold_purity derives its default threshold list from

@@ -63,6 +63,11 @@ extern "C" int ogn_trim(ogn_ctx *ctx) {
         if (kv.second.p) cudaFreeHost(kv.second.p);
     ctx->pins.clear();
     ctx->prep = ogn_prep_state();
+    for (auto e : ctx->events) cudaEventDestroy(e);
+    ctx->events.clear();
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    ctx->h2d_stream = ctx->d2h_stream = nullptr;
     return OGN_OK;
 }
 

@@ -44,6 +44,9 @@ struct ogn_ctx {
     std::map<std::string, ogn_buf> pins;  // named pinned host scratch, grow-only
     bool host_output_pending = false;     // a D2H copy to caller memory was enqueued
     ogn_prep_state prep;
+    // side streams of the streamed host path (created on first use)
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    std::vector<cudaEvent_t> events;
 };
 
 int ogn_fail(ogn_ctx *ctx, int code, const char *fmt, ...);
@@ -122,3 +125,31 @@ int ogn_convert_f32_to_f64(ogn_ctx *ctx, const float *src, double *dst, size_t n
 // Device f32 view [n] of a cube given as host/device f32/f64.
 int ogn_input_cube_f32(ogn_ctx *ctx, const char *name, const void *p, int dtype, size_t n,
                        const float **dev);
+
+// ---- tiled / windowed execution (ogn_tglr.cu, ogn_extrema.cu, ogn_steps.cu) -------------------
+struct ogn_window { int y0, y1, x0, x1; };        // half-open, coordinates of the sub-cube passed in
+struct ogn_place { int gny, gnx, gy0, gx0; };     // where that sub-cube sits in the whole field
+
+struct ogn_tglr_setup_t {
+    int nz = 0, ny = 0, nx = 0, P = 0, WP = 0, nfields = 0, nprof = 0;
+    bool pervoxel = false;
+    ogn_place place{0, 0, 0, 0};
+    float *w32 = nullptr, *w32sq = nullptr, *rs = nullptr;
+    int nzp = 0, ncy = 0, ncx = 0;
+    float *d_taps = nullptr, *d_taps_sq = nullptr;
+    const void *d_desc = nullptr;
+    int ntaps_total = 0, reach = 0, woff_min = 0;
+    std::vector<const double *> w_dev;
+};
+
+int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place, int nfields,
+                   const double *const *fsf, int psize, const double *const *weights, const double *taps,
+                   const int *tap_offsets, int nprof, bool need_spectral, ogn_tglr_setup_t *st);
+int ogn_tglr_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, const float *dcube,
+                    const uint8_t *dmask, ogn_window w, float *d_correl, float *d_cmin, uint8_t *d_prof,
+                    float *d_maxmap, float *d_minmap);
+int ogn_tglr_init_maps(ogn_ctx *ctx, cudaStream_t stream, float *d_maxmap, float *d_minmap, size_t img);
+int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t *mask, int nz, int ny, int nx,
+                    ogn_window owned, ogn_place place, int sz, int sy, int sx, float *dense_max, float *dense_min,
+                    int64_t *max_index, float *max_value, int64_t *min_index, float *min_value, int64_t capacity,
+                    int64_t *counts);

@@ -16,16 +16,17 @@
 // out-of-range part of the window is simply skipped.
 __global__ void local_extrema_kernel(const float *__restrict__ a, const float *__restrict__ b,
                                      const uint8_t *__restrict__ mask, int nz, int ny, int nx, int rz, int ry,
-                                     int rx, float *__restrict__ dense_max, float *__restrict__ dense_min,
+                                     int rx, int oy0, int oy1, int ox0a, int ox0, int ox1,
+                                     float *__restrict__ dense_max, float *__restrict__ dense_min,
                                      uint32_t *__restrict__ flag_max, uint32_t *__restrict__ flag_min, int nxw) {
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = ox0a + blockIdx.x * 32 + threadIdx.x;
+    const int y = oy0 + blockIdx.y * blockDim.y + threadIdx.y;
     const int z = blockIdx.z;
-    if (y >= ny) return;  // whole warp (a warp is one row of 32 x)
+    if (y >= oy1) return;  // whole warp (a warp is one row of 32 x)
     bool keep_a = false, keep_b = false;
     float va = 0.f, vb = 0.f;
     size_t idx = 0;
-    if (x < nx) {
+    if (x >= ox0 && x < ox1) {
         idx = ((size_t)z * ny + y) * nx + x;
         va = a[idx];
         vb = b[idx];
@@ -50,7 +51,7 @@ __global__ void local_extrema_kernel(const float *__restrict__ a, const float *_
     const uint32_t wa = __ballot_sync(0xffffffffu, keep_a);
     const uint32_t wb = __ballot_sync(0xffffffffu, keep_b);
     if (threadIdx.x == 0) {
-        const size_t w = ((size_t)z * ny + y) * nxw + blockIdx.x;
+        const size_t w = ((size_t)z * (oy1 - oy0) + (y - oy0)) * nxw + blockIdx.x;
         flag_max[w] = wa;
         flag_min[w] = wb;
     }
@@ -74,19 +75,21 @@ struct ExPlane {
 
 __global__ void __launch_bounds__(32 * (EX_TY + 2))
 local_extrema3_kernel(const float *__restrict__ a, const float *__restrict__ b, const uint8_t *__restrict__ mask,
-                      int nz, int ny, int nx, float *__restrict__ dense_max, float *__restrict__ dense_min,
+                      int nz, int ny, int nx, int oy0, int oy1, int ox0a, int ox0, int ox1,
+                      float *__restrict__ dense_max, float *__restrict__ dense_min,
                       uint32_t *__restrict__ flag_max, uint32_t *__restrict__ flag_min, int nxw) {
     __shared__ float sa[2][EX_TY + 2][32];
     __shared__ float sb[2][EX_TY + 2][32];
     const int lane = threadIdx.x, row = threadIdx.y;  // row 0 and EX_TY+1 are halo rows
-    const int x0 = blockIdx.x * 32, x = x0 + lane;
-    const int y = blockIdx.y * EX_TY + row - 1;
+    const int x0 = ox0a + blockIdx.x * 32, x = x0 + lane;
+    const int y = oy0 + blockIdx.y * EX_TY + row - 1;
     const int zc0 = blockIdx.z * EX_CZ, zc1 = min(nz, zc0 + EX_CZ);
     const bool row_ok = y >= 0 && y < ny;
     const bool c_ok = row_ok && x < nx;
     const int xe = lane == 0 ? x0 - 1 : x0 + 32;
     const bool e_ok = row_ok && ((lane == 0 && x0 > 0) || (lane == 31 && x0 + 32 < nx));
-    const bool out_row = row >= 1 && row <= EX_TY && y < ny;
+    const bool out_row = row >= 1 && row <= EX_TY && y < oy1;
+    const bool out_col = x >= ox0 && x < ox1;
     const size_t plane = (size_t)ny * nx;
     const size_t oc = (size_t)(row_ok ? y : 0) * nx + (x < nx ? x : 0);
     const size_t oe = (size_t)(row_ok ? y : 0) * nx + (e_ok ? xe : 0);
@@ -129,7 +132,7 @@ local_extrema3_kernel(const float *__restrict__ a, const float *__restrict__ b, 
             const float m9b = fminf(sb[buf][row - 1][lane], fminf(sb[buf][row][lane], sb[buf][row + 1][lane]));
             if (q >= zc0 && q < zc1) {
                 bool keep_a = false, keep_b = false;
-                if (x < nx) {
+                if (out_col) {
                     keep_a = !m_cur && ca_cur == fmaxf(pa_prev, fmaxf(pa_cur, m9a));
                     keep_b = !m_cur && cb_cur == fminf(pb_prev, fminf(pb_cur, m9b));
                     if (dense_max || dense_min) {
@@ -141,7 +144,7 @@ local_extrema3_kernel(const float *__restrict__ a, const float *__restrict__ b, 
                 const uint32_t wa = __ballot_sync(0xffffffffu, keep_a);
                 const uint32_t wb = __ballot_sync(0xffffffffu, keep_b);
                 if (lane == 0) {
-                    const size_t w = ((size_t)q * ny + y) * nxw + blockIdx.x;
+                    const size_t w = ((size_t)q * (oy1 - oy0) + (y - oy0)) * nxw + blockIdx.x;
                     flag_max[w] = wa;
                     flag_min[w] = wb;
                 }
@@ -213,24 +216,32 @@ __global__ void scan_block_offsets_kernel(int64_t *__restrict__ block_tot, int n
 }
 
 // phase 3 (extrema): scatter the set bits of every flag word, in order
+struct ExMap {
+    int ny, nx;            // dims of the arrays the flags were computed on (the sub-cube)
+    int oy0, ony, ox0a;    // flag rows cover y in [oy0, oy0+ony), flag word k starts at x = ox0a + 32 k
+    int gny, gnx, gy0, gx0;  // placement of the sub-cube in the whole field (indices reported globally)
+};
+
 __global__ void scatter_flags_kernel(const uint32_t *__restrict__ flags, size_t nwords,
                                      const int64_t *__restrict__ block_off, const float *__restrict__ src,
-                                     float sign, int nx, int nxw, int64_t *__restrict__ out_index,
+                                     float sign, ExMap m, int nxw, int64_t *__restrict__ out_index,
                                      float *__restrict__ out_value, int64_t capacity) {
     const size_t i = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
     uint32_t w = i < nwords ? flags[i] : 0u;
     int ex = block_exclusive_scan(__popc(w), nullptr);
     if (!w) return;
     int64_t pos = block_off[blockIdx.x] + ex;
-    const size_t rowid = i / nxw;  // z*ny + y
+    const size_t rowid = i / nxw;  // z*ony + (y - oy0)
     const int xw = (int)(i - rowid * nxw);
-    const size_t base = rowid * nx + (size_t)xw * 32;
+    const int z = (int)(rowid / m.ony), y = (int)(rowid - (size_t)z * m.ony) + m.oy0;
+    const size_t lbase = ((size_t)z * m.ny + y) * m.nx + m.ox0a + (size_t)xw * 32;
+    const int64_t gbase = ((int64_t)z * m.gny + (y + m.gy0)) * m.gnx + m.gx0 + m.ox0a + (int64_t)xw * 32;
     while (w) {
         const int bit = __ffs(w) - 1;
         w &= w - 1;
         if (pos < capacity) {
-            out_index[pos] = (int64_t)(base + bit);
-            out_value[pos] = sign * src[base + bit];
+            out_index[pos] = gbase + bit;
+            out_value[pos] = sign * src[lbase + bit];
         }
         ++pos;
     }
@@ -309,7 +320,7 @@ __global__ void threshold_scatter_kernel(const uint32_t *__restrict__ flag, size
 // -------------------------------------------------------------------------------------------
 
 static int compact_flags(ogn_ctx *ctx, const char *tag, const uint32_t *flags, size_t nwords, const float *src,
-                         float sign, int nx, int nxw, int64_t *out_index, float *out_value, int64_t capacity,
+                         float sign, ExMap emap, int nxw, int64_t *out_index, float *out_value, int64_t capacity,
                          int64_t *d_count) {
     const int nblocks = ogn_div_up((int64_t)nwords, SCAN_BLOCK);
     int64_t *block_tot = nullptr;
@@ -320,27 +331,34 @@ static int compact_flags(ogn_ctx *ctx, const char *tag, const uint32_t *flags, s
     scan_block_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(block_tot, nblocks, d_count);
     OGN_LAUNCH_CHECK("scan_block_offsets_kernel");
     if (out_index && out_value && capacity > 0) {
-        scatter_flags_kernel<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, nwords, block_tot, src, sign, nx, nxw,
+        scatter_flags_kernel<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, nwords, block_tot, src, sign, emap, nxw,
                                                                       out_index, out_value, capacity);
         OGN_LAUNCH_CHECK("scatter_flags_kernel");
     }
     return OGN_OK;
 }
 
-extern "C" int ogn_local_extrema(ogn_ctx *ctx, const float *a, const float *b, const uint8_t *mask, int nz, int ny,
-                                 int nx, int sz, int sy, int sx, float *dense_max, float *dense_min,
-                                 int64_t *max_index, float *max_value, int64_t *min_index, float *min_value,
-                                 int64_t capacity, int64_t *counts) {
+// Local extrema of the voxels of `owned` (window of the [nz][ny][nx] sub-cube placed at `place` in
+// the whole field).  Dense products are sub-cube shaped (only the window is written); list
+// indices are linear indices of the whole field.
+int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t *mask, int nz, int ny, int nx,
+                    ogn_window owned, ogn_place place, int sz, int sy, int sx, float *dense_max, float *dense_min,
+                    int64_t *max_index, float *max_value, int64_t *min_index, float *min_value, int64_t capacity,
+                    int64_t *counts) {
     if (!ctx) return OGN_ERR_ARG;
     if (nz <= 0 || ny <= 0 || nx <= 0) return ogn_fail(ctx, OGN_ERR_ARG, "cube shape (%d,%d,%d) is empty", nz, ny, nx);
     if (sz < 1 || sy < 1 || sx < 1 || !(sz & 1) || !(sy & 1) || !(sx & 1))
         return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "window (%d,%d,%d): only odd sizes are supported", sz, sy, sx);
     if (!a || !b) return ogn_fail(ctx, OGN_ERR_ARG, "a / b must not be NULL");
     if (nz > 65535) return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "nz = %d exceeds the launch grid", nz);
+    if (owned.y0 < 0 || owned.x0 < 0 || owned.y1 > ny || owned.x1 > nx || owned.y0 >= owned.y1 || owned.x0 >= owned.x1)
+        return ogn_fail(ctx, OGN_ERR_ARG, "owned window outside the sub-cube");
     OGN_CUDA(cudaSetDevice(ctx->device));
     const size_t vol = (size_t)nz * ny * nx;
-    const int nxw = ogn_div_up(nx, 32);
-    const size_t nwords = (size_t)nz * ny * nxw;
+    const int ony = owned.y1 - owned.y0;
+    const int ox0a = owned.x0 / 32 * 32;
+    const int nxw = ogn_div_up(owned.x1 - ox0a, 32);
+    const size_t nwords = (size_t)nz * ony * nxw;
 
     const void *da = nullptr, *db = nullptr, *dm = nullptr;
     OGN_TRY(ogn_input(ctx, "ext_a", a, vol * 4, &da));
@@ -358,17 +376,19 @@ extern "C" int ogn_local_extrema(ogn_ctx *ctx, const float *a, const float *b, c
     ogn_timer *t_k3 = new ogn_timer(ctx, "k3_local_extrema");
     if (sz == 3 && sy == 3 && sx == 3) {
         dim3 block(32, EX_TY + 2);
-        dim3 grid(nxw, ogn_div_up(ny, EX_TY), ogn_div_up(nz, EX_CZ));
+        dim3 grid(nxw, ogn_div_up(ony, EX_TY), ogn_div_up(nz, EX_CZ));
         local_extrema3_kernel<<<grid, block, 0, ctx->stream>>>((const float *)da, (const float *)db,
-                                                              (const uint8_t *)dm, nz, ny, nx, (float *)d_dmax,
-                                                              (float *)d_dmin, flag_max, flag_min, nxw);
+                                                              (const uint8_t *)dm, nz, ny, nx, owned.y0, owned.y1, ox0a,
+                                                              owned.x0, owned.x1, (float *)d_dmax, (float *)d_dmin,
+                                                              flag_max, flag_min, nxw);
         delete t_k3;
         OGN_LAUNCH_CHECK("local_extrema3_kernel");
     } else {
         dim3 block(32, 8);
-        dim3 grid(nxw, ogn_div_up(ny, 8), nz);
+        dim3 grid(nxw, ogn_div_up(ony, 8), nz);
         local_extrema_kernel<<<grid, block, 0, ctx->stream>>>((const float *)da, (const float *)db,
                                                              (const uint8_t *)dm, nz, ny, nx, sz / 2, sy / 2, sx / 2,
+                                                             owned.y0, owned.y1, ox0a, owned.x0, owned.x1,
                                                              (float *)d_dmax, (float *)d_dmin, flag_max, flag_min, nxw);
         delete t_k3;
         OGN_LAUNCH_CHECK("local_extrema_kernel");
@@ -385,9 +405,10 @@ extern "C" int ogn_local_extrema(ogn_ctx *ctx, const float *a, const float *b, c
     }
     int64_t *d_counts = nullptr;
     OGN_TRY(ogn_scratch_t(ctx, "ext_counts", (size_t)2, &d_counts));
-    OGN_TRY(compact_flags(ctx, "max", flag_max, nwords, (const float *)da, 1.f, nx, nxw, (int64_t *)d_maxi,
+    const ExMap emap{ny, nx, owned.y0, ony, ox0a, place.gny, place.gnx, place.gy0, place.gx0};
+    OGN_TRY(compact_flags(ctx, "max", flag_max, nwords, (const float *)da, 1.f, emap, nxw, (int64_t *)d_maxi,
                           (float *)d_maxv, want_lists ? capacity : 0, d_counts));
-    OGN_TRY(compact_flags(ctx, "min", flag_min, nwords, (const float *)db, -1.f, nx, nxw, (int64_t *)d_mini,
+    OGN_TRY(compact_flags(ctx, "min", flag_min, nwords, (const float *)db, -1.f, emap, nxw, (int64_t *)d_mini,
                           (float *)d_minv, want_lists ? capacity : 0, d_counts + 1));
 
     int64_t h_counts[2] = {0, 0};
@@ -412,6 +433,14 @@ extern "C" int ogn_local_extrema(ogn_ctx *ctx, const float *a, const float *b, c
         return ogn_fail(ctx, OGN_ERR_OVERFLOW, "extremum lists need %lld / %lld entries, capacity is %lld",
                         (long long)h_counts[0], (long long)h_counts[1], (long long)capacity);
     return OGN_OK;
+}
+
+extern "C" int ogn_local_extrema(ogn_ctx *ctx, const float *a, const float *b, const uint8_t *mask, int nz, int ny,
+                                 int nx, int sz, int sy, int sx, float *dense_max, float *dense_min,
+                                 int64_t *max_index, float *max_value, int64_t *min_index, float *min_value,
+                                 int64_t capacity, int64_t *counts) {
+    return ogn_extrema_run(ctx, a, b, mask, nz, ny, nx, ogn_window{0, ny, 0, nx}, ogn_place{ny, nx, 0, 0}, sz, sy, sx,
+                           dense_max, dense_min, max_index, max_value, min_index, min_value, capacity, counts);
 }
 
 __global__ void fill_f32_kernel2(float *p, size_t n, float v) {

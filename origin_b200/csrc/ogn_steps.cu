@@ -1,6 +1,162 @@
 // Fused step-level entry points: the whole array part of one ORIGIN step in one call, so
 // that intermediates stay on the device and every product crosses PCIe at most once.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "ogn_common.cuh"
+
+namespace {
+
+struct Step05Args {
+    const void *cube; int cube_dtype, nz, ny, nx, nfields;
+    const double *const *fsf; int psize;
+    const double *const *weights; const double *taps; const int *tap_offsets; int nprof;
+    const uint8_t *mask; int sz, sy, sx;
+    float *correl, *correl_min; uint8_t *profile; float *maxmap, *minmap, *dense_max, *dense_min;
+    int64_t *max_index; float *max_value; int64_t *min_index; float *min_value; int64_t capacity; int64_t *counts;
+};
+
+int get_event(ogn_ctx *ctx, size_t i, cudaEvent_t *ev) {
+    while (ctx->events.size() <= i) {
+        cudaEvent_t e;
+        OGN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->events.push_back(e);
+    }
+    *ev = ctx->events[i];
+    return OGN_OK;
+}
+
+// Host cube in, host products out: the field is cut into slabs of image rows; the upload of slab
+// s+1, the K1/K2 pass on slab s and the download of the products of slab s-1 overlap on three streams.
+int step05_streamed(ogn_ctx *ctx, const Step05Args &a, const ogn_tglr_setup_t &st) {
+    const int nz = a.nz, ny = a.ny, nx = a.nx;
+    const size_t vol = (size_t)nz * ny * nx, img = (size_t)ny * nx, plane_b = img * 4;
+    constexpr int SLAB = 64;
+    const int nslab = ogn_div_up(ny, SLAB);
+    if (!ctx->h2d_stream) OGN_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    if (!ctx->d2h_stream) OGN_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    float *d_cube = nullptr, *d_correl = nullptr, *d_cmin = nullptr, *d_maxmap = nullptr, *d_minmap = nullptr;
+    uint8_t *d_mask = nullptr, *d_prof = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, "cube", vol, &d_cube));
+    OGN_TRY(ogn_scratch_t(ctx, "s5_correl", vol, &d_correl));
+    OGN_TRY(ogn_scratch_t(ctx, "s5_correl_min", vol, &d_cmin));
+    if (a.profile) OGN_TRY(ogn_scratch_t(ctx, "s5_profile", vol, &d_prof));
+    if (a.mask) OGN_TRY(ogn_scratch_t(ctx, "s5_mask", vol, &d_mask));
+    if (a.maxmap) OGN_TRY(ogn_scratch_t(ctx, "s5_maxmap", img, &d_maxmap));
+    if (a.minmap) OGN_TRY(ogn_scratch_t(ctx, "s5_minmap", img, &d_minmap));
+    OGN_TRY(ogn_tglr_init_maps(ctx, ctx->stream, d_maxmap, d_minmap, img));
+    cudaEvent_t ev;
+    // the side streams start after everything already queued on the main stream (setup, scratch reuse)
+    OGN_TRY(get_event(ctx, 0, &ev));
+    OGN_CUDA(cudaEventRecord(ev, ctx->stream));
+    OGN_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, ev, 0));
+    OGN_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ev, 0));
+    const float *h_cube = static_cast<const float *>(a.cube);
+    for (int s = 0; s < nslab; ++s) {
+        const int y0 = s * SLAB, rows = std::min(SLAB, ny - y0);
+        const size_t off = (size_t)y0 * nx;
+        OGN_CUDA(cudaMemcpy2DAsync(d_cube + off, plane_b, h_cube + off, plane_b, (size_t)rows * nx * 4, nz,
+                                   cudaMemcpyHostToDevice, ctx->h2d_stream));
+        if (a.mask)
+            OGN_CUDA(cudaMemcpy2DAsync(d_mask + off, img, a.mask + off, img, (size_t)rows * nx, nz,
+                                       cudaMemcpyHostToDevice, ctx->h2d_stream));
+        OGN_TRY(get_event(ctx, 1 + s, &ev));
+        OGN_CUDA(cudaEventRecord(ev, ctx->h2d_stream));
+    }
+    for (int s = 0; s < nslab; ++s) {
+        const int y0 = s * SLAB, rows = std::min(SLAB, ny - y0);
+        // slab s needs input rows up to y0 + rows + P/2: they arrive with slab s+1 (SLAB >= P/2)
+        OGN_TRY(get_event(ctx, 1 + std::min(s + 1, nslab - 1), &ev));
+        OGN_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
+        OGN_TRY(ogn_tglr_window(ctx, ctx->stream, st, d_cube, d_mask, ogn_window{y0, y0 + rows, 0, nx}, d_correl,
+                                d_cmin, d_prof, d_maxmap, d_minmap));
+        OGN_TRY(get_event(ctx, 1 + nslab + s, &ev));
+        OGN_CUDA(cudaEventRecord(ev, ctx->stream));
+        OGN_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ev, 0));
+        const size_t off = (size_t)y0 * nx;
+        if (a.correl)
+            OGN_CUDA(cudaMemcpy2DAsync(a.correl + off, plane_b, d_correl + off, plane_b, (size_t)rows * nx * 4, nz,
+                                       cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (a.correl_min)
+            OGN_CUDA(cudaMemcpy2DAsync(a.correl_min + off, plane_b, d_cmin + off, plane_b, (size_t)rows * nx * 4, nz,
+                                       cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (a.profile)
+            OGN_CUDA(cudaMemcpy2DAsync(a.profile + off, img, d_prof + off, img, (size_t)rows * nx, nz,
+                                       cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    }
+    // extremum pass on the complete device cubes while the last products are still travelling
+    int rc = ogn_extrema_run(ctx, d_correl, d_cmin, d_mask, nz, ny, nx, ogn_window{0, ny, 0, nx},
+                             ogn_place{ny, nx, 0, 0}, a.sz, a.sy, a.sx, a.dense_max, a.dense_min, a.max_index,
+                             a.max_value, a.min_index, a.min_value, a.capacity, a.counts);
+    if (rc != OGN_OK && rc != OGN_ERR_OVERFLOW) return rc;
+    OGN_TRY(ogn_output_commit(ctx, a.maxmap, d_maxmap, img * 4));
+    OGN_TRY(ogn_output_commit(ctx, a.minmap, d_minmap, img * 4));
+    OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+    OGN_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+    ctx->host_output_pending = false;
+    return rc;
+}
+
+int step05_run(ogn_ctx *ctx, const Step05Args &a, const int *tile) {
+    if (!ctx) return OGN_ERR_ARG;
+    const int nz = a.nz, ny = a.ny, nx = a.nx;
+    if (nz <= 0 || ny <= 0 || nx <= 0) return ogn_fail(ctx, OGN_ERR_ARG, "cube shape (%d,%d,%d) is empty", nz, ny, nx);
+    OGN_CUDA(cudaSetDevice(ctx->device));
+    ogn_place place{ny, nx, 0, 0};
+    ogn_window owned{0, ny, 0, nx};
+    if (tile) {
+        place = ogn_place{tile[0], tile[1], tile[2], tile[3]};
+        owned = ogn_window{tile[4], tile[5], tile[6], tile[7]};
+        if (owned.y0 < 0 || owned.x0 < 0 || owned.y1 > ny || owned.x1 > nx || owned.y0 >= owned.y1 || owned.x0 >= owned.x1)
+            return ogn_fail(ctx, OGN_ERR_ARG, "owned window [%d,%d)x[%d,%d) outside the %dx%d sub-cube", owned.y0,
+                            owned.y1, owned.x0, owned.x1, ny, nx);
+    }
+    if (a.sz < 1 || a.sy < 1 || a.sx < 1 || !(a.sz & 1) || !(a.sy & 1) || !(a.sx & 1))
+        return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "window (%d,%d,%d): only odd sizes are supported", a.sz, a.sy, a.sx);
+    ogn_tglr_setup_t st;
+    OGN_TRY(ogn_tglr_setup(ctx, nz, ny, nx, &place, a.nfields, a.fsf, a.psize, a.weights, a.taps, a.tap_offsets,
+                           a.nprof, true, &st));
+    const size_t vol = (size_t)nz * ny * nx, img = (size_t)ny * nx;
+
+    const bool host_in = !ogn_is_device_ptr(a.cube);
+    const bool host_out = (a.correl && !ogn_is_device_ptr(a.correl)) || (a.correl_min && !ogn_is_device_ptr(a.correl_min));
+    static const bool no_stream = getenv("OGN_NO_STREAM") != nullptr;
+    if (!no_stream && !tile && host_in && host_out && a.cube_dtype == OGN_F32 && !st.pervoxel && ny >= 128 && nx % 4 == 0 &&
+        (!a.mask || !ogn_is_device_ptr(a.mask)) && (!a.profile || !ogn_is_device_ptr(a.profile)))
+        return step05_streamed(ctx, a, st);
+
+    void *d_correl = nullptr, *d_cmin = nullptr, *d_prof = nullptr, *d_maxmap = nullptr, *d_minmap = nullptr;
+    // correl and correl_min are needed on the device even when the caller does not want them back
+    OGN_TRY(ogn_output(ctx, "s5_correl", a.correl, vol * 4, &d_correl));
+    OGN_TRY(ogn_output(ctx, "s5_correl_min", a.correl_min, vol * 4, &d_cmin));
+    if (a.profile) OGN_TRY(ogn_output(ctx, "s5_profile", a.profile, vol, &d_prof));
+    if (a.maxmap) OGN_TRY(ogn_output(ctx, "s5_maxmap", a.maxmap, img * 4, &d_maxmap));
+    if (a.minmap) OGN_TRY(ogn_output(ctx, "s5_minmap", a.minmap, img * 4, &d_minmap));
+    const void *d_mask = nullptr;
+    if (a.mask) OGN_TRY(ogn_input(ctx, "s5_mask", a.mask, vol, &d_mask));
+    const float *d_cube = nullptr;
+    OGN_TRY(ogn_input_cube_f32(ctx, "cube", a.cube, a.cube_dtype, vol, &d_cube));
+    OGN_TRY(ogn_tglr_init_maps(ctx, ctx->stream, (float *)d_maxmap, (float *)d_minmap, img));
+    // TGLR on the owned window grown by the extremum radius (clipped to the sub-cube)
+    const ogn_window w{std::max(0, owned.y0 - a.sy / 2), std::min(ny, owned.y1 + a.sy / 2),
+                       std::max(0, owned.x0 - a.sx / 2), std::min(nx, owned.x1 + a.sx / 2)};
+    OGN_TRY(ogn_tglr_window(ctx, ctx->stream, st, d_cube, (const uint8_t *)d_mask, w, (float *)d_correl,
+                            (float *)d_cmin, (uint8_t *)d_prof, (float *)d_maxmap, (float *)d_minmap));
+    OGN_TRY(ogn_output_commit(ctx, a.correl, d_correl, vol * 4));
+    OGN_TRY(ogn_output_commit(ctx, a.correl_min, d_cmin, vol * 4));
+    OGN_TRY(ogn_output_commit(ctx, a.profile, d_prof, vol));
+    OGN_TRY(ogn_output_commit(ctx, a.maxmap, d_maxmap, img * 4));
+    OGN_TRY(ogn_output_commit(ctx, a.minmap, d_minmap, img * 4));
+    int rc = ogn_extrema_run(ctx, (const float *)d_correl, (const float *)d_cmin, (const uint8_t *)d_mask, nz, ny, nx,
+                             owned, place, a.sz, a.sy, a.sx, a.dense_max, a.dense_min, a.max_index, a.max_value,
+                             a.min_index, a.min_value, a.capacity, a.counts);
+    if (rc != OGN_OK && rc != OGN_ERR_OVERFLOW) return rc;
+    OGN_TRY(ogn_finish_call(ctx));
+    return rc;
+}
+
+}  // namespace
 
 // ComputeTGLR.run (steps.py:768-802): Correlation_GLR_test + masking + maxmap/minmap +
 // compute_local_max, with correl / correl_min / profile never leaving the device in between.
@@ -10,32 +166,21 @@ extern "C" int ogn_step05(ogn_ctx *ctx, const void *cube, int cube_dtype, int nz
                           float *correl, float *correl_min, uint8_t *profile, float *maxmap, float *minmap,
                           float *dense_max, float *dense_min, int64_t *max_index, float *max_value,
                           int64_t *min_index, float *min_value, int64_t capacity, int64_t *counts) {
-    if (!ctx) return OGN_ERR_ARG;
-    if (nz <= 0 || ny <= 0 || nx <= 0) return ogn_fail(ctx, OGN_ERR_ARG, "cube shape (%d,%d,%d) is empty", nz, ny, nx);
-    OGN_CUDA(cudaSetDevice(ctx->device));
-    const size_t vol = (size_t)nz * ny * nx, img = (size_t)ny * nx;
-    void *d_correl = nullptr, *d_cmin = nullptr, *d_prof = nullptr, *d_maxmap = nullptr, *d_minmap = nullptr;
-    // correl and correl_min are needed on the device even when the caller does not want them back
-    OGN_TRY(ogn_output(ctx, "s5_correl", correl, vol * 4, &d_correl));
-    OGN_TRY(ogn_output(ctx, "s5_correl_min", correl_min, vol * 4, &d_cmin));
-    if (profile) OGN_TRY(ogn_output(ctx, "s5_profile", profile, vol, &d_prof));
-    if (maxmap) OGN_TRY(ogn_output(ctx, "s5_maxmap", maxmap, img * 4, &d_maxmap));
-    if (minmap) OGN_TRY(ogn_output(ctx, "s5_minmap", minmap, img * 4, &d_minmap));
-    const void *d_mask = nullptr;
-    if (mask) OGN_TRY(ogn_input(ctx, "s5_mask", mask, vol, &d_mask));
+    const Step05Args a{cube, cube_dtype, nz, ny, nx, nfields, fsf, psize, weights, taps, tap_offsets, nprof, mask,
+                       sz, sy, sx, correl, correl_min, profile, maxmap, minmap, dense_max, dense_min, max_index,
+                       max_value, min_index, min_value, capacity, counts};
+    return step05_run(ctx, a, nullptr);
+}
 
-    OGN_TRY(ogn_tglr(ctx, cube, cube_dtype, nz, ny, nx, nfields, fsf, psize, weights, taps, tap_offsets, nprof,
-                     (const uint8_t *)d_mask, (float *)d_correl, (float *)d_cmin, (uint8_t *)d_prof,
-                     (float *)d_maxmap, (float *)d_minmap));
-    OGN_TRY(ogn_output_commit(ctx, correl, d_correl, vol * 4));
-    OGN_TRY(ogn_output_commit(ctx, correl_min, d_cmin, vol * 4));
-    OGN_TRY(ogn_output_commit(ctx, profile, d_prof, vol));
-    OGN_TRY(ogn_output_commit(ctx, maxmap, d_maxmap, img * 4));
-    OGN_TRY(ogn_output_commit(ctx, minmap, d_minmap, img * 4));
-    int rc = ogn_local_extrema(ctx, (const float *)d_correl, (const float *)d_cmin, (const uint8_t *)d_mask, nz, ny,
-                               nx, sz, sy, sx, dense_max, dense_min, max_index, max_value, min_index, min_value,
-                               capacity, counts);
-    if (rc != OGN_OK && rc != OGN_ERR_OVERFLOW) return rc;
-    OGN_TRY(ogn_finish_call(ctx));
-    return rc;
+extern "C" int ogn_step05_tile(ogn_ctx *ctx, const void *cube, int cube_dtype, int nz, int ny, int nx,
+                               const int *tile, int nfields, const double *const *fsf, int psize,
+                               const double *const *weights, const double *taps, const int *tap_offsets, int nprof,
+                               const uint8_t *mask, int sz, int sy, int sx, float *correl, float *correl_min,
+                               uint8_t *profile, float *maxmap, float *minmap, int64_t *max_index, float *max_value,
+                               int64_t *min_index, float *min_value, int64_t capacity, int64_t *counts) {
+    if (!tile) return ogn_fail(ctx, OGN_ERR_ARG, "tile is NULL");
+    const Step05Args a{cube, cube_dtype, nz, ny, nx, nfields, fsf, psize, weights, taps, tap_offsets, nprof, mask,
+                       sz, sy, sx, correl, correl_min, profile, maxmap, minmap, nullptr, nullptr, max_index,
+                       max_value, min_index, min_value, capacity, counts};
+    return step05_run(ctx, a, tile);
 }

@@ -393,7 +393,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int ZB, bool PERVOXEL>
 __global__ void __launch_bounds__(NW * 32, PERVOXEL ? 2 : (ZB > 24 ? 2 : 3))
 spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_constant__ CUtensorMap den_map,
-                    int nz, int ny, int nx,
+                    int nz, int wny, int wnx,            // window (= K1 output) dims
+                    int oy_off, int ox_off, int ony, int onx,   // window origin inside the [nz][ony][onx] products
+                    int cy_off, int cx_off, int gny, int gnx,   // window origin / size of the global field (edge classes)
                     const float *__restrict__ taps, const float *__restrict__ taps_sq, int ntaps_total,
                     const ProfDesc *__restrict__ desc, int nprof, int box_rows, int nbox, int woff_min,
                     const float *__restrict__ rs, int nzp, int ncls, int ncx, int P, int stage_rs, int stage_mask,
@@ -414,7 +416,8 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
     float *rs_sm = reinterpret_cast<float *>(mask_sm + (stage_mask ? 2 * NW * ZB * 32 : 0));  // [2][NW][nprof][ZB]
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x0 = blockIdx.x * 32, x = x0 + lane, y = blockIdx.y;
+    const int x0 = blockIdx.x * 32, x = x0 + lane, y = blockIdx.y;   // window coordinates
+    const int oy = y + oy_off, ox = x + ox_off;                       // coordinates in the product cubes
     const int nchunk = (nz + NW * ZB - 1) / (NW * ZB);
     const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
 
@@ -433,9 +436,9 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
     int cls_base = 0;
     bool rs_staged = false;
     if (!PERVOXEL) {
-        cls_base = cls_of(y, ny, P) * ncx + cls_of(min(x, nx - 1), nx, P);
+        cls_base = cls_of(y + cy_off, gny, P) * ncx + cls_of(min(x + cx_off, gnx - 1), gnx, P);
         // the warp shares one denominator row when all its lanes are interior in x
-        rs_staged = stage_rs && nx >= P && x0 >= P / 2 && x0 + 31 < nx - P / 2;
+        rs_staged = stage_rs && gnx >= P && x0 + cx_off >= P / 2 && x0 + cx_off + 31 < gnx - P / 2;
     }
 
     // TMA window of one chunk (elected thread)
@@ -458,8 +461,8 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
             for (int j = 0; j < (ZB * 2 + 31) / 32; ++j) {
                 const int c = lane + 32 * j, row = c >> 1, half = c & 1;
                 if (row < ZB) {
-                    const bool ok = z0 + row < nz && x0 + 16 * half < nx;
-                    const uint8_t *src = ok ? mask + ((size_t)(z0 + row) * ny + y) * nx + x0 + 16 * half : mask;
+                    const bool ok = z0 + row < nz && x0 + ox_off + 16 * half < onx;
+                    const uint8_t *src = ok ? mask + ((size_t)(z0 + row) * ony + oy) * onx + x0 + ox_off + 16 * half : mask;
                     cp_async16(dst + row * 32 + 16 * half, src, ok);
                 }
             }
@@ -540,7 +543,7 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
                 }
             }
 
-            if (x < nx) {
+            if (x < wnx) {
                 // mask bits of this thread's ZB voxels
                 uint32_t mbits = 0;
                 if (mask) {
@@ -552,7 +555,7 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
                         uint8_t mv[ZB];
 #pragma unroll
                         for (int i = 0; i < ZB; ++i)
-                            mv[i] = (z0 + i < nz) ? mask[((size_t)(z0 + i) * ny + y) * nx + x] : (uint8_t)0;
+                            mv[i] = (z0 + i < nz) ? mask[((size_t)(z0 + i) * ony + oy) * onx + ox] : (uint8_t)0;
 #pragma unroll
                         for (int i = 0; i < ZB; ++i) mbits |= (mv[i] ? 1u : 0u) << i;
                     }
@@ -562,7 +565,7 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
                 for (int i = 0; i < ZB; ++i) {
                     const int z = z0 + i;
                     if (z < nz) {
-                        const size_t o = ((size_t)z * ny + y) * nx + x;
+                        const size_t o = ((size_t)z * ony + oy) * onx + ox;
                         const bool masked = (mbits >> i) & 1u;
                         const float c = masked ? 0.f : mx[i];
                         if (correl) correl[o] = c;
@@ -572,8 +575,8 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
                         cmin = fminf(cmin, mn[i]);
                     }
                 }
-                if (maxmap) atomic_max_float(maxmap + (size_t)y * nx + x, cmax);
-                if (minmap) atomic_min_float(minmap + (size_t)y * nx + x, cmin);
+                if (maxmap) atomic_max_float(maxmap + (size_t)oy * onx + ox, cmax);
+                if (minmap) atomic_min_float(minmap + (size_t)oy * onx + ox, cmin);
             }
         }
         __syncthreads();  // the stage is free again before the next iteration refills it
@@ -637,11 +640,12 @@ static int make_tile_map(ogn_ctx *ctx, CUtensorMap *map, const float *base, int 
     return OGN_OK;
 }
 
-// Launch K1 (or the naive fallback) for one field: out (+)= corr(in, weights).
+// Launch K1 (or the naive fallback) for one field: out (+)= corr(in, weights) on the output window
+// [wy0, wy0+wny) x [wx0, wx0+wnx) of the input; out is window-relative [nz][wny][opitch].
 //   in: device f32 [nz or 1][iny][ipitch], 16-byte aligned, ipitch % 4 == 0
-static int launch_fsf_correlate(ogn_ctx *ctx, const float *in, int in_z_invariant, int nz, int iny, int inx,
-                                int ipitch, const float *weights, int P, int WP, float *out, int ony, int onx,
-                                int opitch, int accumulate) {
+static int launch_fsf_correlate(ogn_ctx *ctx, cudaStream_t stream, const float *in, int in_z_invariant, int nz,
+                                int iny, int inx, int ipitch, const float *weights, int P, int WP, float *out,
+                                int wy0, int wx0, int wny, int wnx, int opitch, int accumulate) {
     if (P == 25) {
         using G = k1::Geo<25>;
         CUtensorMap map;
@@ -652,106 +656,19 @@ static int launch_fsf_correlate(ogn_ctx *ctx, const float *in, int in_z_invarian
             OGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
             attr_set = true;
         }
-        const int tx = ogn_div_up(onx, k1::TILE), ty = ogn_div_up(ony, k1::TILE);
+        const int tx = ogn_div_up(wnx, k1::TILE), ty = ogn_div_up(wny, k1::TILE);
         // one wave of resident blocks (4 per SM); every block walks nz/zsplit planes
         int zsplit = std::max(1, (ctx->sm_count * 4) / (tx * ty));
         zsplit = std::min(zsplit, nz);
         dim3 grid(tx, ty, zsplit);
-        kern<<<grid, k1::THREADS, G::SMEM, ctx->stream>>>(map, in_z_invariant, weights, out, 0, 0, ony, onx, opitch,
-                                                          nz, zsplit, accumulate);
+        kern<<<grid, k1::THREADS, G::SMEM, stream>>>(map, in_z_invariant, weights, out, wy0, wx0, wny, wnx, opitch, nz,
+                                                     zsplit, accumulate);
         OGN_LAUNCH_CHECK("fsf_correlate_kernel");
     } else {
-        dim3 grid(ogn_div_up(onx, 128), ony, nz);
-        fsf_correlate_naive_kernel<<<grid, 128, 0, ctx->stream>>>(in, in_z_invariant, iny, inx, ipitch, weights, P, WP,
-                                                                 out, 0, 0, ony, onx, opitch, nz, accumulate);
+        dim3 grid(ogn_div_up(wnx, 128), wny, nz);
+        fsf_correlate_naive_kernel<<<grid, 128, 0, stream>>>(in, in_z_invariant, iny, inx, ipitch, weights, P, WP, out,
+                                                            wy0, wx0, wny, wnx, opitch, nz, accumulate);
         OGN_LAUNCH_CHECK("fsf_correlate_naive_kernel");
-    }
-    return OGN_OK;
-}
-
-struct TglrPlan {
-    int nz, ny, nx, pitch, P, WP, nfields, nprof;
-    bool pervoxel;
-    float *w32 = nullptr, *w32sq = nullptr;
-    float *cube_fsf = nullptr, *norm_fsf = nullptr;
-};
-
-// Spatial stage on the device: fills plan.cube_fsf (and plan.norm_fsf when pervoxel).
-static int run_fsf_stage(ogn_ctx *ctx, const float *cube, const double *const *fsf_host,
-                         const double *const *weights_host, TglrPlan &pl, double **normcls_out, int nzp, int ncy,
-                         int ncx) {
-    const int nz = pl.nz, ny = pl.ny, nx = pl.nx, P = pl.P, WP = pl.WP, nf = pl.nfields;
-    const size_t fsf_bytes = (size_t)nz * P * P * sizeof(double);
-    // FSF cubes -> device, pointer table
-    std::vector<const double *> fsf_dev(nf), w_dev(nf, nullptr);
-    for (int f = 0; f < nf; ++f) {
-        char name[32];
-        snprintf(name, sizeof(name), "fsf%d", f);
-        const void *d = nullptr;
-        OGN_TRY(ogn_input(ctx, name, fsf_host[f], fsf_bytes, &d));
-        fsf_dev[f] = static_cast<const double *>(d);
-        if (weights_host) {
-            snprintf(name, sizeof(name), "wmap%d", f);
-            OGN_TRY(ogn_input(ctx, name, weights_host[f], (size_t)ny * nx * sizeof(double), &d));
-            w_dev[f] = static_cast<const double *>(d);
-        }
-    }
-    const double **fsf_tab = nullptr;
-    OGN_TRY(ogn_scratch_t(ctx, "fsf_tab", (size_t)nf, &fsf_tab));
-    OGN_CUDA(cudaMemcpyAsync(fsf_tab, fsf_dev.data(), nf * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
-    // the pageable source vector dies at return: make sure the copy has been staged
-    OGN_CUDA(cudaStreamSynchronize(ctx->stream));
-
-    OGN_TRY(ogn_scratch_t(ctx, "w32", (size_t)nf * nz * P * WP, &pl.w32));
-    double *normcls = nullptr;
-    if (pl.pervoxel) {
-        OGN_TRY(ogn_scratch_t(ctx, "w32sq", (size_t)nf * nz * P * WP, &pl.w32sq));
-    } else {
-        OGN_TRY(ogn_scratch_t(ctx, "normcls", (size_t)ncy * ncx * nzp, &normcls));
-        OGN_CUDA(cudaMemsetAsync(normcls, 0, (size_t)ncy * ncx * nzp * sizeof(double), ctx->stream));
-    }
-    {
-        ogn_timer t_(ctx, "fsf_prep");
-        dim3 grid(nz, nf);
-        size_t sm = ((size_t)P * P + 32) * sizeof(double);
-        fsf_prep_kernel<<<grid, 256, sm, ctx->stream>>>(fsf_tab, nz, P, WP, pl.w32, pl.w32sq, normcls, nzp, ny, nx,
-                                                        ncy, ncx);
-        OGN_LAUNCH_CHECK("fsf_prep_kernel");
-    }
-    if (normcls_out) *normcls_out = normcls;
-
-    const size_t vol_p = (size_t)nz * ny * pl.pitch;
-    OGN_TRY(ogn_scratch_t(ctx, "cube_fsf", vol_p, &pl.cube_fsf));
-    if (pl.pervoxel) OGN_TRY(ogn_scratch_t(ctx, "norm_fsf", vol_p, &pl.norm_fsf));
-
-    const bool aligned = (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(cube) & 15) == 0);
-    ogn_timer t_k1(ctx, "k1_fsf_correlate");
-    for (int f = 0; f < nf; ++f) {
-        const float *in = cube;
-        int ipitch = nx;
-        if (w_dev[f] || !aligned) {
-            // weighted data (lib_origin.py:1030) or a TMA-incompatible layout: stage a padded copy
-            ipitch = (int)ogn_round_up(nx, 4);
-            float *tmp = nullptr;
-            OGN_TRY(ogn_scratch_t(ctx, "cube_w", (size_t)nz * ny * ipitch, &tmp));
-            dim3 grid(ogn_div_up(ipitch, 128), ny, nz);
-            pitch_copy_kernel<<<grid, 128, 0, ctx->stream>>>(cube, w_dev[f], tmp, nz, ny, nx, ipitch, 0);
-            OGN_LAUNCH_CHECK("pitch_copy_kernel");
-            in = tmp;
-        }
-        OGN_TRY(launch_fsf_correlate(ctx, in, 0, nz, ny, nx, ipitch, pl.w32 + (size_t)f * nz * P * WP, P, WP,
-                                     pl.cube_fsf, ny, nx, pl.pitch, f > 0));
-        if (pl.pervoxel) {
-            // norm_fsf += corr(w_f or ones, K^2)   (lib_origin.py:1028-1031, 1040-1041)
-            int wpitch = (int)ogn_round_up(nx, 4);
-            float *wplane = nullptr;
-            OGN_TRY(ogn_scratch_t(ctx, "wplane", (size_t)ny * wpitch, &wplane));
-            dim3 grid(ogn_div_up(wpitch, 128), ny, 1);
-            pitch_copy_kernel<<<grid, 128, 0, ctx->stream>>>(nullptr, w_dev[f], wplane, 1, ny, nx, wpitch, 1);
-            OGN_LAUNCH_CHECK("pitch_copy_kernel");
-            OGN_TRY(launch_fsf_correlate(ctx, wplane, 1, nz, ny, nx, wpitch, pl.w32sq + (size_t)f * nz * P * WP, P,
-                                         WP, pl.norm_fsf, ny, nx, pl.pitch, f > 0));
-        }
     }
     return OGN_OK;
 }
@@ -767,6 +684,246 @@ static int check_dims(ogn_ctx *ctx, int nz, int ny, int nx, int nfields, int psi
     return OGN_OK;
 }
 
+// ---- setup: everything that depends on (FSF, dictionary, geometry) but not on the data ------------
+int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place, int nfields,
+                   const double *const *fsf, int psize, const double *const *weights, const double *taps,
+                   const int *tap_offsets, int nprof, bool need_spectral, ogn_tglr_setup_t *st) {
+    OGN_TRY(check_dims(ctx, nz, ny, nx, nfields, psize));
+    if (!fsf) return ogn_fail(ctx, OGN_ERR_ARG, "fsf must not be NULL");
+    if (need_spectral) {
+        if (nprof < 1 || nprof > 255)
+            return ogn_fail(ctx, OGN_ERR_ARG, "nprof = %d: the profile index is a uint8 (lib_origin.py:1197), 1..255", nprof);
+        if (!taps || !tap_offsets) return ogn_fail(ctx, OGN_ERR_ARG, "taps / tap_offsets must not be NULL");
+    }
+    st->nz = nz; st->ny = ny; st->nx = nx; st->P = psize; st->WP = (psize + 3) / 4 * 4;
+    st->nfields = nfields; st->nprof = nprof;
+    st->place = place ? *place : ogn_place{ny, nx, 0, 0};
+    if (st->place.gy0 < 0 || st->place.gx0 < 0 || st->place.gy0 + ny > st->place.gny || st->place.gx0 + nx > st->place.gnx)
+        return ogn_fail(ctx, OGN_ERR_ARG, "sub-cube (%d,%d)+(%d,%d) does not fit the %dx%d field", st->place.gy0,
+                        st->place.gx0, ny, nx, st->place.gny, st->place.gnx);
+    st->pervoxel = weights != nullptr || nfields > 1 || !need_spectral;
+    const int P = psize, WP = st->WP, nf = nfields;
+    constexpr int ZB = 32;
+    st->nzp = (int)ogn_round_up(nz, ZB) + ZB;
+    st->ncy = std::min(st->place.gny, P);
+    st->ncx = std::min(st->place.gnx, P);
+
+    // ---- profiles: reversed, zero-padded to a multiple of U, float32 ----------------
+    std::vector<k2::ProfDesc> desc(std::max(nprof, 1));
+    std::vector<float> tp, tpsq;
+    st->woff_min = 0; st->reach = 0;
+    double *d_taps64 = nullptr;
+    int *d_tapoff = nullptr;
+    if (need_spectral) {
+        const int ntaps_in = tap_offsets[nprof];
+        for (int k = 0; k < nprof; ++k) {
+            const int L = tap_offsets[k + 1] - tap_offsets[k];
+            if (L < 1) return ogn_fail(ctx, OGN_ERR_ARG, "profile %d is empty", k);
+            const int ck = (L - 1) / 2;           // 'same' window start, lib_origin.py:1179
+            const int woff = ck - (L - 1);        // first window sample relative to the output index
+            st->woff_min = std::min(st->woff_min, woff);
+            const int LP = (int)ogn_round_up(L, k2::U);
+            desc[k].tap_off = (int)tp.size();
+            desc[k].nchunks = LP / k2::U;
+            desc[k].row_off = woff;               // made relative to woff_min below
+            desc[k].pad = 0;
+            for (int i = 0; i < LP; ++i) {
+                double v = i < L ? taps[tap_offsets[k] + (L - 1 - i)] : 0.0;
+                tp.push_back((float)v);
+                tpsq.push_back((float)(v * v));
+            }
+        }
+        for (int k = 0; k < nprof; ++k) {
+            desc[k].row_off -= st->woff_min;
+            st->reach = std::max(st->reach, desc[k].row_off + desc[k].nchunks * k2::U);
+        }
+        st->ntaps_total = (int)tp.size();
+        OGN_TRY(ogn_scratch_t(ctx, "taps32", (size_t)st->ntaps_total, &st->d_taps));
+        OGN_TRY(ogn_scratch_t(ctx, "taps32sq", (size_t)st->ntaps_total, &st->d_taps_sq));
+        k2::ProfDesc *d_desc = nullptr;
+        OGN_TRY(ogn_scratch_t(ctx, "prof_desc", (size_t)nprof, &d_desc));
+        st->d_desc = d_desc;
+        OGN_TRY(ogn_scratch_t(ctx, "taps64", (size_t)ntaps_in, &d_taps64));
+        OGN_TRY(ogn_scratch_t(ctx, "tap_off", (size_t)nprof + 1, &d_tapoff));
+        OGN_CUDA(cudaMemcpyAsync(st->d_taps, tp.data(), st->ntaps_total * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        OGN_CUDA(cudaMemcpyAsync(st->d_taps_sq, tpsq.data(), st->ntaps_total * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        OGN_CUDA(cudaMemcpyAsync(d_desc, desc.data(), nprof * sizeof(k2::ProfDesc), cudaMemcpyHostToDevice, ctx->stream));
+        OGN_CUDA(cudaMemcpyAsync(d_taps64, taps, ntaps_in * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        OGN_CUDA(cudaMemcpyAsync(d_tapoff, tap_offsets, (nprof + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+
+    // ---- FSF cubes / weight maps -> device, pointer table ------------------------------
+    const size_t fsf_bytes = (size_t)nz * P * P * sizeof(double);
+    std::vector<const double *> fsf_dev(nf);
+    st->w_dev.assign(nf, nullptr);
+    for (int f = 0; f < nf; ++f) {
+        char name[32];
+        snprintf(name, sizeof(name), "fsf%d", f);
+        const void *d = nullptr;
+        OGN_TRY(ogn_input(ctx, name, fsf[f], fsf_bytes, &d));
+        fsf_dev[f] = static_cast<const double *>(d);
+        if (weights) {
+            snprintf(name, sizeof(name), "wmap%d", f);
+            OGN_TRY(ogn_input(ctx, name, weights[f], (size_t)ny * nx * sizeof(double), &d));
+            st->w_dev[f] = static_cast<const double *>(d);
+        }
+    }
+    const double **fsf_tab = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, "fsf_tab", (size_t)nf, &fsf_tab));
+    OGN_CUDA(cudaMemcpyAsync(fsf_tab, fsf_dev.data(), nf * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
+    // the pageable host vectors above die at return: make sure the copies have been staged
+    OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+
+    // ---- K0: weights (+ squares) and the edge-class norm table ---------------------------
+    OGN_TRY(ogn_scratch_t(ctx, "w32", (size_t)nf * nz * P * WP, &st->w32));
+    double *normcls = nullptr;
+    st->w32sq = nullptr;
+    if (st->pervoxel) {
+        OGN_TRY(ogn_scratch_t(ctx, "w32sq", (size_t)nf * nz * P * WP, &st->w32sq));
+    } else {
+        OGN_TRY(ogn_scratch_t(ctx, "normcls", (size_t)st->ncy * st->ncx * st->nzp, &normcls));
+        OGN_CUDA(cudaMemsetAsync(normcls, 0, (size_t)st->ncy * st->ncx * st->nzp * sizeof(double), ctx->stream));
+    }
+    {
+        ogn_timer t_(ctx, "fsf_prep");
+        dim3 grid(nz, nf);
+        size_t sm = ((size_t)P * P + 32) * sizeof(double);
+        fsf_prep_kernel<<<grid, 256, sm, ctx->stream>>>(fsf_tab, nz, P, WP, st->w32, st->w32sq, normcls, st->nzp,
+                                                        st->place.gny, st->place.gnx, st->ncy, st->ncx);
+        OGN_LAUNCH_CHECK("fsf_prep_kernel");
+    }
+    st->rs = nullptr;
+    if (!st->pervoxel) {
+        OGN_TRY(ogn_scratch_t(ctx, "rs", (size_t)nprof * st->ncy * st->ncx * st->nzp, &st->rs));
+        ogn_timer t_(ctx, "den_table");
+        dim3 grid(ogn_div_up(st->nzp, 128), st->ncy * st->ncx, nprof);
+        den_table_kernel<<<grid, 128, 0, ctx->stream>>>(normcls, nz, st->nzp, st->ncy * st->ncx, d_taps64, d_tapoff,
+                                                        nprof, st->rs);
+        OGN_LAUNCH_CHECK("den_table_kernel");
+    }
+    return OGN_OK;
+}
+
+// ---- spatial stage on one window: fills cube_fsf (and norm_fsf when pervoxel), window-relative ----
+static int run_fsf_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, const float *cube,
+                          ogn_window w, float **cube_fsf_out, float **norm_fsf_out, int *pitch_out) {
+    const int nz = st.nz, ny = st.ny, nx = st.nx, P = st.P, WP = st.WP, nf = st.nfields;
+    const int wny = w.y1 - w.y0, wnx = w.x1 - w.x0;
+    const int pitch = (int)ogn_round_up(wnx, 32);
+    float *cube_fsf = nullptr, *norm_fsf = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, "cube_fsf", (size_t)nz * wny * pitch, &cube_fsf));
+    if (st.pervoxel) OGN_TRY(ogn_scratch_t(ctx, "norm_fsf", (size_t)nz * wny * pitch, &norm_fsf));
+    const bool aligned = (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(cube) & 15) == 0);
+    for (int f = 0; f < nf; ++f) {
+        const float *in = cube;
+        int ipitch = nx;
+        if (st.w_dev[f] || !aligned) {
+            // weighted data (lib_origin.py:1030) or a TMA-incompatible layout: stage a padded copy
+            ipitch = (int)ogn_round_up(nx, 4);
+            float *tmp = nullptr;
+            OGN_TRY(ogn_scratch_t(ctx, "cube_w", (size_t)nz * ny * ipitch, &tmp));
+            dim3 grid(ogn_div_up(ipitch, 128), ny, nz);
+            pitch_copy_kernel<<<grid, 128, 0, stream>>>(cube, st.w_dev[f], tmp, nz, ny, nx, ipitch, 0);
+            OGN_LAUNCH_CHECK("pitch_copy_kernel");
+            in = tmp;
+        }
+        OGN_TRY(launch_fsf_correlate(ctx, stream, in, 0, nz, ny, nx, ipitch, st.w32 + (size_t)f * nz * P * WP, P, WP,
+                                     cube_fsf, w.y0, w.x0, wny, wnx, pitch, f > 0));
+        if (st.pervoxel) {
+            // norm_fsf += corr(w_f or ones, K^2)   (lib_origin.py:1028-1031, 1040-1041)
+            int wpitch = (int)ogn_round_up(nx, 4);
+            float *wplane = nullptr;
+            OGN_TRY(ogn_scratch_t(ctx, "wplane", (size_t)ny * wpitch, &wplane));
+            dim3 grid(ogn_div_up(wpitch, 128), ny, 1);
+            pitch_copy_kernel<<<grid, 128, 0, stream>>>(nullptr, st.w_dev[f], wplane, 1, ny, nx, wpitch, 1);
+            OGN_LAUNCH_CHECK("pitch_copy_kernel");
+            OGN_TRY(launch_fsf_correlate(ctx, stream, wplane, 1, nz, ny, nx, wpitch, st.w32sq + (size_t)f * nz * P * WP,
+                                         P, WP, norm_fsf, w.y0, w.x0, wny, wnx, pitch, f > 0));
+        }
+    }
+    *cube_fsf_out = cube_fsf;
+    *norm_fsf_out = norm_fsf;
+    *pitch_out = pitch;
+    return OGN_OK;
+}
+
+template <int ZB, bool PV>
+static int launch_spectral(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, ogn_window w,
+                           const float *cube_fsf, const float *norm_fsf, int pitch, const uint8_t *mask,
+                           float *correl, float *correl_min, uint8_t *profile, float *maxmap, float *minmap) {
+    auto kern = k2::spectral_glr_kernel<ZB, PV>;
+    const int wny = w.y1 - w.y0, wnx = w.x1 - w.x0;
+    // window rows per chunk: the chunk itself, the longest profile, and the ring's read-ahead
+    const int need_rows = k2::NW * ZB + st.reach + 2 * k2::U;
+    const int nbox = ogn_div_up(need_rows, k2::MAX_BOX_ROWS);
+    const int box_rows = ogn_div_up(need_rows, nbox);
+    const int win_rows = nbox * box_rows;
+    size_t smem = ((size_t)2 * (PV ? 2 : 1) * win_rows * 32 + (size_t)(PV ? 2 : 1) * (st.ntaps_total + 4)) * sizeof(float) + 16;
+    if (smem > 110 * 1024)
+        return ogn_fail(ctx, OGN_ERR_UNSUPPORTED,
+                        "profile dictionary needs %zu bytes of shared memory per block (limit 110 KiB)", smem);
+    // optional per-warp staging of the mask rows (needs 16-byte aligned rows) and of the denominator rows
+    const int stage_mask = mask && st.nx % 16 == 0 && w.x0 % 16 == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0;
+    if (stage_mask) smem += (size_t)2 * k2::NW * ZB * 32;
+    const size_t rs_bytes = (size_t)2 * k2::NW * st.nprof * ZB * sizeof(float);
+    const int stage_rs = !PV && smem + rs_bytes <= 110 * 1024;
+    if (stage_rs) smem += rs_bytes;
+    OGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUtensorMap num_map, den_map;
+    OGN_TRY(make_tile_map(ctx, &num_map, cube_fsf, st.nz, wny, wnx, pitch, 32, 1, box_rows));
+    if (PV) OGN_TRY(make_tile_map(ctx, &den_map, norm_fsf, st.nz, wny, wnx, pitch, 32, 1, box_rows));
+    else den_map = num_map;
+    const int nchunk = ogn_div_up(st.nz, k2::NW * ZB);
+    const int cols = (pitch / 32) * wny;
+    // enough blocks for ~8 waves of 2 resident blocks per SM, at most one block per chunk
+    int zsplit = ogn_div_up((int64_t)ctx->sm_count * 2 * 8, cols);
+    zsplit = std::max(1, std::min(zsplit, nchunk));
+    dim3 grid(pitch / 32, wny, zsplit);
+    if (grid.y > 65535) return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "cube too large for the K2 launch grid");
+    kern<<<grid, k2::NW * 32, smem, stream>>>(num_map, den_map, st.nz, wny, wnx, w.y0, w.x0, st.ny, st.nx,
+                                              w.y0 + st.place.gy0, w.x0 + st.place.gx0, st.place.gny, st.place.gnx,
+                                              st.d_taps, st.d_taps_sq, st.ntaps_total,
+                                              static_cast<const k2::ProfDesc *>(st.d_desc), st.nprof, box_rows, nbox,
+                                              st.woff_min, st.rs, st.nzp, st.ncy * st.ncx, st.ncx, st.P, stage_rs,
+                                              stage_mask, mask, correl, correl_min, profile, maxmap, minmap);
+    OGN_LAUNCH_CHECK("spectral_glr_kernel");
+    return OGN_OK;
+}
+
+// K1 + K2 on one window of a device-resident sub-cube.  Products are [nz][ny][nx] device arrays of
+// which only the window is written; maxmap / minmap must have been initialised (ogn_tglr_init_maps).
+int ogn_tglr_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, const float *dcube,
+                    const uint8_t *dmask, ogn_window w, float *d_correl, float *d_cmin, uint8_t *d_prof,
+                    float *d_maxmap, float *d_minmap) {
+    if (w.y0 < 0 || w.x0 < 0 || w.y1 > st.ny || w.x1 > st.nx || w.y0 >= w.y1 || w.x0 >= w.x1)
+        return ogn_fail(ctx, OGN_ERR_ARG, "window [%d,%d)x[%d,%d) outside the %dx%d sub-cube", w.y0, w.y1, w.x0, w.x1,
+                        st.ny, st.nx);
+    float *cube_fsf = nullptr, *norm_fsf = nullptr;
+    int pitch = 0;
+    {
+        ogn_timer t_(ctx, "k1_fsf_correlate");
+        OGN_TRY(run_fsf_window(ctx, stream, st, dcube, w, &cube_fsf, &norm_fsf, &pitch));
+    }
+    ogn_timer t_(ctx, "k2_spectral_glr");
+    if (st.pervoxel)
+        return launch_spectral<16, true>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, dmask, d_correl, d_cmin,
+                                         d_prof, d_maxmap, d_minmap);
+    return launch_spectral<32, false>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, dmask, d_correl, d_cmin, d_prof,
+                                      d_maxmap, d_minmap);
+}
+
+int ogn_tglr_init_maps(ogn_ctx *ctx, cudaStream_t stream, float *d_maxmap, float *d_minmap, size_t img) {
+    if (d_maxmap) {
+        fill_f32_kernel<<<ogn_div_up(img, 256), 256, 0, stream>>>(d_maxmap, img, -INFINITY);
+        OGN_LAUNCH_CHECK("fill_f32_kernel");
+    }
+    if (d_minmap) {
+        fill_f32_kernel<<<ogn_div_up(img, 256), 256, 0, stream>>>(d_minmap, img, INFINITY);
+        OGN_LAUNCH_CHECK("fill_f32_kernel");
+    }
+    return OGN_OK;
+}
+
 extern "C" int ogn_fsf_stage(ogn_ctx *ctx, const void *cube, int cube_dtype, int nz, int ny, int nx, int nfields,
                              const double *const *fsf, int psize, const double *const *weights, float *cube_fsf,
                              float *norm_fsf) {
@@ -775,67 +932,27 @@ extern "C" int ogn_fsf_stage(ogn_ctx *ctx, const void *cube, int cube_dtype, int
     const size_t vol = (size_t)nz * ny * nx;
     const float *dcube = nullptr;
     OGN_TRY(ogn_input_cube_f32(ctx, "cube", cube, cube_dtype, vol, &dcube));
-    TglrPlan pl;
-    pl.nz = nz; pl.ny = ny; pl.nx = nx; pl.pitch = (int)ogn_round_up(nx, 32);
-    pl.P = psize; pl.WP = (psize + 3) / 4 * 4; pl.nfields = nfields; pl.nprof = 0;
-    pl.pervoxel = true;
-    OGN_TRY(run_fsf_stage(ctx, dcube, fsf, weights, pl, nullptr, 0, 0, 0));
+    ogn_tglr_setup_t st;
+    OGN_TRY(ogn_tglr_setup(ctx, nz, ny, nx, nullptr, nfields, fsf, psize, weights, nullptr, nullptr, 0, false, &st));
+    float *d_cf = nullptr, *d_nf = nullptr;
+    int pitch = 0;
+    OGN_TRY(run_fsf_window(ctx, ctx->stream, st, dcube, ogn_window{0, ny, 0, nx}, &d_cf, &d_nf, &pitch));
     dim3 grid(ogn_div_up(nx, 128), ny, nz);
     if (cube_fsf) {
         void *d = nullptr;
         OGN_TRY(ogn_output(ctx, "out_cube_fsf", cube_fsf, vol * 4, &d));
-        unpitch_kernel<<<grid, 128, 0, ctx->stream>>>(pl.cube_fsf, (float *)d, ny, nx, pl.pitch);
+        unpitch_kernel<<<grid, 128, 0, ctx->stream>>>(d_cf, (float *)d, ny, nx, pitch);
         OGN_LAUNCH_CHECK("unpitch_kernel");
         OGN_TRY(ogn_output_commit(ctx, cube_fsf, d, vol * 4));
     }
     if (norm_fsf) {
         void *d = nullptr;
         OGN_TRY(ogn_output(ctx, "out_norm_fsf", norm_fsf, vol * 4, &d));
-        unpitch_kernel<<<grid, 128, 0, ctx->stream>>>(pl.norm_fsf, (float *)d, ny, nx, pl.pitch);
+        unpitch_kernel<<<grid, 128, 0, ctx->stream>>>(d_nf, (float *)d, ny, nx, pitch);
         OGN_LAUNCH_CHECK("unpitch_kernel");
         OGN_TRY(ogn_output_commit(ctx, norm_fsf, d, vol * 4));
     }
     return ogn_finish_call(ctx);
-}
-
-template <int ZB, bool PV>
-static int launch_spectral(ogn_ctx *ctx, const TglrPlan &pl, const float *taps, const float *taps_sq,
-                           int ntaps_total, const k2::ProfDesc *desc, int reach, int woff_min, const float *rs,
-                           int nzp, int ncls, int ncx, const uint8_t *mask, float *correl, float *correl_min,
-                           uint8_t *profile, float *maxmap, float *minmap) {
-    auto kern = k2::spectral_glr_kernel<ZB, PV>;
-    // window rows per chunk: the chunk itself, the longest profile, and the ring's read-ahead
-    const int need_rows = k2::NW * ZB + reach + 2 * k2::U;
-    const int nbox = ogn_div_up(need_rows, k2::MAX_BOX_ROWS);
-    const int box_rows = ogn_div_up(need_rows, nbox);
-    const int win_rows = nbox * box_rows;
-    size_t smem = ((size_t)2 * (PV ? 2 : 1) * win_rows * 32 + (size_t)(PV ? 2 : 1) * (ntaps_total + 4)) * sizeof(float) + 16;
-    if (smem > 110 * 1024)
-        return ogn_fail(ctx, OGN_ERR_UNSUPPORTED,
-                        "profile dictionary needs %zu bytes of shared memory per block (limit 110 KiB)", smem);
-    // optional per-warp staging of the mask rows (needs 16-byte aligned rows) and of the denominator rows
-    const int stage_mask = mask && pl.nx % 16 == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0;
-    if (stage_mask) smem += (size_t)2 * k2::NW * ZB * 32;
-    const size_t rs_bytes = (size_t)2 * k2::NW * pl.nprof * ZB * sizeof(float);
-    const int stage_rs = !PV && smem + rs_bytes <= 110 * 1024;
-    if (stage_rs) smem += rs_bytes;
-    OGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUtensorMap num_map, den_map;
-    OGN_TRY(make_tile_map(ctx, &num_map, pl.cube_fsf, pl.nz, pl.ny, pl.nx, pl.pitch, 32, 1, box_rows));
-    if (PV) OGN_TRY(make_tile_map(ctx, &den_map, pl.norm_fsf, pl.nz, pl.ny, pl.nx, pl.pitch, 32, 1, box_rows));
-    else den_map = num_map;
-    const int nchunk = ogn_div_up(pl.nz, k2::NW * ZB);
-    const int cols = (pl.pitch / 32) * pl.ny;
-    // enough blocks for ~8 waves of 2 resident blocks per SM, at most one block per chunk
-    int zsplit = ogn_div_up((int64_t)ctx->sm_count * 2 * 8, cols);
-    zsplit = std::max(1, std::min(zsplit, nchunk));
-    dim3 grid(pl.pitch / 32, pl.ny, zsplit);
-    if (grid.y > 65535) return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "cube too large for the K2 launch grid");
-    kern<<<grid, k2::NW * 32, smem, ctx->stream>>>(num_map, den_map, pl.nz, pl.ny, pl.nx, taps, taps_sq, ntaps_total,
-                                                   desc, pl.nprof, box_rows, nbox, woff_min, rs, nzp, ncls, ncx, pl.P,
-                                                   stage_rs, stage_mask, mask, correl, correl_min, profile, maxmap, minmap);
-    OGN_LAUNCH_CHECK("spectral_glr_kernel");
-    return OGN_OK;
 }
 
 extern "C" int ogn_tglr(ogn_ctx *ctx, const void *cube, int cube_dtype, int nz, int ny, int nx, int nfields,
@@ -843,64 +960,12 @@ extern "C" int ogn_tglr(ogn_ctx *ctx, const void *cube, int cube_dtype, int nz, 
                         const int *tap_offsets, int nprof, const uint8_t *mask, float *correl, float *correl_min,
                         uint8_t *profile, float *maxmap, float *minmap) {
     OGN_TRY(check_dims(ctx, nz, ny, nx, nfields, psize));
-    if (nprof < 1 || nprof > 255)
-        return ogn_fail(ctx, OGN_ERR_ARG, "nprof = %d: the profile index is a uint8 (lib_origin.py:1197), 1..255", nprof);
-    if (!fsf || !taps || !tap_offsets) return ogn_fail(ctx, OGN_ERR_ARG, "fsf / taps / tap_offsets must not be NULL");
     OGN_CUDA(cudaSetDevice(ctx->device));
-    constexpr int ZB = 32;
     const size_t vol = (size_t)nz * ny * nx;
     const size_t img = (size_t)ny * nx;
+    ogn_tglr_setup_t st;
+    OGN_TRY(ogn_tglr_setup(ctx, nz, ny, nx, nullptr, nfields, fsf, psize, weights, taps, tap_offsets, nprof, true, &st));
 
-    TglrPlan pl;
-    pl.nz = nz; pl.ny = ny; pl.nx = nx; pl.pitch = (int)ogn_round_up(nx, 32);
-    pl.P = psize; pl.WP = (psize + 3) / 4 * 4; pl.nfields = nfields; pl.nprof = nprof;
-    pl.pervoxel = weights != nullptr || nfields > 1;
-
-    // ---- profiles: reversed, zero-padded to a multiple of U, float32 ----------------
-    const int ntaps_in = tap_offsets[nprof];
-    std::vector<k2::ProfDesc> desc(nprof);
-    std::vector<float> tp, tpsq;
-    int woff_min = 0, reach = 0;
-    for (int k = 0; k < nprof; ++k) {
-        const int L = tap_offsets[k + 1] - tap_offsets[k];
-        if (L < 1) return ogn_fail(ctx, OGN_ERR_ARG, "profile %d is empty", k);
-        const int ck = (L - 1) / 2;           // 'same' window start, lib_origin.py:1179
-        const int woff = ck - (L - 1);        // first window sample relative to the output index
-        woff_min = std::min(woff_min, woff);
-        const int LP = (int)ogn_round_up(L, k2::U);
-        desc[k].tap_off = (int)tp.size();
-        desc[k].nchunks = LP / k2::U;
-        desc[k].row_off = woff;               // made relative to woff_min below
-        desc[k].pad = 0;
-        for (int i = 0; i < LP; ++i) {
-            double v = i < L ? taps[tap_offsets[k] + (L - 1 - i)] : 0.0;
-            tp.push_back((float)v);
-            tpsq.push_back((float)(v * v));
-        }
-    }
-    for (int k = 0; k < nprof; ++k) {
-        desc[k].row_off -= woff_min;
-        reach = std::max(reach, desc[k].row_off + desc[k].nchunks * k2::U);
-    }
-    const int ntaps_total = (int)tp.size();
-
-    float *d_taps = nullptr, *d_taps_sq = nullptr;
-    k2::ProfDesc *d_desc = nullptr;
-    double *d_taps64 = nullptr;
-    int *d_tapoff = nullptr;
-    OGN_TRY(ogn_scratch_t(ctx, "taps32", (size_t)ntaps_total, &d_taps));
-    OGN_TRY(ogn_scratch_t(ctx, "taps32sq", (size_t)ntaps_total, &d_taps_sq));
-    OGN_TRY(ogn_scratch_t(ctx, "prof_desc", (size_t)nprof, &d_desc));
-    OGN_TRY(ogn_scratch_t(ctx, "taps64", (size_t)ntaps_in, &d_taps64));
-    OGN_TRY(ogn_scratch_t(ctx, "tap_off", (size_t)nprof + 1, &d_tapoff));
-    OGN_CUDA(cudaMemcpyAsync(d_taps, tp.data(), ntaps_total * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    OGN_CUDA(cudaMemcpyAsync(d_taps_sq, tpsq.data(), ntaps_total * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    OGN_CUDA(cudaMemcpyAsync(d_desc, desc.data(), nprof * sizeof(k2::ProfDesc), cudaMemcpyHostToDevice, ctx->stream));
-    OGN_CUDA(cudaMemcpyAsync(d_taps64, taps, ntaps_in * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    OGN_CUDA(cudaMemcpyAsync(d_tapoff, tap_offsets, (nprof + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    OGN_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors above go out of scope
-
-    // ---- inputs ----------------------------------------------------------------------
     const float *dcube = nullptr;
     OGN_TRY(ogn_input_cube_f32(ctx, "cube", cube, cube_dtype, vol, &dcube));
     const uint8_t *dmask = nullptr;
@@ -909,51 +974,15 @@ extern "C" int ogn_tglr(ogn_ctx *ctx, const void *cube, int cube_dtype, int nz, 
         OGN_TRY(ogn_input(ctx, "mask", mask, vol, &d));
         dmask = static_cast<const uint8_t *>(d);
     }
-
-    // ---- K0 + K1 ---------------------------------------------------------------------
-    const int nzp = (int)ogn_round_up(nz, ZB) + ZB;
-    const int ncy = std::min(ny, psize), ncx = std::min(nx, psize);
-    double *normcls = nullptr;
-    OGN_TRY(run_fsf_stage(ctx, dcube, fsf, weights, pl, &normcls, nzp, ncy, ncx));
-
-    float *rs = nullptr;
-    if (!pl.pervoxel) {
-        OGN_TRY(ogn_scratch_t(ctx, "rs", (size_t)nprof * ncy * ncx * nzp, &rs));
-        ogn_timer t_(ctx, "den_table");
-        dim3 grid(ogn_div_up(nzp, 128), ncy * ncx, nprof);
-        den_table_kernel<<<grid, 128, 0, ctx->stream>>>(normcls, nz, nzp, ncy * ncx, d_taps64, d_tapoff, nprof, rs);
-        OGN_LAUNCH_CHECK("den_table_kernel");
-    }
-
-    // ---- K2 ----------------------------------------------------------------------------
     void *d_correl = nullptr, *d_cmin = nullptr, *d_prof = nullptr, *d_maxmap = nullptr, *d_minmap = nullptr;
     if (correl) OGN_TRY(ogn_output(ctx, "out_correl", correl, vol * 4, &d_correl));
     if (correl_min) OGN_TRY(ogn_output(ctx, "out_correl_min", correl_min, vol * 4, &d_cmin));
     if (profile) OGN_TRY(ogn_output(ctx, "out_profile", profile, vol, &d_prof));
-    if (maxmap) {
-        OGN_TRY(ogn_output(ctx, "out_maxmap", maxmap, img * 4, &d_maxmap));
-        fill_f32_kernel<<<ogn_div_up(img, 256), 256, 0, ctx->stream>>>((float *)d_maxmap, img, -INFINITY);
-        OGN_LAUNCH_CHECK("fill_f32_kernel");
-    }
-    if (minmap) {
-        OGN_TRY(ogn_output(ctx, "out_minmap", minmap, img * 4, &d_minmap));
-        fill_f32_kernel<<<ogn_div_up(img, 256), 256, 0, ctx->stream>>>((float *)d_minmap, img, INFINITY);
-        OGN_LAUNCH_CHECK("fill_f32_kernel");
-    }
-    ogn_timer *t_k2 = new ogn_timer(ctx, "k2_spectral_glr");
-    int rc_k2;
-    if (pl.pervoxel)
-        rc_k2 = (launch_spectral<16, true>(ctx, pl, d_taps, d_taps_sq, ntaps_total, d_desc, reach, woff_min, nullptr,
-                                            nzp, 0, 0, dmask,
-                                            (float *)d_correl, (float *)d_cmin, (uint8_t *)d_prof,
-                                            (float *)d_maxmap, (float *)d_minmap));
-    else
-        rc_k2 = (launch_spectral<ZB, false>(ctx, pl, d_taps, d_taps_sq, ntaps_total, d_desc, reach, woff_min, rs,
-                                             nzp, ncy * ncx, ncx, dmask, (float *)d_correl, (float *)d_cmin,
-                                             (uint8_t *)d_prof, (float *)d_maxmap, (float *)d_minmap));
-    delete t_k2;
-    OGN_TRY(rc_k2);
-
+    if (maxmap) OGN_TRY(ogn_output(ctx, "out_maxmap", maxmap, img * 4, &d_maxmap));
+    if (minmap) OGN_TRY(ogn_output(ctx, "out_minmap", minmap, img * 4, &d_minmap));
+    OGN_TRY(ogn_tglr_init_maps(ctx, ctx->stream, (float *)d_maxmap, (float *)d_minmap, img));
+    OGN_TRY(ogn_tglr_window(ctx, ctx->stream, st, dcube, dmask, ogn_window{0, ny, 0, nx}, (float *)d_correl,
+                            (float *)d_cmin, (uint8_t *)d_prof, (float *)d_maxmap, (float *)d_minmap));
     OGN_TRY(ogn_output_commit(ctx, correl, d_correl, vol * 4));
     OGN_TRY(ogn_output_commit(ctx, correl_min, d_cmin, vol * 4));
     OGN_TRY(ogn_output_commit(ctx, profile, d_prof, vol));

@@ -74,6 +74,8 @@ def _as_u8(x, like=None):
     x = np.asarray(x)
     if x.dtype == np.bool_:
         return np.ascontiguousarray(x).view(np.uint8)
+    if x.dtype == np.uint8:                      # any non-zero byte means "masked"; no copy
+        return np.ascontiguousarray(x)
     return np.ascontiguousarray(x != 0).view(np.uint8)
 
 
@@ -292,7 +294,7 @@ def _tglr_args(cube, fsf, weights, profiles, mask, pcut, pmeansub):
 
 
 def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True, out=None, dense=False,
-           capacity=None, want=('correl', 'profile', 'correl_min', 'maxmap', 'minmap'), ctx=None):
+           capacity=None, want=('correl', 'profile', 'correl_min', 'maxmap', 'minmap'), tile=None, ctx=None):
     """The array part of ``ComputeTGLR.run`` (reference steps.py:768-802) in one
     device pass: TGLR, masking, maxmap / minmap and the local extrema.
 
@@ -302,6 +304,12 @@ def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True,
     Returns a dict with the products in ``want`` plus ``extrema``
     (:class:`LocalExtrema`) and, when ``dense``, ``cube_local_max`` /
     ``cube_local_min``.
+
+    Multi-GPU: ``tile`` is an :class:`origin_b200.tiles.Tile` plus the field size,
+    ``(tile, (gny, gnx))``; ``cube`` / ``mask`` are then the tile's padded
+    sub-cube, only the owned window (grown by the extremum radius) is computed,
+    the products are sub-cube shaped, and ``extrema`` holds the owned voxels with
+    linear indices of the whole ``(nz, gny, gnx)`` field.
     """
     cube, fsfs, fsf_ptrs, w_ptrs, taps, offs, nprof, m = _tglr_args(cube, fsf, weights, profiles, mask, pcut, pmeansub)
     if np.isscalar(size):
@@ -327,25 +335,44 @@ def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True,
     if capacity is None:
         capacity = len(out['max_index']) if out.get('max_index') is not None else max(4096, vol // 40)
     counts = np.zeros(2, dtype=np.int64)
+    tdesc, ext_shape = None, cube.shape
+    if tile is not None:
+        if dense:
+            raise ValueError('dense extremum cubes are not produced in tile mode')
+        t, (gny, gnx) = tile
+        tdesc = np.array([gny, gnx, t.py0, t.px0, t.y0 - t.py0, t.y1 - t.py0, t.x0 - t.px0, t.x1 - t.px0],
+                         dtype=np.int32)
+        if (t.py1 - t.py0, t.px1 - t.px0) != (ny, nx):
+            raise ValueError('cube does not have the shape of the padded tile')
+        ext_shape = (nz, gny, gnx)
     while True:
         lists = {}
         for key, dt in (('max_index', np.int64), ('max_value', np.float32), ('min_index', np.int64),
                         ('min_value', np.float32)):
             buf = out.get(key)
             lists[key] = buf if buf is not None and len(buf) >= capacity else _empty_like_kind(cube, (capacity,), dt)
-        rc = ctx.check(ctx.lib.ogn_step05(
-            ctx.handle, ptr(cube), _dtype_code(cube), nz, ny, nx, len(fsfs), fsf_ptrs.address, fsfs[0].shape[1],
-            w_ptrs.address if w_ptrs else None, ptr(taps), ptr(offs), nprof, ptr(m), size[0], size[1], size[2],
-            ptr(res.get('correl')), ptr(res.get('correl_min')), ptr(res.get('profile')), ptr(res.get('maxmap')),
-            ptr(res.get('minmap')), ptr(res.get('cube_local_max')), ptr(res.get('cube_local_min')),
-            ptr(lists['max_index']), ptr(lists['max_value']), ptr(lists['min_index']), ptr(lists['min_value']),
-            capacity, ptr(counts)), allow_overflow=True)
+        if tdesc is None:
+            rc = ctx.lib.ogn_step05(
+                ctx.handle, ptr(cube), _dtype_code(cube), nz, ny, nx, len(fsfs), fsf_ptrs.address, fsfs[0].shape[1],
+                w_ptrs.address if w_ptrs else None, ptr(taps), ptr(offs), nprof, ptr(m), size[0], size[1], size[2],
+                ptr(res.get('correl')), ptr(res.get('correl_min')), ptr(res.get('profile')), ptr(res.get('maxmap')),
+                ptr(res.get('minmap')), ptr(res.get('cube_local_max')), ptr(res.get('cube_local_min')),
+                ptr(lists['max_index']), ptr(lists['max_value']), ptr(lists['min_index']), ptr(lists['min_value']),
+                capacity, ptr(counts))
+        else:
+            rc = ctx.lib.ogn_step05_tile(
+                ctx.handle, ptr(cube), _dtype_code(cube), nz, ny, nx, ptr(tdesc), len(fsfs), fsf_ptrs.address,
+                fsfs[0].shape[1], w_ptrs.address if w_ptrs else None, ptr(taps), ptr(offs), nprof, ptr(m), size[0],
+                size[1], size[2], ptr(res.get('correl')), ptr(res.get('correl_min')), ptr(res.get('profile')),
+                ptr(res.get('maxmap')), ptr(res.get('minmap')), ptr(lists['max_index']), ptr(lists['max_value']),
+                ptr(lists['min_index']), ptr(lists['min_value']), capacity, ptr(counts))
+        rc = ctx.check(rc, allow_overflow=True)
         if rc == 0:
             break
         capacity = int(counts.max())
         out = {k: v for k, v in out.items() if k not in lists}
     n1, n0 = int(counts[0]), int(counts[1])
-    res['extrema'] = LocalExtrema(cube.shape, lists['max_index'][:n1], lists['max_value'][:n1],
+    res['extrema'] = LocalExtrema(ext_shape, lists['max_index'][:n1], lists['max_value'][:n1],
                                   lists['min_index'][:n0], lists['min_value'][:n0])
     return res
 

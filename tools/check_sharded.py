@@ -42,8 +42,14 @@ def main():
                                owned=(t.y0 - t.py0, t.y1 - t.py0, t.x0 - t.px0, t.x1 - t.px0))
     cube_std = torch.from_numpy(s1['cube_std']).to(dev)
     msk = torch.from_numpy(np.ascontiguousarray(mask[sl]).view(np.uint8)).to(dev)
-    res = lib_origin.step05(cube_std, fsf, None, profs, msk, 3, 1e-8, True)
-    ext = ogd.owned_extrema(res['extrema'], t, shape)
+    res = lib_origin.step05(cube_std, fsf, None, profs, msk, 3, 1e-8, True, tile=(t, (ny, nx)))
+    ext = res['extrema']
+    # same lists through the host-side mapping of a full padded-tile run
+    res_full = lib_origin.step05(cube_std, fsf, None, profs, msk, 3, 1e-8, True)
+    ext2 = ogd.owned_extrema(res_full['extrema'], t, shape)
+    assert torch.equal(ext.max_index, ext2.max_index) and torch.equal(ext.min_value, ext2.min_value)
+    ys, xs = t.owned
+    assert torch.equal(res['correl'][:, ys, xs], res_full['correl'][:, ys, xs])
     thr, tab = lib_origin.Compute_threshold_purity(0.8, ext, None, seg, allreduce=red)
     correl_full = ogd.gather_owned(res['correl'], t, plan, shape)
     std_full = ogd.gather_owned(cube_std, t, plan, shape)
