@@ -11,6 +11,7 @@
 //
 // See DESIGN.md for the data layout and the roofline of each kernel.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -223,6 +224,9 @@ fsf_correlate_kernel(const __grid_constant__ CUtensorMap in_map, int in_z_invari
     const int oy = ty0 + row;
     const int ox = tx0 + strip * STRIP;
     const bool live = oy < ony && ox < opitch;
+    // a warp is 32 rows of one strip: warps whose whole patch lies outside the window skip the
+    // arithmetic (they still take part in the barriers), so ragged windows cost 32x32 granularity
+    const bool warp_live = (ty0 + (row & ~31)) < ony && ox < onx;
     const float *trow = tile + row * G::PITCH + strip * STRIP;
     uint32_t phase = 0;
 
@@ -240,7 +244,7 @@ fsf_correlate_kernel(const __grid_constant__ CUtensorMap in_map, int in_z_invari
         for (int i = 0; i < STRIP; ++i) acc[i] = 0.f;
 
 #pragma unroll 1
-        for (int dy = 0; dy < P; ++dy) {
+        for (int dy = 0; dy < (warp_live ? P : 0); ++dy) {
             float in[G::IN_N];
             float w[G::WP];
             const float4 *ip = reinterpret_cast<const float4 *>(trow + dy * G::PITCH);
@@ -261,7 +265,7 @@ fsf_correlate_kernel(const __grid_constant__ CUtensorMap in_map, int in_z_invari
                 for (int i = 0; i < STRIP; ++i) acc[i] = fmaf(w[dx], in[i + dx], acc[i]);
         }
 
-        if (live) {
+        if (live && warp_live) {
             float *op = out + ((size_t)z * ony + oy) * opitch + ox;
 #pragma unroll
             for (int i = 0; i < STRIP / 4; ++i) {
@@ -328,7 +332,6 @@ __global__ void fsf_correlate_naive_kernel(const float *__restrict__ in, int in_
 namespace k2 {
 using namespace tma;
 constexpr int U = 4;
-constexpr int NW = 4;
 constexpr int MAX_BOX_ROWS = 256;
 
 struct ProfDesc {
@@ -337,6 +340,13 @@ struct ProfDesc {
     int row_off;   // window row where this profile's taps start, relative to the block window
     int pad;
 };
+
+// Dictionaries that fit (all shipped ones do) live in constant memory: the taps are then read
+// through the uniform datapath (ULDC) and enter the FFMAs as uniform-register operands, which
+// issue at the full FP32 rate; a vector-register tap costs a third register-file read per FFMA.
+constexpr int CONST_TAPS = 15360;
+__constant__ float4 c_taps4[CONST_TAPS / 4];
+__constant__ ProfDesc c_desc[256];
 
 __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
     if (v >= 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
@@ -348,9 +358,9 @@ __device__ __forceinline__ void atomic_min_float(float *addr, float v) {
 }
 
 // acc[i] += sum_j taps[j] * window[i + j] for one profile, window rows 32 floats apart
-template <int ZB>
+template <int ZB, bool CTAPS>
 __device__ __forceinline__ void ring_correlate(const float *__restrict__ wp, const float4 *__restrict__ tp,
-                                               int nchunks, float (&acc)[ZB]) {
+                                               int tap4, int nchunks, float (&acc)[ZB]) {
     constexpr int RING = ZB + 2 * U;
     constexpr int PERIOD = RING / U;
     static_assert(RING % U == 0, "ring must be a multiple of the chunk");
@@ -359,27 +369,29 @@ __device__ __forceinline__ void ring_correlate(const float *__restrict__ wp, con
     for (int t = 0; t < ZB + U - 1; ++t) ring[t] = wp[t * 32];
 #pragma unroll
     for (int i = 0; i < ZB; ++i) acc[i] = 0.f;
-    float4 e = tp[0];
+    static_assert(PERIOD % 2 == 0, "tap double buffer needs an even period");
+    float4 e[2];
+    e[0] = CTAPS ? c_taps4[tap4] : tp[0];
 #pragma unroll 1
     for (int qb = 0; qb < nchunks; qb += PERIOD) {
 #pragma unroll
         for (int qq = 0; qq < PERIOD; ++qq) {
             if (qb + qq < nchunks) {
                 // taps and window samples of the NEXT chunk are requested before this chunk's FFMAs
-                const float4 e_next = tp[qq + 1];  // one float4 past the profile is readable padding
+                e[(qq + 1) & 1] = CTAPS ? c_taps4[tap4 + qq + 1] : tp[qq + 1];  // one float4 past the profile is padding
 #pragma unroll
                 for (int ii = 0; ii < U; ++ii)
                     ring[(U * qq + ZB + U - 1 + ii) % RING] = wp[(U * qq + ZB + U - 1 + ii) * 32];
-                const float ev[U] = {e.x, e.y, e.z, e.w};
+                const float ev[U] = {e[qq & 1].x, e[qq & 1].y, e[qq & 1].z, e[qq & 1].w};
 #pragma unroll
                 for (int ii = 0; ii < U; ++ii)
 #pragma unroll
                     for (int i = 0; i < ZB; ++i) acc[i] = fmaf(ev[ii], ring[(U * qq + i + ii) % RING], acc[i]);
-                e = e_next;
             }
         }
         wp += PERIOD * U * 32;
         tp += PERIOD;
+        tap4 += PERIOD;
     }
 }
 
@@ -390,8 +402,9 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src, bool vali
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int ZB, bool PERVOXEL>
-__global__ void __launch_bounds__(NW * 32, PERVOXEL ? 2 : (ZB > 24 ? 2 : 3))
+template <int ZB, int NW, bool PERVOXEL, bool CTAPS>
+// no minBlocksPerSM here: with it ptxas (12.9) stops using uniform registers for the taps
+__global__ void __launch_bounds__(NW * 32)
 spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_constant__ CUtensorMap den_map,
                     int nz, int wny, int wnx,            // window (= K1 output) dims
                     int oy_off, int ox_off, int ony, int onx,   // window origin inside the [nz][ony][onx] products
@@ -415,7 +428,9 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
     uint8_t *mask_sm = reinterpret_cast<uint8_t *>(bars + 2);                         // [2][NW][ZB][32]
     float *rs_sm = reinterpret_cast<float *>(mask_sm + (stage_mask ? 2 * NW * ZB * 32 : 0));  // [2][NW][nprof][ZB]
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the shuffle tells the compiler the warp index is warp-uniform, so everything indexed by it
+    // (chunk bounds, profile loop, tap loads) can run on the uniform datapath
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int x0 = blockIdx.x * 32, x = x0 + lane, y = blockIdx.y;   // window coordinates
     const int oy = y + oy_off, ox = x + ox_off;                       // coordinates in the product cubes
     const int nchunk = (nz + NW * ZB - 1) / (NW * ZB);
@@ -509,14 +524,16 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
 
 #pragma unroll 1
             for (int k = 0; k < nprof; ++k) {
-                const ProfDesc d = desc[k];
+                const ProfDesc d = CTAPS ? c_desc[k] : desc[k];
                 float acc[ZB];
-                ring_correlate<ZB>(win + (warp * ZB + d.row_off) * 32 + lane,
-                                   reinterpret_cast<const float4 *>(tap_sm + d.tap_off), d.nchunks, acc);
+                ring_correlate<ZB, CTAPS>(win + (warp * ZB + d.row_off) * 32 + lane,
+                                          reinterpret_cast<const float4 *>(tap_sm + d.tap_off), d.tap_off / 4,
+                                          d.nchunks, acc);
                 if (PERVOXEL) {
                     float den[ZB];
-                    ring_correlate<ZB>(win_den + (warp * ZB + d.row_off) * 32 + lane,
-                                       reinterpret_cast<const float4 *>(tap_sq_sm + d.tap_off), d.nchunks, den);
+                    ring_correlate<ZB, false>(win_den + (warp * ZB + d.row_off) * 32 + lane,
+                                              reinterpret_cast<const float4 *>(tap_sq_sm + d.tap_off), 0, d.nchunks,
+                                              den);
 #pragma unroll
                     for (int i = 0; i < ZB; ++i) acc[i] = den[i] > 0.f ? acc[i] / sqrtf(den[i]) : 0.f;
                 } else if (rs_staged) {
@@ -847,14 +864,20 @@ static int run_fsf_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setu
     return OGN_OK;
 }
 
-template <int ZB, bool PV>
+template <int ZB, int NW, bool PV, bool CT>
 static int launch_spectral(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, ogn_window w,
                            const float *cube_fsf, const float *norm_fsf, int pitch, const uint8_t *mask,
                            float *correl, float *correl_min, uint8_t *profile, float *maxmap, float *minmap) {
-    auto kern = k2::spectral_glr_kernel<ZB, PV>;
+    auto kern = k2::spectral_glr_kernel<ZB, NW, PV, CT>;
+    if (CT) {
+        OGN_CUDA(cudaMemcpyToSymbolAsync(k2::c_taps4, st.d_taps, (size_t)st.ntaps_total * sizeof(float), 0,
+                                         cudaMemcpyDeviceToDevice, stream));
+        OGN_CUDA(cudaMemcpyToSymbolAsync(k2::c_desc, st.d_desc, (size_t)st.nprof * sizeof(k2::ProfDesc), 0,
+                                         cudaMemcpyDeviceToDevice, stream));
+    }
     const int wny = w.y1 - w.y0, wnx = w.x1 - w.x0;
     // window rows per chunk: the chunk itself, the longest profile, and the ring's read-ahead
-    const int need_rows = k2::NW * ZB + st.reach + 2 * k2::U;
+    const int need_rows = NW * ZB + st.reach + 2 * k2::U;
     const int nbox = ogn_div_up(need_rows, k2::MAX_BOX_ROWS);
     const int box_rows = ogn_div_up(need_rows, nbox);
     const int win_rows = nbox * box_rows;
@@ -864,8 +887,8 @@ static int launch_spectral(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_set
                         "profile dictionary needs %zu bytes of shared memory per block (limit 110 KiB)", smem);
     // optional per-warp staging of the mask rows (needs 16-byte aligned rows) and of the denominator rows
     const int stage_mask = mask && st.nx % 16 == 0 && w.x0 % 16 == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0;
-    if (stage_mask) smem += (size_t)2 * k2::NW * ZB * 32;
-    const size_t rs_bytes = (size_t)2 * k2::NW * st.nprof * ZB * sizeof(float);
+    if (stage_mask) smem += (size_t)2 * NW * ZB * 32;
+    const size_t rs_bytes = (size_t)2 * NW * st.nprof * ZB * sizeof(float);
     const int stage_rs = !PV && smem + rs_bytes <= 110 * 1024;
     if (stage_rs) smem += rs_bytes;
     OGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -873,14 +896,14 @@ static int launch_spectral(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_set
     OGN_TRY(make_tile_map(ctx, &num_map, cube_fsf, st.nz, wny, wnx, pitch, 32, 1, box_rows));
     if (PV) OGN_TRY(make_tile_map(ctx, &den_map, norm_fsf, st.nz, wny, wnx, pitch, 32, 1, box_rows));
     else den_map = num_map;
-    const int nchunk = ogn_div_up(st.nz, k2::NW * ZB);
+    const int nchunk = ogn_div_up(st.nz, NW * ZB);
     const int cols = (pitch / 32) * wny;
     // enough blocks for ~8 waves of 2 resident blocks per SM, at most one block per chunk
     int zsplit = ogn_div_up((int64_t)ctx->sm_count * 2 * 8, cols);
     zsplit = std::max(1, std::min(zsplit, nchunk));
     dim3 grid(pitch / 32, wny, zsplit);
     if (grid.y > 65535) return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "cube too large for the K2 launch grid");
-    kern<<<grid, k2::NW * 32, smem, stream>>>(num_map, den_map, st.nz, wny, wnx, w.y0, w.x0, st.ny, st.nx,
+    kern<<<grid, NW * 32, smem, stream>>>(num_map, den_map, st.nz, wny, wnx, w.y0, w.x0, st.ny, st.nx,
                                               w.y0 + st.place.gy0, w.x0 + st.place.gx0, st.place.gny, st.place.gnx,
                                               st.d_taps, st.d_taps_sq, st.ntaps_total,
                                               static_cast<const k2::ProfDesc *>(st.d_desc), st.nprof, box_rows, nbox,
@@ -906,10 +929,21 @@ int ogn_tglr_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &s
     }
     ogn_timer t_(ctx, "k2_spectral_glr");
     if (st.pervoxel)
-        return launch_spectral<16, true>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, dmask, d_correl, d_cmin,
-                                         d_prof, d_maxmap, d_minmap);
-    return launch_spectral<32, false>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, dmask, d_correl, d_cmin, d_prof,
-                                      d_maxmap, d_minmap);
+        return launch_spectral<16, 4, true, false>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, dmask, d_correl,
+                                                   d_cmin, d_prof, d_maxmap, d_minmap);
+    static const int variant = getenv("OGN_K2_VARIANT") ? atoi(getenv("OGN_K2_VARIANT")) : 0;
+#define OGN_K2(ZB_, NW_, CT_) launch_spectral<ZB_, NW_, false, CT_>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, dmask, \
+                                                                  d_correl, d_cmin, d_prof, d_maxmap, d_minmap)
+    const bool fits = st.ntaps_total + 4 <= k2::CONST_TAPS;
+    // default: 16 wavelengths per thread, 4 warps, taps through the uniform datapath (fastest measured)
+    switch (fits ? variant : 100) {
+        case 1: return OGN_K2(32, 4, true);
+        case 10: return OGN_K2(32, 4, false);
+        case 11: return OGN_K2(16, 8, false);
+        case 100: return OGN_K2(32, 4, false);
+        default: return OGN_K2(16, 4, true);
+    }
+#undef OGN_K2
 }
 
 int ogn_tglr_init_maps(ogn_ctx *ctx, cudaStream_t stream, float *d_maxmap, float *d_minmap, size_t img) {
