@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include "ogn_common.cuh"
+#include "ogn_tma.cuh"
 
 // A maximum filter with scipy's 'reflect' boundary only ever sees in-range
 // samples (the reflected positions lie inside the clipped window), so the
@@ -308,6 +309,196 @@ local_extrema3_brick_kernel(const float *__restrict__ a, const float *__restrict
     }
 }
 
+// TMA-staged, vectorised 3 x 3 x 3 pass (the default when nx % 4 == 0).  Same decomposition as
+// local_extrema3_kernel — x by shuffles, y through a double-buffered shared tile, z in registers,
+// one block barrier per plane — but
+//  * the raw planes arrive by TMA: per plane one elected thread issues two 3-D bulk tensor loads
+//    (box {136 x, TY+2 y, 1 z} of each array, starting 4 columns / 1 row outside the tile so the
+//    halo comes with it) into a ring of E4_NST shared-memory stages; E4_NST-1 planes are in flight
+//    while one is reduced, without costing registers.  Elements outside the cube are filled with
+//    NaN by the TMA unit: fmaxf / fminf ignore NaN operands, which is exactly scipy's 'reflect'
+//    maximum filter (out-of-range neighbours never win) — no edge tests in the kernel;
+//  * every lane owns FOUR consecutive x (one LDS.128 per array and plane), so a warp covers 128
+//    voxels of a row and the instruction count per voxel is ~6x below the scalar kernel: the pass
+//    is limited by HBM, not by issue slots.
+// Flag words keep the layout of the scalar kernels (one 32-bit word per 32 consecutive x): the
+// 4-bit nibbles of 8 neighbouring lanes are OR-ed with three shuffles.
+constexpr int E4_TY = 14;    // output rows per block; 16 warps with the two halo rows
+constexpr int E4_CZ = 64;    // planes per block (E4_CZ + 2 is a multiple of E4_NST)
+constexpr int E4_NST = 3;    // raw-plane stages (= unroll factor of the plane loop)
+constexpr int E4_BX = 136;   // TMA box width: 128 + 4 columns either side (16-byte granularity)
+constexpr int E4_ROWS = E4_TY + 2;
+constexpr int E4_STAGE_FLOATS = 2 * E4_ROWS * E4_BX;   // a rows, then b rows
+constexpr int E4_XROWS = E4_ROWS + 2;                  // exchange tile rows (one pad row either side)
+constexpr int E4_SMEM = E4_NST * E4_STAGE_FLOATS * 4 + 2 * 2 * E4_XROWS * 32 * 16 + E4_NST * 8;
+
+__device__ __forceinline__ float max3(float x, float y, float z) { return fmaxf(fmaxf(x, y), z); }
+__device__ __forceinline__ float min3(float x, float y, float z) { return fminf(fminf(x, y), z); }
+__device__ __forceinline__ float4 max3v(float4 p, float4 q, float4 r) {
+    return make_float4(max3(p.x, q.x, r.x), max3(p.y, q.y, r.y), max3(p.z, q.z, r.z), max3(p.w, q.w, r.w));
+}
+__device__ __forceinline__ float4 min3v(float4 p, float4 q, float4 r) {
+    return make_float4(min3(p.x, q.x, r.x), min3(p.y, q.y, r.y), min3(p.z, q.z, r.z), min3(p.w, q.w, r.w));
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(32 * E4_ROWS, 2)
+local_extrema3_tma_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
+                          const uint8_t *__restrict__ mask, int nz, int ny, int nx, int oy0, int oy1, int ox0a,
+                          int ox0, int ox1, float *__restrict__ dense_max, float *__restrict__ dense_min,
+                          uint32_t *__restrict__ flag_max, uint32_t *__restrict__ flag_min, int nxw) {
+    using namespace tma;
+    extern __shared__ __align__(128) unsigned char e4_smem[];
+    float *raw = reinterpret_cast<float *>(e4_smem);                                  // [NST][2][ROWS][BX]
+    float4 *xa = reinterpret_cast<float4 *>(e4_smem + E4_NST * E4_STAGE_FLOATS * 4);  // [2][XROWS][32]
+    float4 *xb = xa + 2 * E4_XROWS * 32;                                              // [2][XROWS][32]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(xb + 2 * E4_XROWS * 32);            // [NST]
+
+    const int lane = threadIdx.x, row = threadIdx.y;  // rows 0 and E4_TY+1 are halo rows
+    const int tid = row * 32 + lane;
+    const int x0 = ox0a + blockIdx.x * 128, x = x0 + 4 * lane;
+    const int ty0 = oy0 + blockIdx.y * E4_TY;         // first output row of the block
+    const int y = ty0 + row - 1;
+    const int zc0 = blockIdx.z * E4_CZ, zc1 = min(nz, zc0 + E4_CZ);
+    const bool is_l = lane == 0, is_r = lane == 31;
+    const bool out_row = row >= 1 && row <= E4_TY && y < oy1;
+    const bool m_ok = mask != nullptr && out_row && x < nx;
+    uint32_t colbits = 0;  // voxels of this lane that are outputs (none for the halo warps)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (out_row && x + i >= ox0 && x + i < ox1) colbits |= 1u << i;
+    const size_t plane = (size_t)ny * nx;
+    const int wcol = blockIdx.x * 4 + (lane >> 3);
+    const bool w_ok = out_row && (lane & 7) == 0 && wcol < nxw;
+    const uint32_t yx = out_row ? (uint32_t)y * nx + x : 0u;   // offset inside a plane
+    const uint32_t wyx = (out_row ? (uint32_t)(y - oy0) : 0u) * nxw + wcol;
+    const uint32_t wstride = (uint32_t)(oy1 - oy0) * nxw;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < E4_NST; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    // Planes zc0-1 .. zc1 are needed; the loop walks a multiple of 2 E4_NST planes (extra planes are
+    // loaded and reduced but never output).  Plane indices outside [0, nz) are legal: NaN fill.
+    const int nplanes = (zc1 - zc0 + 2 + 2 * E4_NST - 1) / (2 * E4_NST) * (2 * E4_NST);
+    auto issue = [&](int it) {  // elected thread: plane zc0 - 1 + it into stage it % NST
+        float *dst = raw + (it % E4_NST) * E4_STAGE_FLOATS;
+        uint64_t *bar = &bars[it % E4_NST];
+        mbar_expect_tx(bar, E4_STAGE_FLOATS * 4);
+        tma_load_3d(dst, &a_map, bar, x0 - 4, ty0 - 1, zc0 - 1 + it);
+        tma_load_3d(dst + E4_ROWS * E4_BX, &b_map, bar, x0 - 4, ty0 - 1, zc0 - 1 + it);
+    };
+    if (tid == 0)
+        for (int it = 0; it < E4_NST; ++it) issue(it);
+
+    // mask words are prefetched two planes ahead in registers (4 bytes per thread and plane)
+    uint32_t m_use = 0, m_nxt = 0;
+    if (m_ok) m_use = __ldg(reinterpret_cast<const uint32_t *>(mask + (size_t)zc0 * plane + yx));
+    if (m_ok && zc0 + 1 < zc1) m_nxt = __ldg(reinterpret_cast<const uint32_t *>(mask + (size_t)(zc0 + 1) * plane + yx));
+
+    const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    const float4 pinf4 = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+    float4 pa_prev = ninf4, pa_cur = ninf4, ca_cur = ninf4;
+    float4 pb_prev = pinf4, pb_cur = pinf4, cb_cur = pinf4;
+    const float *ra0 = raw + row * E4_BX, *rb0 = ra0 + E4_ROWS * E4_BX;
+    float4 *ea0 = xa + (row + 1) * 32 + lane, *eb0 = xb + (row + 1) * 32 + lane;
+
+#pragma unroll 1
+    for (int it0 = 0; it0 < nplanes; it0 += 2 * E4_NST) {
+#pragma unroll
+        for (int s = 0; s < 2 * E4_NST; ++s) {   // unrolled by 2 x NST: stage and exchange buffer are static
+            const int it = it0 + s;
+            const int p = zc0 - 1 + it, st = s % E4_NST, buf = s & 1;
+            mbar_wait(&bars[st], (s / E4_NST) & 1);  // it0 is a multiple of 2 NST: the parity is static
+            const float *ra = ra0 + st * E4_STAGE_FLOATS, *rb = rb0 + st * E4_STAGE_FLOATS;
+            const float4 va = *reinterpret_cast<const float4 *>(ra + 4 + 4 * lane);
+            const float4 vb = *reinterpret_cast<const float4 *>(rb + 4 + 4 * lane);
+            float l = __shfl_up_sync(0xffffffffu, va.w, 1), r = __shfl_down_sync(0xffffffffu, va.x, 1);
+            if (is_l) l = ra[3];
+            if (is_r) r = ra[132];
+            const float4 ha = make_float4(max3(l, va.x, va.y), max3(va.x, va.y, va.z), max3(va.y, va.z, va.w),
+                                          max3(va.z, va.w, r));
+            l = __shfl_up_sync(0xffffffffu, vb.w, 1);
+            r = __shfl_down_sync(0xffffffffu, vb.x, 1);
+            if (is_l) l = rb[3];
+            if (is_r) r = rb[132];
+            const float4 hb = make_float4(min3(l, vb.x, vb.y), min3(vb.x, vb.y, vb.z), min3(vb.y, vb.z, vb.w),
+                                          min3(vb.z, vb.w, r));
+            float4 *ea = ea0 + buf * E4_XROWS * 32, *eb = eb0 + buf * E4_XROWS * 32;
+            *ea = ha;
+            *eb = hb;
+            __syncthreads();
+            // every thread has read its raw row: the stage can be refilled
+            if (tid == 0 && it + E4_NST < nplanes) issue(it + E4_NST);
+            // the halo warps run the same code on the pad rows of the exchange tile; they own no outputs
+            const float4 m9a = max3v(ea[-32], ha, ea[32]);
+            const float4 m9b = min3v(eb[-32], hb, eb[32]);
+            const float4 wa = max3v(pa_prev, pa_cur, m9a);
+            const float4 wb = min3v(pb_prev, pb_cur, m9b);
+            const bool emit = p > zc0 && p <= zc1;  // output plane p - 1 in [zc0, zc1); block-uniform
+            const uint32_t m_cur = m_use;
+            if (emit) {
+                m_use = m_nxt;
+                m_nxt = 0;
+                if (m_ok && p + 1 < zc1)
+                    m_nxt = __ldg(reinterpret_cast<const uint32_t *>(mask + (size_t)(p + 1) * plane + yx));
+            }
+            uint32_t free4 = 0;  // bit i set: voxel i is an output and not masked
+            free4 |= (m_cur & 0x000000ffu) ? 0u : 1u;
+            free4 |= (m_cur & 0x0000ff00u) ? 0u : 2u;
+            free4 |= (m_cur & 0x00ff0000u) ? 0u : 4u;
+            free4 |= (m_cur & 0xff000000u) ? 0u : 8u;
+            free4 &= colbits;
+            uint32_t ka = 0, kb = 0;
+            ka |= ca_cur.x == wa.x ? 1u : 0u;
+            ka |= ca_cur.y == wa.y ? 2u : 0u;
+            ka |= ca_cur.z == wa.z ? 4u : 0u;
+            ka |= ca_cur.w == wa.w ? 8u : 0u;
+            kb |= cb_cur.x == wb.x ? 1u : 0u;
+            kb |= cb_cur.y == wb.y ? 2u : 0u;
+            kb |= cb_cur.z == wb.z ? 4u : 0u;
+            kb |= cb_cur.w == wb.w ? 8u : 0u;
+            ka &= free4;
+            kb &= free4;
+            if (DENSE && emit && colbits) {
+                const size_t oidx = (size_t)(p - 1) * plane + yx;
+                const float4 da = make_float4((ka & 1u) ? ca_cur.x : 0.f, (ka & 2u) ? ca_cur.y : 0.f,
+                                              (ka & 4u) ? ca_cur.z : 0.f, (ka & 8u) ? ca_cur.w : 0.f);
+                const float4 db = make_float4((kb & 1u) ? -cb_cur.x : 0.f, (kb & 2u) ? -cb_cur.y : 0.f,
+                                              (kb & 4u) ? -cb_cur.z : 0.f, (kb & 8u) ? -cb_cur.w : 0.f);
+                if (colbits == 0xfu) {
+                    if (dense_max) *reinterpret_cast<float4 *>(dense_max + oidx) = da;
+                    if (dense_min) *reinterpret_cast<float4 *>(dense_min + oidx) = db;
+                } else {
+                    const float dav[4] = {da.x, da.y, da.z, da.w}, dbv[4] = {db.x, db.y, db.z, db.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (colbits & (1u << i)) {
+                            if (dense_max) dense_max[oidx + i] = dav[i];
+                            if (dense_min) dense_min[oidx + i] = dbv[i];
+                        }
+                }
+            }
+            // nibbles of 8 neighbouring lanes -> one flag word (bit = x offset inside the word)
+            uint32_t fa = ka << (4 * (lane & 7)), fb = kb << (4 * (lane & 7));
+            fa |= __shfl_xor_sync(0xffffffffu, fa, 1); fb |= __shfl_xor_sync(0xffffffffu, fb, 1);
+            fa |= __shfl_xor_sync(0xffffffffu, fa, 2); fb |= __shfl_xor_sync(0xffffffffu, fb, 2);
+            fa |= __shfl_xor_sync(0xffffffffu, fa, 4); fb |= __shfl_xor_sync(0xffffffffu, fb, 4);
+            if (emit && w_ok) {
+                const size_t widx = (size_t)(p - 1) * wstride + wyx;
+                flag_max[widx] = fa;
+                flag_min[widx] = fb;
+            }
+            pa_prev = pa_cur; pa_cur = m9a; ca_cur = va;
+            pb_prev = pb_cur; pb_cur = m9b; cb_cur = vb;
+        }
+    }
+}
+
 // ---- exclusive scan of popcounts (3 phases, 1024 words per block) ------------------------
 constexpr int SCAN_BLOCK = 1024;
 
@@ -526,7 +717,26 @@ int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t 
     // the barrier-free brick kernel is kept for experiments (OGN_K3_BRICK=1); the shared-memory
     // tile kernel is faster on B200 as measured (2.4 ms vs 3.4 ms at 3681x320x320)
     static const bool use_brick_kernel = getenv("OGN_K3_BRICK") != nullptr;
-    if (sz == 3 && sy == 3 && sx == 3 && use_brick_kernel) {
+    static const bool no_v4_kernel = getenv("OGN_K3_SCALAR") != nullptr;
+    const bool vec_ok = nx % 4 == 0 && ((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(db)) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(dm) & 3) == 0 &&
+                        (!d_dmax || (reinterpret_cast<uintptr_t>(d_dmax) & 15) == 0) &&
+                        (!d_dmin || (reinterpret_cast<uintptr_t>(d_dmin) & 15) == 0);
+    if (sz == 3 && sy == 3 && sx == 3 && vec_ok && !use_brick_kernel && !no_v4_kernel) {
+        CUtensorMap a_map, b_map;
+        OGN_TRY(ogn_make_tile_map(ctx, &a_map, (const float *)da, nz, ny, nx, nx, E4_BX, E4_ROWS, 1, true));
+        OGN_TRY(ogn_make_tile_map(ctx, &b_map, (const float *)db, nz, ny, nx, nx, E4_BX, E4_ROWS, 1, true));
+        auto kern = (d_dmax || d_dmin) ? local_extrema3_tma_kernel<true> : local_extrema3_tma_kernel<false>;
+        OGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, E4_SMEM));
+        dim3 block(32, E4_ROWS);
+        dim3 grid(ogn_div_up(nxw, 4), ogn_div_up(ony, E4_TY), ogn_div_up(nz, E4_CZ));
+        kern<<<grid, block, E4_SMEM, ctx->stream>>>(a_map, b_map, (const uint8_t *)dm, nz, ny, nx,
+                                                                        owned.y0, owned.y1, ox0a, owned.x0, owned.x1,
+                                                                        (float *)d_dmax, (float *)d_dmin, flag_max,
+                                                                        flag_min, nxw);
+        delete t_k3;
+        OGN_LAUNCH_CHECK("local_extrema3_tma_kernel");
+    } else if (sz == 3 && sy == 3 && sx == 3 && use_brick_kernel) {
         const int nby = ogn_div_up(ony, BR_R), nbz = ogn_div_up(nz, BR_CZ);
         const long long nbrick = (long long)nxw * nby * nbz;
         const unsigned blocks = (unsigned)((nbrick + BR_WARPS - 1) / BR_WARPS);

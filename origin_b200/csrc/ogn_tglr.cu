@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "ogn_common.cuh"
+#include "ogn_tma.cuh"
 
 // ---------------------------------------------------------------------------
 // Edge classes.  With a single FSF the denominator of the GLR does not depend
@@ -137,41 +138,6 @@ __global__ void den_table_kernel(const double *__restrict__ normcls, int nz, int
 // consecutive rows) and the P weights of the row (LDS.128 broadcast) and issues
 // 32*P FFMAs from registers.
 // ---------------------------------------------------------------------------
-namespace tma {
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(phase)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-}  // namespace tma
 
 namespace k1 {
 using namespace tma;
@@ -630,33 +596,6 @@ __global__ void unpitch_kernel(const float *__restrict__ src, float *__restrict_
     if (x < nx) dst[((size_t)z * ny + y) * nx + x] = src[((size_t)z * ny + y) * pitch + x];
 }
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                    CUtensorMapFloatOOBfill);
-
-static int make_tile_map(ogn_ctx *ctx, CUtensorMap *map, const float *base, int nz, int ny, int nx, int pitch,
-                         int box_x, int box_y, int box_z = 1) {
-    static PFN_encodeTiled encode = nullptr;
-    if (!encode) {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
-            return ogn_fail(ctx, OGN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-        encode = reinterpret_cast<PFN_encodeTiled>(fn);
-    }
-    cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
-    cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)ny * pitch * 4};
-    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, (cuuint32_t)box_z};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box,
-                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return ogn_fail(ctx, OGN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return OGN_OK;
-}
-
 // Launch K1 (or the naive fallback) for one field: out (+)= corr(in, weights) on the output window
 // [wy0, wy0+wny) x [wx0, wx0+wnx) of the input; out is window-relative [nz][wny][opitch].
 //   in: device f32 [nz or 1][iny][ipitch], 16-byte aligned, ipitch % 4 == 0
@@ -666,7 +605,7 @@ static int launch_fsf_correlate(ogn_ctx *ctx, cudaStream_t stream, const float *
     if (P == 25) {
         using G = k1::Geo<25>;
         CUtensorMap map;
-        OGN_TRY(make_tile_map(ctx, &map, in, in_z_invariant ? 1 : nz, iny, inx, ipitch, G::PITCH, G::ROWS));
+        OGN_TRY(ogn_make_tile_map(ctx, &map, in, in_z_invariant ? 1 : nz, iny, inx, ipitch, G::PITCH, G::ROWS));
         auto kern = k1::fsf_correlate_kernel<25>;
         static bool attr_set = false;
         if (!attr_set) {
@@ -893,8 +832,8 @@ static int launch_spectral(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_set
     if (stage_rs) smem += rs_bytes;
     OGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUtensorMap num_map, den_map;
-    OGN_TRY(make_tile_map(ctx, &num_map, cube_fsf, st.nz, wny, wnx, pitch, 32, 1, box_rows));
-    if (PV) OGN_TRY(make_tile_map(ctx, &den_map, norm_fsf, st.nz, wny, wnx, pitch, 32, 1, box_rows));
+    OGN_TRY(ogn_make_tile_map(ctx, &num_map, cube_fsf, st.nz, wny, wnx, pitch, 32, 1, box_rows));
+    if (PV) OGN_TRY(ogn_make_tile_map(ctx, &den_map, norm_fsf, st.nz, wny, wnx, pitch, 32, 1, box_rows));
     else den_map = num_map;
     const int nchunk = ogn_div_up(st.nz, NW * ZB);
     const int cols = (pitch / 32) * wny;
