@@ -75,6 +75,11 @@ OGN_API int64_t ogn_launch_count(const ogn_ctx *ctx);
  * stage timed since the previous report into buf, and clears the list. */
 OGN_API int ogn_timing_enable(ogn_ctx *ctx, int on);
 OGN_API int ogn_timing_report(ogn_ctx *ctx, char *buf, size_t size);
+/* Diagnostics of the last ogn_tglr / ogn_fsf_stage / ogn_step05* call on `ctx`: *folded receives 1
+ * when every FSF plane was mirror-symmetric in y (as float32) and the spatial stage therefore added
+ * footprint rows dy and P-1-dy before multiplying (half the FFMAs of _convolve_fsf's direct form,
+ * lib_origin.py:1027-1043), 0 when the general kernel ran.  Synchronises the stream. */
+OGN_API int ogn_fsf_folded(ogn_ctx *ctx, int *folded);
 /* Release the context's scratch memory (it is re-grown on demand). */
 OGN_API int ogn_trim(ogn_ctx *ctx);
 /* Pinned host memory for fast staging (optional; any host pointer works). */

@@ -27,6 +27,7 @@ SIGNATURES = {
     'ogn_synchronize': (c_int, [c_void_p]),
     'ogn_launch_count': (c_int64, [c_void_p]),
     'ogn_trim': (c_int, [c_void_p]),
+    'ogn_fsf_folded': (c_int, [c_void_p, c_void_p]),
     'ogn_timing_enable': (c_int, [c_void_p, c_int]),
     'ogn_timing_report': (c_int, [c_void_p, ctypes.c_char_p, ctypes.c_size_t]),
     'ogn_host_alloc': (c_int, [ctypes.c_size_t, ctypes.POINTER(c_void_p)]),
@@ -148,6 +149,13 @@ class Context:
 
     def trim(self):
         self.check(self.lib.ogn_trim(self.handle))
+
+    @property
+    def fsf_folded(self):
+        """True when the last TGLR call used the row-folded spatial kernel (mirror-symmetric FSF)."""
+        v = c_int(0)
+        self.check(self.lib.ogn_fsf_folded(self.handle, ctypes.byref(v)))
+        return bool(v.value)
 
     def close(self):
         if getattr(self, 'handle', None):

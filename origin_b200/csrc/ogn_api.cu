@@ -117,6 +117,17 @@ extern "C" int ogn_timing_report(ogn_ctx *ctx, char *buf, size_t size) {
     return OGN_OK;
 }
 
+extern "C" int ogn_fsf_folded(ogn_ctx *ctx, int *folded) {
+    if (!ctx || !folded) return OGN_ERR_ARG;
+    auto it = ctx->bufs.find("fsf_asym");
+    if (it == ctx->bufs.end() || !it->second.p) return ogn_fail(ctx, OGN_ERR_ARG, "no TGLR call has run on this context");
+    int asym = 1;
+    OGN_CUDA(cudaMemcpyAsync(&asym, it->second.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+    *folded = asym == 0;
+    return OGN_OK;
+}
+
 extern "C" int64_t ogn_launch_count(const ogn_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int ogn_host_alloc(size_t bytes, void **out) {

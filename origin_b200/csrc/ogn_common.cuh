@@ -135,6 +135,7 @@ struct ogn_tglr_setup_t {
     bool pervoxel = false;
     ogn_place place{0, 0, 0, 0};
     float *w32 = nullptr, *w32sq = nullptr, *rs = nullptr;
+    int *asym = nullptr;   // device flag: != 0 when the FSF weights are not mirror-symmetric in y
     int nzp = 0, ncy = 0, ncx = 0;
     float *d_taps = nullptr, *d_taps_sq = nullptr;
     const void *d_desc = nullptr;

@@ -48,9 +48,11 @@ __host__ __device__ static inline void cls_range(int c, int n, int P, int *lo, i
 //   w32   [nf][nz][P][WP] float   K = psf - mean(psf), rows padded to WP with zeros
 //   w32sq [nf][nz][P][WP] float   K^2 (only when want_sq: weighted / multi-field path)
 //   normcls [NC][nzp] double      box sums of K^2 per edge class (single-field path)
+//   asym                          set to 1 when some plane's weights are not mirror-symmetric in y
 __global__ void fsf_prep_kernel(const double *const *__restrict__ fsf, int nz, int P, int WP,
                                 float *__restrict__ w32, float *__restrict__ w32sq,
-                                double *__restrict__ normcls, int nzp, int ny, int nx, int ncy, int ncx) {
+                                double *__restrict__ normcls, int nzp, int ny, int nx, int ncy, int ncx,
+                                int *__restrict__ asym) {
     extern __shared__ double sm[];
     double *k2 = sm;           // P*P, later its 2-D inclusive prefix sum
     double *red = sm + P * P;  // 32
@@ -76,6 +78,9 @@ __global__ void fsf_prep_kernel(const double *const *__restrict__ fsf, int nz, i
         wz[i] = (float)k;
         if (wq) wq[i] = (float)(k * k);
         if (dx < P) k2[dy * P + dx] = k * k;
+        // y-mirror symmetry of the float32 weights (what K1 multiplies with) decides whether K1 may
+        // fold rows dy and P-1-dy; any mismatch in any plane clears the fast path
+        if (dx < P && (float)k != (float)(psf[(P - 1 - dy) * P + dx] - mean)) atomicOr(asym, 1);
     }
     if (!normcls) return;
     __syncthreads();
@@ -160,12 +165,48 @@ struct Geo {
     static_assert(PITCH <= 256, "TMA box dimension limit");
 };
 
+// in[0..N) = row[0..N)  (LDS.128)
+template <int N>
+__device__ __forceinline__ void load_row(float (&in)[N], const float *row) {
+    const float4 *ip = reinterpret_cast<const float4 *>(row);
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+        const float4 v = ip[i];
+        in[4 * i] = v.x; in[4 * i + 1] = v.y; in[4 * i + 2] = v.z; in[4 * i + 3] = v.w;
+    }
+}
+// in[0..N) += row[0..N)
+template <int N>
+__device__ __forceinline__ void add_row(float (&in)[N], const float *row) {
+    const float4 *ip = reinterpret_cast<const float4 *>(row);
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+        const float4 v = ip[i];
+        in[4 * i] += v.x; in[4 * i + 1] += v.y; in[4 * i + 2] += v.z; in[4 * i + 3] += v.w;
+    }
+}
+// acc[i] += sum_dx wrow[dx] * in[i + dx]: the P weights of the row are one broadcast LDS.128 per four
+template <int P, int WP, int N>
+__device__ __forceinline__ void strip_fma(float (&acc)[STRIP], const float (&in)[N], const float *wrow) {
+    float w[WP];
+    const float4 *wp = reinterpret_cast<const float4 *>(wrow);
+#pragma unroll
+    for (int i = 0; i < WP / 4; ++i) {
+        const float4 v = wp[i];
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+#pragma unroll
+    for (int dx = 0; dx < P; ++dx)
+#pragma unroll
+        for (int i = 0; i < STRIP; ++i) acc[i] = fmaf(w[dx], in[i + dx], acc[i]);
+}
+
 template <int P>
 __global__ void __launch_bounds__(THREADS, 4)
 fsf_correlate_kernel(const __grid_constant__ CUtensorMap in_map, int in_z_invariant,
                      const float *__restrict__ weights,  // [nz][P][WP]
                      float *__restrict__ out, int oy0, int ox0, int ony, int onx, int opitch,
-                     int nz, int zsplit, int accumulate) {
+                     int nz, int zsplit, int accumulate, const int *__restrict__ asym) {
     using G = Geo<P>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *tile = reinterpret_cast<float *>(smem_raw);
@@ -194,6 +235,7 @@ fsf_correlate_kernel(const __grid_constant__ CUtensorMap in_map, int in_z_invari
     // arithmetic (they still take part in the barriers), so ragged windows cost 32x32 granularity
     const bool warp_live = (ty0 + (row & ~31)) < ony && ox < onx;
     const float *trow = tile + row * G::PITCH + strip * STRIP;
+    const bool fold = asym != nullptr && *asym == 0;  // block-uniform
     uint32_t phase = 0;
 
     for (int z = zbeg; z < zend; ++z) {
@@ -209,26 +251,29 @@ fsf_correlate_kernel(const __grid_constant__ CUtensorMap in_map, int in_z_invari
 #pragma unroll
         for (int i = 0; i < STRIP; ++i) acc[i] = 0.f;
 
+        if (fold) {
+            // mirror-symmetric weights: rows c+d and c-d of the footprint share their weights, so the
+            // two input rows are added first (IN_N FADDs, amortised over the P taps of the row) and
+            // the row costs one set of STRIP*P FFMAs instead of two
+            if (warp_live) {
+                float in[G::IN_N];
+                load_row<G::IN_N>(in, trow + (P / 2) * G::PITCH);
+                strip_fma<P, G::WP>(acc, in, wsm + (P / 2) * G::WP);
+            }
 #pragma unroll 1
-        for (int dy = 0; dy < (warp_live ? P : 0); ++dy) {
-            float in[G::IN_N];
-            float w[G::WP];
-            const float4 *ip = reinterpret_cast<const float4 *>(trow + dy * G::PITCH);
-            const float4 *wp = reinterpret_cast<const float4 *>(wsm + dy * G::WP);
-#pragma unroll
-            for (int i = 0; i < G::IN_N / 4; ++i) {
-                float4 v = ip[i];
-                in[4 * i] = v.x; in[4 * i + 1] = v.y; in[4 * i + 2] = v.z; in[4 * i + 3] = v.w;
+            for (int d = 1; d <= (warp_live ? P / 2 : 0); ++d) {
+                float in[G::IN_N];
+                load_row<G::IN_N>(in, trow + (P / 2 + d) * G::PITCH);
+                add_row<G::IN_N>(in, trow + (P / 2 - d) * G::PITCH);
+                strip_fma<P, G::WP>(acc, in, wsm + (P / 2 + d) * G::WP);
             }
-#pragma unroll
-            for (int i = 0; i < G::WP / 4; ++i) {
-                float4 v = wp[i];
-                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        } else {
+#pragma unroll 1
+            for (int dy = 0; dy < (warp_live ? P : 0); ++dy) {
+                float in[G::IN_N];
+                load_row<G::IN_N>(in, trow + dy * G::PITCH);
+                strip_fma<P, G::WP>(acc, in, wsm + dy * G::WP);
             }
-#pragma unroll
-            for (int dx = 0; dx < P; ++dx)
-#pragma unroll
-                for (int i = 0; i < STRIP; ++i) acc[i] = fmaf(w[dx], in[i + dx], acc[i]);
         }
 
         if (live && warp_live) {
@@ -601,7 +646,7 @@ __global__ void unpitch_kernel(const float *__restrict__ src, float *__restrict_
 //   in: device f32 [nz or 1][iny][ipitch], 16-byte aligned, ipitch % 4 == 0
 static int launch_fsf_correlate(ogn_ctx *ctx, cudaStream_t stream, const float *in, int in_z_invariant, int nz,
                                 int iny, int inx, int ipitch, const float *weights, int P, int WP, float *out,
-                                int wy0, int wx0, int wny, int wnx, int opitch, int accumulate) {
+                                int wy0, int wx0, int wny, int wnx, int opitch, int accumulate, const int *asym) {
     if (P == 25) {
         using G = k1::Geo<25>;
         CUtensorMap map;
@@ -618,7 +663,7 @@ static int launch_fsf_correlate(ogn_ctx *ctx, cudaStream_t stream, const float *
         zsplit = std::min(zsplit, nz);
         dim3 grid(tx, ty, zsplit);
         kern<<<grid, k1::THREADS, G::SMEM, stream>>>(map, in_z_invariant, weights, out, wy0, wx0, wny, wnx, opitch, nz,
-                                                     zsplit, accumulate);
+                                                     zsplit, accumulate, asym);
         OGN_LAUNCH_CHECK("fsf_correlate_kernel");
     } else {
         dim3 grid(ogn_div_up(wnx, 128), wny, nz);
@@ -740,12 +785,15 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
         OGN_TRY(ogn_scratch_t(ctx, "normcls", (size_t)st->ncy * st->ncx * st->nzp, &normcls));
         OGN_CUDA(cudaMemsetAsync(normcls, 0, (size_t)st->ncy * st->ncx * st->nzp * sizeof(double), ctx->stream));
     }
+    OGN_TRY(ogn_scratch_t(ctx, "fsf_asym", (size_t)1, &st->asym));
+    static const bool no_fold = getenv("OGN_K1_NOFOLD") != nullptr;
+    OGN_CUDA(cudaMemsetAsync(st->asym, no_fold ? 0xff : 0, sizeof(int), ctx->stream));
     {
         ogn_timer t_(ctx, "fsf_prep");
         dim3 grid(nz, nf);
         size_t sm = ((size_t)P * P + 32) * sizeof(double);
         fsf_prep_kernel<<<grid, 256, sm, ctx->stream>>>(fsf_tab, nz, P, WP, st->w32, st->w32sq, normcls, st->nzp,
-                                                        st->place.gny, st->place.gnx, st->ncy, st->ncx);
+                                                        st->place.gny, st->place.gnx, st->ncy, st->ncx, st->asym);
         OGN_LAUNCH_CHECK("fsf_prep_kernel");
     }
     st->rs = nullptr;
@@ -784,7 +832,7 @@ static int run_fsf_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setu
             in = tmp;
         }
         OGN_TRY(launch_fsf_correlate(ctx, stream, in, 0, nz, ny, nx, ipitch, st.w32 + (size_t)f * nz * P * WP, P, WP,
-                                     cube_fsf, w.y0, w.x0, wny, wnx, pitch, f > 0));
+                                     cube_fsf, w.y0, w.x0, wny, wnx, pitch, f > 0, st.asym));
         if (st.pervoxel) {
             // norm_fsf += corr(w_f or ones, K^2)   (lib_origin.py:1028-1031, 1040-1041)
             int wpitch = (int)ogn_round_up(nx, 4);
@@ -794,7 +842,7 @@ static int run_fsf_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setu
             pitch_copy_kernel<<<grid, 128, 0, stream>>>(nullptr, st.w_dev[f], wplane, 1, ny, nx, wpitch, 1);
             OGN_LAUNCH_CHECK("pitch_copy_kernel");
             OGN_TRY(launch_fsf_correlate(ctx, stream, wplane, 1, nz, ny, nx, wpitch, st.w32sq + (size_t)f * nz * P * WP,
-                                         P, WP, norm_fsf, w.y0, w.x0, wny, wnx, pitch, f > 0));
+                                         P, WP, norm_fsf, w.y0, w.x0, wny, wnx, pitch, f > 0, st.asym));
         }
     }
     *cube_fsf_out = cube_fsf;

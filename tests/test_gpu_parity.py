@@ -129,6 +129,34 @@ def test_tglr_float64_input_and_odd_width(lo):
         assert np.mean(profile == ref[1]) > 0.999
 
 
+@pytest.mark.parametrize('kind', ['asymmetric', 'one_plane_asymmetric', 'symmetric'])
+def test_tglr_fsf_symmetry_paths(lo, kind):
+    # K1 folds FSF rows dy and P-1-dy when every plane's float32 weights are mirror-symmetric in y
+    # (a Moffat FSF is); an FSF that is not — a sheared / random one, or a single odd plane — must take
+    # the general path.  Both are checked against the float64 oracle, which knows nothing of symmetry.
+    shape = (48, 70, 72)   # more than one 64x64 K1 tile in both directions
+    rng = np.random.default_rng(21)
+    fsf = synthetic.moffat_fsf(shape[0])
+    if kind == 'asymmetric':
+        fsf = fsf * (1.0 + 0.3 * rng.random(fsf.shape))
+        fsf /= fsf.sum(axis=(1, 2), keepdims=True)
+    elif kind == 'one_plane_asymmetric':
+        fsf = fsf.copy()
+        fsf[17, 3, 5] *= 1.5
+    cube, _ = synthetic.faint_cube(shape, synthetic.moffat_fsf(shape[0]), n_src=3, seed=22)
+    cf, nf = lo.fsf_stage(cube, fsf, None)
+    rcf, rnf = orc.fsf_correlate_direct(cube, fsf)
+    assert_close(cf, rcf, kind + ' cube_fsf')
+    assert_close(nf, rnf, kind + ' norm_fsf')
+    assert lo.default_context().fsf_folded == (kind == 'symmetric')
+    profs = dictionaries.dico_3fwhm()[0]
+    ref = orc.correlation_glr_test(cube, fsf, None, profs, pcut=1e-8)
+    correl, profile, correl_min = lo.Correlation_GLR_test(cube, fsf, None, profs, pcut=1e-8)
+    assert_close(correl, ref[0], kind + ' correl')
+    assert_close(correl_min, ref[2], kind + ' correl_min')
+    assert np.mean(profile == ref[1]) > 0.999
+
+
 def test_tglr_small_fsf_fallback(lo):
     # FSF size without a TMA-tiled instantiation (9x9) goes through the generic kernel
     shape = (40, 20, 24)
