@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -130,6 +131,22 @@ int ogn_input_cube_f32(ogn_ctx *ctx, const char *name, const void *p, int dtype,
 struct ogn_window { int y0, y1, x0, x1; };        // half-open, coordinates of the sub-cube passed in
 struct ogn_place { int gny, gnx, gy0, gx0; };     // where that sub-cube sits in the whole field
 
+// Dictionary of the folded spectral kernel K2f (ogn_tglr_fold.cu), passed by value as a kernel
+// parameter so that the taps are read through the uniform datapath from the parameter bank.
+namespace k2f {
+constexpr int ZB = 8;       // wavelengths per thread and pass
+constexpr int GMAX = 10;    // profiles sharing one set of folded samples
+constexpr int MAXG = 16;    // groups
+constexpr int MAXT = 2048;  // tap table entries
+struct FoldDict {
+    float4 t4[MAXT / 4];           // [group][distance j][slot, padded to 4]: tap d_k[h_k + j] (0 beyond h_k)
+    unsigned char na[MAXG][256];   // [group][j]: profiles of the group with h_k >= j (a suffix of the slots)
+    int k[MAXG][GMAX];             // [group][slot]: profile index, -1 = empty slot
+    int toff[MAXG], H[MAXG];       // tap table offset and largest half-length of the group
+    int ngroups, G, hmax, nprof;
+};
+}  // namespace k2f
+
 struct ogn_tglr_setup_t {
     int nz = 0, ny = 0, nx = 0, P = 0, WP = 0, nfields = 0, nprof = 0;
     bool pervoxel = false;
@@ -141,6 +158,7 @@ struct ogn_tglr_setup_t {
     const void *d_desc = nullptr;
     int ntaps_total = 0, reach = 0, woff_min = 0;
     std::vector<const double *> w_dev;
+    std::shared_ptr<k2f::FoldDict> fold;   // set when the dictionary qualifies for K2f
 };
 
 int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place, int nfields,
@@ -149,6 +167,10 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
 int ogn_tglr_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, const float *dcube,
                     const uint8_t *dmask, ogn_window w, float *d_correl, float *d_cmin, uint8_t *d_prof,
                     float *d_maxmap, float *d_minmap);
+bool ogn_k2f_prepare(const double *taps, const int *tap_offsets, int nprof, k2f::FoldDict *d);
+int ogn_k2f_launch(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, ogn_window w, const float *cube_fsf,
+                   int pitch, const uint8_t *mask, float *correl, float *correl_min, uint8_t *profile, float *maxmap,
+                   float *minmap);
 int ogn_tglr_init_maps(ogn_ctx *ctx, cudaStream_t stream, float *d_maxmap, float *d_minmap, size_t img);
 int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t *mask, int nz, int ny, int nx,
                     ogn_window owned, ogn_place place, int sz, int sy, int sx, float *dense_max, float *dense_min,

@@ -703,6 +703,11 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
         return ogn_fail(ctx, OGN_ERR_ARG, "sub-cube (%d,%d)+(%d,%d) does not fit the %dx%d field", st->place.gy0,
                         st->place.gx0, ny, nx, st->place.gny, st->place.gnx);
     st->pervoxel = weights != nullptr || nfields > 1 || !need_spectral;
+    st->fold.reset();
+    if (need_spectral && !st->pervoxel) {
+        st->fold = std::make_shared<k2f::FoldDict>();
+        if (!ogn_k2f_prepare(taps, tap_offsets, nprof, st->fold.get())) st->fold.reset();
+    }
     const int P = psize, WP = st->WP, nf = nfields;
     constexpr int ZB = 32;
     st->nzp = (int)ogn_round_up(nz, ZB) + ZB;
@@ -918,6 +923,8 @@ int ogn_tglr_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &s
     if (st.pervoxel)
         return launch_spectral<16, 4, true, false>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, dmask, d_correl,
                                                    d_cmin, d_prof, d_maxmap, d_minmap);
+    if (st.fold)  // symmetric, width-sorted dictionary: folded kernel (ogn_tglr_fold.cu)
+        return ogn_k2f_launch(ctx, stream, st, w, cube_fsf, pitch, dmask, d_correl, d_cmin, d_prof, d_maxmap, d_minmap);
     static const int variant = getenv("OGN_K2_VARIANT") ? atoi(getenv("OGN_K2_VARIANT")) : 0;
 #define OGN_K2(ZB_, NW_, CT_) launch_spectral<ZB_, NW_, false, CT_>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, dmask, \
                                                                   d_correl, d_cmin, d_prof, d_maxmap, d_minmap)
