@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument('--dico', default='3FWHM', choices=['3FWHM', '2_12'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--trace', action='store_true', help='host wall-clock per phase of a step (stderr)')
     return ap.parse_args()
 
 
@@ -250,26 +251,58 @@ def main_gpu(args):
     tz, ty_, tx_ = cube.shape
     vol_tile = tz * ty_ * tx_
     cap = max(4096, vol_tile // 40)
-    out_dev = dict(correl=torch.empty_like(cube), correl_min=torch.empty_like(cube),
-                   profile=torch.empty(cube.shape, dtype=torch.uint8, device=dev),
-                   maxmap=torch.empty((ty_, tx_), device=dev), minmap=torch.empty((ty_, tx_), device=dev),
-                   max_index=torch.empty(cap, dtype=torch.int64, device=dev),
-                   max_value=torch.empty(cap, device=dev),
-                   min_index=torch.empty(cap, dtype=torch.int64, device=dev),
-                   min_value=torch.empty(cap, device=dev))
+    def alloc_out():
+        return dict(correl=torch.empty_like(cube), correl_min=torch.empty_like(cube),
+                    profile=torch.empty(cube.shape, dtype=torch.uint8, device=dev),
+                    maxmap=torch.empty((ty_, tx_), device=dev), minmap=torch.empty((ty_, tx_), device=dev),
+                    max_index=torch.empty(cap, dtype=torch.int64, device=dev),
+                    max_value=torch.empty(cap, device=dev),
+                    min_index=torch.empty(cap, dtype=torch.int64, device=dev),
+                    min_value=torch.empty(cap, device=dev))
+
+    # N > 1: two product sets, so that the peer copy of step i (side stream) overlaps the kernels of step i+1
+    out_sets = [alloc_out() for _ in range(2 if world > 1 else 1)]
     reducer = ogd.Reducer() if world > 1 else None
+    gather, gather_mode = None, None
+    if world > 1:
+        try:
+            gather = ogd.PeerGather(ctx, (nz, ny, nx), dst=0, slots=2)
+            gather_mode = 'owned correl tiles stored into rank 0 over NVLink peer memory (ogn_scatter_tile, CUDA IPC)'
+        except Exception as exc:  # noqa: BLE001
+            gather_mode = 'NCCL send/recv (peer mapping unavailable: %s)' % str(exc)[:120]
     thresholds = np.linspace(4.0, 12.0, 50)
-    state = {}
+    thr_dev = torch.from_numpy(thresholds).to(dev)
+    counts_dev = torch.zeros(2 * len(thresholds), dtype=torch.int64, device=dev)
+    state = {'i': 0}
+
+    trace = {}
+
+    def tick(name, t0):
+        if args.trace:
+            trace[name] = trace.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
 
     def step():
-        res = lib_origin.step05(cube, fsf, None, profs, mask, 3, 1e-8, True, out=out_dev, ctx=ctx,
+        i = state['i']
+        state['i'] = i + 1
+        t0 = time.perf_counter()
+        res = lib_origin.step05(cube, fsf, None, profs, mask, 3, 1e-8, True, out=out_sets[i % len(out_sets)], ctx=ctx,
                                 tile=(tile, (ny, nx)) if world > 1 else None)
+        t0 = tick('step05', t0)
         ext = res['extrema']                                                      # owned voxels, global indices
-        n1, n0 = lib_origin.purity_counts(ext, None, thresholds, ctx)            # step06 counting loop
+        # step06 counting loop on the device lists; the counts stay on the device ...
+        n1, n0 = lib_origin.purity_counts(ext, None, thr_dev, ctx, out=counts_dev)
+        t0 = tick('purity_counts', t0)
         if world > 1:
-            both = reducer.sum(np.concatenate([n1, n0]))                          # NCCL allreduce of the histograms
-            n1, n0 = both[:50], both[50:]
-            state['correl_full'] = ogd.gather_owned(res['correl'], tile, all_tiles, (nz, ny, nx))
+            reducer.sum_(counts_dev)                                              # ... NCCL allreduce of the histograms
+            t0 = tick('allreduce', t0)
+            # correl -> rank 0.  Enqueued last: the bulk stores would otherwise sit in front of the small
+            # allreduce on the NVLink queues; this way they overlap the kernels of the next step instead.
+            if gather is not None:
+                gather.scatter(res['correl'], tile, (ny, nx), slot=i % 2)
+            else:
+                state['correl_full'] = ogd.gather_owned(res['correl'], tile, all_tiles, (nz, ny, nx))
+            t0 = tick('gather', t0)
         state['n1'], state['n0'], state['ext'] = n1, n0, ext
         return res
 
@@ -284,6 +317,7 @@ def main_gpu(args):
     sync_all()
     ctx.timing(True)
     ctx.timing_report()
+    trace.clear()
     launches0 = ctx.launch_count
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -293,9 +327,14 @@ def main_gpu(args):
     e0.record()
     for _ in range(args.steps):
         step()
+    if gather is not None:
+        gather.join()                     # the timed region ends after the last peer copy
     e1.record()
     sync_all()
     ms_total = e0.elapsed_time(e1)
+    if args.trace:
+        sys.stderr.write('rank %d host ms/step: %s\n' % (rank, ' '.join('%s=%.3f' % (k, v * 1e3 / args.steps)
+                                                                          for k, v in trace.items())))
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
     stages = {}
@@ -404,6 +443,7 @@ def main_gpu(args):
                              % (nz, ny, nx, args.dico, nprof),
                     psf_size=PSF_SIZE, parallelism='spatial tiles %s with %d-px halos' % (
                         'x'.join(str(v) for v in tiles.grid_shape(world, ny, nx)), halo),
+                    gather=gather_mode,
                     l2='inputs (%.1f GB per rank) exceed the 126 MB L2; no flush needed' % (cube.numel() * 4 / 1e9),
                     timed_region='CUDA events on the launching stream around %d steps, barrier + synchronize on both '
                                  'sides, max over ranks' % args.steps),

@@ -195,6 +195,27 @@ OGN_API int ogn_step05_tile(ogn_ctx *ctx,
                     int64_t *min_index, float *min_value,
                     int64_t capacity, int64_t *counts);
 
+/* ---- multi-GPU: gather of owned tiles over NVLink peer memory ------------ */
+
+/* north_star: "correl is gathered to rank 0" (the reference has no distributed code).  Rank 0
+ * allocates the full [nz][gny][gnx] product with ogn_peer_alloc, which also returns the 64-byte
+ * CUDA IPC handle of the buffer; the host layer ships the handle to the other ranks (any transport:
+ * torch.distributed, MPI, a file), which map the buffer with ogn_peer_open.  ogn_scatter_tile then
+ * copies the window a rank owns of its sub-cube product `src` ([nz][ny][nx] device memory; `tile`
+ * as in ogn_step05_tile) into `dst` — the mapped peer buffer, or the local one on the owning rank —
+ * with a kernel whose stores cross NVLink.  The copy is enqueued on an internal stream behind the
+ * work already queued on the context's stream and the call returns at once, so the transfer overlaps
+ * the next step; a later TGLR call that overwrites `src` waits for it on the device.  ogn_peer_join
+ * makes the context's stream wait for all copies enqueued so far, ogn_peer_sync the host; the
+ * ranks still need a barrier of their own before the owner reads `dst`. */
+OGN_API int ogn_peer_alloc(ogn_ctx *ctx, size_t bytes, void **dev_ptr, unsigned char *handle64);
+OGN_API int ogn_peer_free(ogn_ctx *ctx, void *dev_ptr);
+OGN_API int ogn_peer_open(ogn_ctx *ctx, const unsigned char *handle64, void **dev_ptr);
+OGN_API int ogn_peer_close(ogn_ctx *ctx, void *dev_ptr);
+OGN_API int ogn_scatter_tile(ogn_ctx *ctx, const float *src, int nz, int ny, int nx, const int *tile, float *dst);
+OGN_API int ogn_peer_join(ogn_ctx *ctx);
+OGN_API int ogn_peer_sync(ogn_ctx *ctx);
+
 /* ---- step06: purity threshold counts ------------------------------------ */
 
 /* Statistics Compute_threshold_purity derives its default threshold list from

@@ -28,6 +28,13 @@ SIGNATURES = {
     'ogn_launch_count': (c_int64, [c_void_p]),
     'ogn_trim': (c_int, [c_void_p]),
     'ogn_fsf_folded': (c_int, [c_void_p, c_void_p]),
+    'ogn_peer_alloc': (c_int, [c_void_p, ctypes.c_size_t, ctypes.POINTER(c_void_p), c_void_p]),
+    'ogn_peer_free': (c_int, [c_void_p, c_void_p]),
+    'ogn_peer_open': (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p)]),
+    'ogn_peer_close': (c_int, [c_void_p, c_void_p]),
+    'ogn_scatter_tile': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'ogn_peer_join': (c_int, [c_void_p]),
+    'ogn_peer_sync': (c_int, [c_void_p]),
     'ogn_timing_enable': (c_int, [c_void_p, c_int]),
     'ogn_timing_report': (c_int, [c_void_p, ctypes.c_char_p, ctypes.c_size_t]),
     'ogn_host_alloc': (c_int, [ctypes.c_size_t, ctypes.POINTER(c_void_p)]),

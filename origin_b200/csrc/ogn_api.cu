@@ -1,6 +1,9 @@
 // libogn context, scratch arena and staging helpers.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <unistd.h>
 
 #include "ogn_common.cuh"
 #include "ogn_tma.cuh"
@@ -18,6 +21,17 @@ int ogn_fail(ogn_ctx *ctx, int code, const char *fmt, ...) {
     else
         g_create_error = buf;
     return code;
+}
+
+void ogn_host_trace(const char *label) {
+    static const bool on = getenv("OGN_HOST_TRACE") != nullptr;
+    if (!on) return;
+    static timespec prev = {0, 0};
+    timespec now;
+    clock_gettime(CLOCK_MONOTONIC, &now);
+    const double ms = (now.tv_sec - prev.tv_sec) * 1e3 + (now.tv_nsec - prev.tv_nsec) * 1e-6;
+    fprintf(stderr, "[ogn %d] %-28s +%.3f ms\n", (int)getpid(), label, prev.tv_sec ? ms : 0.0);
+    prev = now;
 }
 
 extern "C" int ogn_version(void) { return OGN_VERSION; }
@@ -69,12 +83,24 @@ extern "C" int ogn_trim(ogn_ctx *ctx) {
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     ctx->h2d_stream = ctx->d2h_stream = nullptr;
+    if (ctx->peer_stream) {
+        cudaStreamSynchronize(ctx->peer_stream);
+        cudaStreamDestroy(ctx->peer_stream);
+        ctx->peer_stream = nullptr;
+    }
+    for (auto &kv : ctx->readers) cudaEventDestroy(kv.second);
+    ctx->readers.clear();
+    if (ctx->peer_ev_begin) cudaEventDestroy(ctx->peer_ev_begin);
+    if (ctx->peer_ev_end) cudaEventDestroy(ctx->peer_ev_end);
+    ctx->peer_ev_begin = ctx->peer_ev_end = nullptr;
     return OGN_OK;
 }
 
 extern "C" void ogn_destroy(ogn_ctx *ctx) {
     if (!ctx) return;
     ogn_trim(ctx);
+    for (void *p : ctx->peer_mapped) cudaIpcCloseMemHandle(p);
+    for (void *p : ctx->peer_owned) cudaFree(p);
     delete ctx;
 }
 

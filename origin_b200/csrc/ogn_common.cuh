@@ -48,9 +48,18 @@ struct ogn_ctx {
     // side streams of the streamed host path (created on first use)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> events;
+    // peer gather (ogn_peer.cu)
+    cudaStream_t peer_stream = nullptr;
+    cudaEvent_t peer_ev_begin = nullptr, peer_ev_end = nullptr;
+    std::vector<void *> peer_owned, peer_mapped;
+    std::map<const void *, cudaEvent_t> readers;   // source buffer -> event of the last scatter reading it
 };
 
 int ogn_fail(ogn_ctx *ctx, int code, const char *fmt, ...);
+
+// Host wall-clock trace points (OGN_HOST_TRACE=1): "label +ms" since the previous point, on stderr.
+void ogn_host_trace(const char *label);
+#define OGN_HT(label) ogn_host_trace(label)
 
 // Scoped CUDA-event timer on the context's stream (active only after ogn_timing_enable).
 struct ogn_timer {
@@ -171,6 +180,7 @@ bool ogn_k2f_prepare(const double *taps, const int *tap_offsets, int nprof, k2f:
 int ogn_k2f_launch(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, ogn_window w, const float *cube_fsf,
                    int pitch, const uint8_t *mask, float *correl, float *correl_min, uint8_t *profile, float *maxmap,
                    float *minmap);
+int ogn_wait_readers(ogn_ctx *ctx, cudaStream_t stream, const void *buf);
 int ogn_tglr_init_maps(ogn_ctx *ctx, cudaStream_t stream, float *d_maxmap, float *d_minmap, size_t img);
 int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t *mask, int nz, int ny, int nx,
                     ogn_window owned, ogn_place place, int sz, int sy, int sx, float *dense_max, float *dense_min,

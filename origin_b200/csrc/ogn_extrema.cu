@@ -783,8 +783,10 @@ int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t 
                           (float *)d_minv, want_lists ? capacity : 0, d_counts + 1));
 
     int64_t h_counts[2] = {0, 0};
+    OGN_HT("extrema enqueued");
     OGN_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost, ctx->stream));
     OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+    OGN_HT("extrema counts back");
     if (counts) {
         if (ogn_is_device_ptr(counts)) OGN_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToDevice, ctx->stream));
         else { counts[0] = h_counts[0]; counts[1] = h_counts[1]; }

@@ -114,9 +114,11 @@ int step05_run(ogn_ctx *ctx, const Step05Args &a, const int *tile) {
     }
     if (a.sz < 1 || a.sy < 1 || a.sx < 1 || !(a.sz & 1) || !(a.sy & 1) || !(a.sx & 1))
         return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "window (%d,%d,%d): only odd sizes are supported", a.sz, a.sy, a.sx);
+    OGN_HT("step05 enter");
     ogn_tglr_setup_t st;
     OGN_TRY(ogn_tglr_setup(ctx, nz, ny, nx, &place, a.nfields, a.fsf, a.psize, a.weights, a.taps, a.tap_offsets,
                            a.nprof, true, &st));
+    OGN_HT("setup done");
     const size_t vol = (size_t)nz * ny * nx, img = (size_t)ny * nx;
 
     const bool host_in = !ogn_is_device_ptr(a.cube);
@@ -143,6 +145,7 @@ int step05_run(ogn_ctx *ctx, const Step05Args &a, const int *tile) {
                        std::max(0, owned.x0 - a.sx / 2), std::min(nx, owned.x1 + a.sx / 2)};
     OGN_TRY(ogn_tglr_window(ctx, ctx->stream, st, d_cube, (const uint8_t *)d_mask, w, (float *)d_correl,
                             (float *)d_cmin, (uint8_t *)d_prof, (float *)d_maxmap, (float *)d_minmap));
+    OGN_HT("tglr enqueued");
     OGN_TRY(ogn_output_commit(ctx, a.correl, d_correl, vol * 4));
     OGN_TRY(ogn_output_commit(ctx, a.correl_min, d_cmin, vol * 4));
     OGN_TRY(ogn_output_commit(ctx, a.profile, d_prof, vol));
@@ -153,6 +156,7 @@ int step05_run(ogn_ctx *ctx, const Step05Args &a, const int *tile) {
                              a.min_index, a.min_value, a.capacity, a.counts);
     if (rc != OGN_OK && rc != OGN_ERR_OVERFLOW) return rc;
     OGN_TRY(ogn_finish_call(ctx));
+    OGN_HT("step05 done");
     return rc;
 }
 

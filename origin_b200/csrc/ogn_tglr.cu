@@ -108,11 +108,14 @@ __global__ void fsf_prep_kernel(const double *const *__restrict__ fsf, int nz, i
 
 // K0b: rs[k][cls][z] = 1/sqrt(sum_j d_k[j]^2 normcls[cls][z + c_k - j]) (0 when the sum is <= 0,
 // the reference's "norm <= 0 -> inf", lib_origin.py:1057-1059).
+// Only the classes that occur in the sub-cube are tabulated (cls_list): all 25 x 25 for a whole field,
+// a single one for an interior tile of a multi-GPU run.
 __global__ void den_table_kernel(const double *__restrict__ normcls, int nz, int nzp, int ncls,
+                                 const int *__restrict__ cls_list,
                                  const double *__restrict__ taps, const int *__restrict__ tap_off, int nprof,
                                  float *__restrict__ rs) {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
-    const int cls = blockIdx.y, k = blockIdx.z;
+    const int cls = cls_list[blockIdx.y], k = blockIdx.z;
     if (z >= nzp) return;
     float out = 0.f;
     if (z < nz) {
@@ -774,11 +777,31 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
             st->w_dev[f] = static_cast<const double *>(d);
         }
     }
+    // edge classes present in this sub-cube: (row classes) x (column classes)
+    std::vector<int> cls_list;
+    int *d_cls_list = nullptr;
+    if (!st->pervoxel) {
+        std::vector<int> rc, cc;
+        for (int y = 0; y < ny; ++y) {
+            const int c = cls_of(y + st->place.gy0, st->place.gny, P);
+            if (rc.empty() || rc.back() != c) rc.push_back(c);   // classes are monotone along an axis
+        }
+        for (int x = 0; x < nx; ++x) {
+            const int c = cls_of(x + st->place.gx0, st->place.gnx, P);
+            if (cc.empty() || cc.back() != c) cc.push_back(c);
+        }
+        for (int a : rc)
+            for (int b : cc) cls_list.push_back(a * st->ncx + b);
+        OGN_TRY(ogn_scratch_t(ctx, "cls_list", cls_list.size(), &d_cls_list));
+        OGN_CUDA(cudaMemcpyAsync(d_cls_list, cls_list.data(), cls_list.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
     const double **fsf_tab = nullptr;
     OGN_TRY(ogn_scratch_t(ctx, "fsf_tab", (size_t)nf, &fsf_tab));
     OGN_CUDA(cudaMemcpyAsync(fsf_tab, fsf_dev.data(), nf * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
+    OGN_HT("setup copies enqueued");
     // the pageable host vectors above die at return: make sure the copies have been staged
     OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+    OGN_HT("setup sync");
 
     // ---- K0: weights (+ squares) and the edge-class norm table ---------------------------
     OGN_TRY(ogn_scratch_t(ctx, "w32", (size_t)nf * nz * P * WP, &st->w32));
@@ -805,8 +828,8 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
     if (!st->pervoxel) {
         OGN_TRY(ogn_scratch_t(ctx, "rs", (size_t)nprof * st->ncy * st->ncx * st->nzp, &st->rs));
         ogn_timer t_(ctx, "den_table");
-        dim3 grid(ogn_div_up(st->nzp, 128), st->ncy * st->ncx, nprof);
-        den_table_kernel<<<grid, 128, 0, ctx->stream>>>(normcls, nz, st->nzp, st->ncy * st->ncx, d_taps64, d_tapoff,
+        dim3 grid(ogn_div_up(st->nzp, 128), (unsigned)cls_list.size(), nprof);
+        den_table_kernel<<<grid, 128, 0, ctx->stream>>>(normcls, nz, st->nzp, st->ncy * st->ncx, d_cls_list, d_taps64, d_tapoff,
                                                         nprof, st->rs);
         OGN_LAUNCH_CHECK("den_table_kernel");
     }
@@ -913,6 +936,8 @@ int ogn_tglr_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &s
     if (w.y0 < 0 || w.x0 < 0 || w.y1 > st.ny || w.x1 > st.nx || w.y0 >= w.y1 || w.x0 >= w.x1)
         return ogn_fail(ctx, OGN_ERR_ARG, "window [%d,%d)x[%d,%d) outside the %dx%d sub-cube", w.y0, w.y1, w.x0, w.x1,
                         st.ny, st.nx);
+    // a peer scatter of the previous step may still be reading the buffer K2 is about to overwrite
+    OGN_TRY(ogn_wait_readers(ctx, stream, d_correl));
     float *cube_fsf = nullptr, *norm_fsf = nullptr;
     int pitch = 0;
     {

@@ -39,6 +39,13 @@ class Reducer:
         dtype = np.int64 if arr.dtype.kind in 'iu' else np.float64
         return self._reduce(arr, self.dist.ReduceOp.SUM, dtype)
 
+    def sum_(self, tensor):
+        """In-place SUM of a tensor that already lives on the group's device (no host round trip; the
+        result is ordered after the call on the current stream, like any torch collective)."""
+        self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.calls += 1
+        return tensor
+
     def max(self, arr):
         return self._reduce(arr, self.dist.ReduceOp.MAX, np.float64)
 
@@ -103,3 +110,98 @@ def gather_owned(cube_tile, tile, all_tiles, global_shape, dst=0, group=None):
             dist.recv(buf, src=t.rank, group=group)
             out[:, gy, gx] = buf
     return out
+
+
+class _DeviceBuffer:
+    """``__cuda_array_interface__`` view of a raw device allocation (lets torch wrap it without a copy)."""
+
+    def __init__(self, ptr, shape, typestr='<f4'):
+        self.__cuda_array_interface__ = dict(shape=tuple(int(s) for s in shape), typestr=typestr,
+                                             data=(int(ptr), False), version=3, strides=None)
+
+
+class PeerGather:
+    """Gather of the owned tiles of a per-rank product into ``dst``'s full cube over NVLink peer memory
+    (``ogn_peer_alloc`` / ``ogn_peer_open`` / ``ogn_scatter_tile``): no packing, no NCCL send/recv, no
+    unpacking — every rank's copy kernel stores straight into the destination rank's buffer, on a side
+    stream, so the transfer of one step overlaps the kernels of the next.
+
+    ``slots`` destination cubes are allocated on ``dst`` (use 2 when consecutive steps overlap so that a
+    step never overwrites the cube the previous one is still filling).  ``torch.distributed`` only
+    carries the 64-byte IPC handles.  Raises :class:`origin_b200._lib.OgnError` when the GPUs cannot map
+    each other's memory; callers may then fall back to :func:`gather_owned`.
+    """
+
+    def __init__(self, ctx, global_shape, dst=0, slots=1, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.dst, self.group, self.dist = ctx, dst, group, dist
+        self.rank = dist.get_rank(group)
+        self.shape = tuple(int(s) for s in global_shape)
+        self.nbytes = int(np.prod(self.shape)) * 4
+        self.ptrs, self._owned, self._mapped = [], [], []
+        handles = []
+        if self.rank == dst:
+            for _ in range(slots):
+                p = ctypes.c_void_p()
+                h = ctypes.create_string_buffer(64)
+                ctx.check(ctx.lib.ogn_peer_alloc(ctx.handle, self.nbytes, ctypes.byref(p), h))
+                self._owned.append(p.value)
+                handles.append(bytes(h.raw))
+        box = [handles]
+        dist.broadcast_object_list(box, src=dst, group=group)
+        handles = box[0]
+        err = None
+        if self.rank == dst:
+            self.ptrs = list(self._owned)
+        else:
+            try:
+                for h in handles:
+                    p = ctypes.c_void_p()
+                    ctx.check(ctx.lib.ogn_peer_open(ctx.handle, ctypes.create_string_buffer(h, 64), ctypes.byref(p)))
+                    self._mapped.append(p.value)
+                self.ptrs = list(self._mapped)
+            except Exception as exc:  # noqa: BLE001 - reported collectively below
+                err = exc
+        # all ranks agree on whether the mapping worked
+        flags = [None] * dist.get_world_size(group)
+        dist.all_gather_object(flags, err is None, group=group)
+        if not all(flags):
+            self.close()
+            raise err if err is not None else RuntimeError('peer mapping failed on another rank')
+        self._torch = torch
+
+    def scatter(self, cube_tile, tile, global_hw, slot=0):
+        """Enqueue the copy of the owned window of ``cube_tile`` (``[nz][th][tw]`` float32 device tensor)
+        into slot ``slot`` of the destination; returns immediately."""
+        from ._lib import ptr
+        nz, th, tw = cube_tile.shape
+        gny, gnx = global_hw
+        desc = np.array([gny, gnx, tile.py0, tile.px0, tile.y0 - tile.py0, tile.y1 - tile.py0, tile.x0 - tile.px0,
+                         tile.x1 - tile.px0], dtype=np.int32)
+        self.ctx.check(self.ctx.lib.ogn_scatter_tile(self.ctx.handle, ptr(cube_tile), nz, th, tw, ptr(desc),
+                                                     self.ptrs[slot]))
+
+    def join(self):
+        """The context's stream waits (on the device) for the copies enqueued so far."""
+        self.ctx.check(self.ctx.lib.ogn_peer_join(self.ctx.handle))
+
+    def wait(self):
+        """Host waits for this rank's copies, then a barrier: afterwards ``result()`` is complete."""
+        self.ctx.check(self.ctx.lib.ogn_peer_sync(self.ctx.handle))
+        self.dist.barrier(group=self.group)
+
+    def result(self, slot=0):
+        """The assembled ``[nz][ny][nx]`` tensor on the destination rank (a view of the peer buffer), else None."""
+        if self.rank != self.dst:
+            return None
+        dev = self._torch.device('cuda', self.ctx.device)
+        return self._torch.as_tensor(_DeviceBuffer(self.ptrs[slot], self.shape), device=dev)
+
+    def close(self):
+        for p in self._mapped:
+            self.ctx.lib.ogn_peer_close(self.ctx.handle, p)
+        for p in self._owned:
+            self.ctx.lib.ogn_peer_free(self.ctx.handle, p)
+        self._mapped, self._owned, self.ptrs = [], [], []

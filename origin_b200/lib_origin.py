@@ -551,16 +551,36 @@ def purity_stats(ext, segmask, ctx=None):
     return float(stats[0]), float(stats[1]), spmax
 
 
-def purity_counts(ext, segmask, thresholds, ctx=None):
+def purity_counts(ext, segmask, thresholds, ctx=None, out=None):
     """``n1[t] = #{maxima > t}``, ``n0[t] = #{background minima > t}`` (int64;
-    the loop at reference lib_origin.py:1443-1449)."""
+    the loop at reference lib_origin.py:1443-1449).
+
+    Host thresholds give numpy counts (the call synchronises).  When ``thresholds`` is a float64 CUDA
+    tensor the counts are written to ``out`` (an int64 CUDA tensor of ``2 * len(thresholds)`` entries,
+    ``n1`` then ``n0``; allocated when None) and the call returns without synchronising, so a
+    multi-GPU caller can hand ``out`` straight to an NCCL allreduce."""
     ctx = _ctx_for(ext.max_value, ctx)
     nz, ny, nx = ext.shape
+    seg = _as_u8(segmask)
+    c1, c0 = ext.counts
+    if _is_torch(thresholds) and thresholds.is_cuda:
+        torch = _torch()
+        if thresholds.dtype != torch.float64 or not thresholds.is_contiguous():
+            raise TypeError('device thresholds must be a contiguous float64 tensor')
+        nt = thresholds.numel()
+        if out is None:
+            out = torch.empty(2 * nt, dtype=torch.int64, device=thresholds.device)
+        if out.dtype != torch.int64 or out.numel() != 2 * nt or not out.is_contiguous():
+            raise TypeError('out must be a contiguous int64 tensor of 2 * len(thresholds) entries')
+        if seg is not None and not _is_torch(seg):
+            seg = torch.from_numpy(seg).to(thresholds.device)
+        ctx.check(ctx.lib.ogn_purity_counts(ctx.handle, ptr(ext.max_index), ptr(ext.max_value), c1, ptr(ext.min_index),
+                                            ptr(ext.min_value), c0, ptr(seg), ny, nx, ptr(thresholds), nt,
+                                            out.data_ptr(), out.data_ptr() + 8 * nt))
+        return out[:nt], out[nt:]
     thr = np.ascontiguousarray(thresholds, dtype=np.float64)
     n1 = np.zeros(len(thr), dtype=np.int64)
     n0 = np.zeros(len(thr), dtype=np.int64)
-    seg = _as_u8(segmask)
-    c1, c0 = ext.counts
     ctx.check(ctx.lib.ogn_purity_counts(ctx.handle, ptr(ext.max_index), ptr(ext.max_value), c1, ptr(ext.min_index),
                                         ptr(ext.min_value), c0, ptr(seg), ny, nx, ptr(thr), len(thr), ptr(n1),
                                         ptr(n0)))

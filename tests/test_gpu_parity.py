@@ -461,3 +461,46 @@ def test_step05_streamed_host_path_matches_device_path(lo):
     # and both agree with the oracle
     ref = orc.tglr_step(cube, fsf, None, profs, mask, 3, 4, 1e-8, True)
     assert_close(host['correl'], ref['cube_correl'], 'streamed correl')
+
+
+def test_purity_counts_device_mode_matches_host_mode(lo):
+    """Device thresholds -> device counts, no host synchronisation (what the multi-GPU step hands to the
+    NCCL allreduce); must equal the host-mode counts, also with a segmentation mask."""
+    import torch
+    rng = np.random.default_rng(41)
+    shape = (40, 24, 32)
+    a = rng.standard_normal(shape).astype(np.float32)
+    ext, _, _ = lo.local_extrema(torch.from_numpy(a).cuda(), torch.from_numpy(-a).cuda(), None, 3)
+    seg = (rng.random(shape[1:]) < 0.25).astype(np.uint8)
+    thr = np.linspace(0.5, 3.0, 50)
+    host = lo.purity_counts(lo.LocalExtrema(shape, ext.max_index.cpu().numpy(), ext.max_value.cpu().numpy(),
+                                            ext.min_index.cpu().numpy(), ext.min_value.cpu().numpy()), seg, thr)
+    out = torch.full((100,), -7, dtype=torch.int64, device='cuda')
+    n1, n0 = lo.purity_counts(ext, seg, torch.from_numpy(thr).cuda(), out=out)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(n1.cpu().numpy(), host[0])
+    np.testing.assert_array_equal(n0.cpu().numpy(), host[1])
+    assert host[0][0] > 0 and host[1][0] > 0
+
+
+def test_scatter_tile_assembles_the_field(lo):
+    """ogn_scatter_tile with a local destination (what rank 0 does with its own tile; the peer mapping
+    itself needs two processes: tools/check_sharded.py): four tiles copied into one cube reproduce it,
+    halos never leak, vector and scalar paths agree."""
+    import torch
+    from origin_b200 import tiles
+    from origin_b200._lib import ptr
+    ctx = lo.default_context()
+    for (ny, nx) in ((64, 96), (37, 51)):          # float4-aligned and ragged
+        nz = 9
+        full = torch.arange(nz * ny * nx, dtype=torch.float32, device='cuda').reshape(nz, ny, nx)
+        dst = torch.full_like(full, -1.0)
+        for t in tiles.plan_tiles(ny, nx, 4, 13):
+            sub = (full[(slice(None),) + t.padded] + 0.0).contiguous()
+            desc = np.array([ny, nx, t.py0, t.px0, t.y0 - t.py0, t.y1 - t.py0, t.x0 - t.px0, t.x1 - t.px0], dtype=np.int32)
+            ctx.check(ctx.lib.ogn_scatter_tile(ctx.handle, ptr(sub), nz, sub.shape[1], sub.shape[2], ptr(desc),
+                                               dst.data_ptr()))
+            ctx.check(ctx.lib.ogn_peer_sync(ctx.handle))   # `sub` dies at the end of the iteration
+        ctx.check(ctx.lib.ogn_peer_join(ctx.handle))
+        torch.cuda.synchronize()
+        assert torch.equal(dst, full)

@@ -52,6 +52,14 @@ def main():
     assert torch.equal(res['correl'][:, ys, xs], res_full['correl'][:, ys, xs])
     thr, tab = lib_origin.Compute_threshold_purity(0.8, ext, None, seg, allreduce=red)
     correl_full = ogd.gather_owned(res['correl'], t, plan, shape)
+    # the same gather through NVLink peer memory (ogn_scatter_tile) must assemble the identical cube
+    pg = ogd.PeerGather(lib_origin.default_context(), shape, dst=0, slots=2)
+    for slot in (0, 1):
+        pg.scatter(res['correl'], t, (ny, nx), slot=slot)
+    pg.wait()
+    peer_same = True
+    if rank == 0:
+        peer_same = all(torch.equal(pg.result(slot), correl_full) for slot in (0, 1))
     std_full = ogd.gather_owned(cube_std, t, plan, shape)
     # gather the owned lists on rank 0 (variable length: pad to the max)
     n = torch.tensor([len(ext.max_index)], device=dev)
@@ -75,11 +83,13 @@ def main():
         same_tab = all(np.array_equal(np.asarray(tab[k]), np.asarray(gtab[k])) for k in ('Det_M', 'Det_m'))
         print('world=%d  max|d cube_std|=%.3g  max|d correl|=%.3g  lists identical=%s  purity counts identical=%s  '
               'threshold %.6f vs %.6f' % (world, d_std, d_cor, same_lists, same_tab, thr, gthr))
-        ok = d_std <= 2e-6 and d_cor <= 2e-5 and same_tab and abs(thr - gthr) <= 1e-6 * abs(gthr)
+        print('peer gather identical to NCCL gather: %s' % peer_same)
+        ok = d_std <= 2e-6 and d_cor <= 2e-5 and same_tab and abs(thr - gthr) <= 1e-6 * abs(gthr) and peer_same
         # cube_std of a tile differs from the global run only through the summation order of the
         # per-wavelength mean (float64 sums, different partial sums): bounded, not bit-exact
         print('CHECK_SHARDED', 'PASS' if ok else 'FAIL')
     dist.barrier()
+    pg.close()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
