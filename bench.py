@@ -337,6 +337,7 @@ def main_gpu(args):
                                                                           for k, v in trace.items())))
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
+    state['folded'] = ctx.fsf_folded
     stages = {}
     for name, ms in ctx.timing_report():
         stages.setdefault(name, []).append(ms)
@@ -413,9 +414,20 @@ def main_gpu(args):
     k2_flops = 2.0 * sum_taps(profs) * vol_tile
     fp32_peak = peak.get('fp32_tflops')
     summ = ncu_summary()
+    folded = bool(state.get('folded'))
+    half = PSF_SIZE // 2
+    # FP32-pipe instructions K1 executes per voxel (x2 = flop slots of the FFMA peak): direct form P^2 FFMA;
+    # folded form (half+1) rows x P FFMA + half rows x (32+P-1)/32 FADD (one add per loaded input sample)
+    k1_slots = 2.0 * ((half + 1) * PSF_SIZE + half * (32 + PSF_SIZE - 1) / 32.0) if folded else 2.0 * PSF_SIZE ** 2
+    k1_alg = k1_flops / (k1_ms * 1e-3) / 1e12
+    k1_exec = k1_slots * vol_tile / (k1_ms * 1e-3) / 1e12
     roofline = dict(
-        bound='fp32', kernel='k1::fsf_correlate_kernel<25>', achieved=k1_flops / (k1_ms * 1e-3) / 1e12,
-        peak=fp32_peak, unit='TFLOP/s', frac=(k1_flops / (k1_ms * 1e-3) / 1e12 / fp32_peak) if fp32_peak else None,
+        bound='fp32', kernel='k1::fsf_correlate_kernel<25>' + (' (row-folded: mirror-symmetric FSF)' if folded else ''),
+        achieved=k1_alg, peak=fp32_peak, unit='TFLOP/s', frac=(k1_alg / fp32_peak) if fp32_peak else None,
+        executed=dict(flop_slots_per_voxel=k1_slots, tflops=k1_exec, frac=(k1_exec / fp32_peak) if fp32_peak else None,
+                      note='FP32-pipe issue slots actually used (FFMA and FADD both count 2): the figure to read as '
+                           'pipe utilisation; "achieved" counts the direct-form 2*P^2 flops of SURVEY.md 8d, which the '
+                           'folded kernel does not execute, so it can exceed the peak'),
         traffic=summ.get('k1_dram_bytes_per_launch'),
         peak_source='FP32 FFMA peak measured on this device in this run by tools/fma_peak '
                     '(MEASURED_PEAKS.json has no FP32 figure; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)',

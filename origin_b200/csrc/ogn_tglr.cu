@@ -661,9 +661,12 @@ static int launch_fsf_correlate(ogn_ctx *ctx, cudaStream_t stream, const float *
             attr_set = true;
         }
         const int tx = ogn_div_up(wnx, k1::TILE), ty = ogn_div_up(wny, k1::TILE);
-        // one wave of resident blocks (4 per SM); every block walks nz/zsplit planes
-        int zsplit = std::max(1, (ctx->sm_count * 4) / (tx * ty));
-        zsplit = std::min(zsplit, nz);
+        // several waves of resident blocks (4 per SM), every block walking nz/zsplit >= 8 planes: tiles of a
+        // ragged window differ in live warps (32 x 32 patches outside the window are skipped), so the block
+        // scheduler needs spare blocks to even out the SMs
+        static const int waves = getenv("OGN_K1_WAVES") ? std::max(1, atoi(getenv("OGN_K1_WAVES"))) : 4;
+        int zsplit = std::max(1, (ctx->sm_count * 4 * waves) / (tx * ty));
+        zsplit = std::min(zsplit, std::max(1, nz / 8));
         dim3 grid(tx, ty, zsplit);
         kern<<<grid, k1::THREADS, G::SMEM, stream>>>(map, in_z_invariant, weights, out, wy0, wx0, wny, wnx, opitch, nz,
                                                      zsplit, accumulate, asym);
@@ -759,6 +762,14 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
         OGN_CUDA(cudaMemcpyAsync(d_desc, desc.data(), nprof * sizeof(k2::ProfDesc), cudaMemcpyHostToDevice, ctx->stream));
         OGN_CUDA(cudaMemcpyAsync(d_taps64, taps, ntaps_in * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         OGN_CUDA(cudaMemcpyAsync(d_tapoff, tap_offsets, (nprof + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        // K2's uniform-datapath variant reads the taps from constant memory.  Host -> symbol here (not a
+        // device-to-device copy at launch time, which would queue behind a peer gather on the copy engine).
+        if (st->ntaps_total + 4 <= k2::CONST_TAPS) {
+            OGN_CUDA(cudaMemcpyToSymbolAsync(k2::c_taps4, tp.data(), (size_t)st->ntaps_total * sizeof(float), 0,
+                                             cudaMemcpyHostToDevice, ctx->stream));
+            OGN_CUDA(cudaMemcpyToSymbolAsync(k2::c_desc, desc.data(), (size_t)nprof * sizeof(k2::ProfDesc), 0,
+                                             cudaMemcpyHostToDevice, ctx->stream));
+        }
     }
 
     // ---- FSF cubes / weight maps -> device, pointer table ------------------------------
@@ -884,12 +895,6 @@ static int launch_spectral(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_set
                            const float *cube_fsf, const float *norm_fsf, int pitch, const uint8_t *mask,
                            float *correl, float *correl_min, uint8_t *profile, float *maxmap, float *minmap) {
     auto kern = k2::spectral_glr_kernel<ZB, NW, PV, CT>;
-    if (CT) {
-        OGN_CUDA(cudaMemcpyToSymbolAsync(k2::c_taps4, st.d_taps, (size_t)st.ntaps_total * sizeof(float), 0,
-                                         cudaMemcpyDeviceToDevice, stream));
-        OGN_CUDA(cudaMemcpyToSymbolAsync(k2::c_desc, st.d_desc, (size_t)st.nprof * sizeof(k2::ProfDesc), 0,
-                                         cudaMemcpyDeviceToDevice, stream));
-    }
     const int wny = w.y1 - w.y0, wnx = w.x1 - w.x0;
     // window rows per chunk: the chunk itself, the longest profile, and the ring's read-ahead
     const int need_rows = NW * ZB + st.reach + 2 * k2::U;
