@@ -309,28 +309,28 @@ local_extrema3_brick_kernel(const float *__restrict__ a, const float *__restrict
     }
 }
 
-// TMA-staged, vectorised 3 x 3 x 3 pass (the default when nx % 4 == 0).  Same decomposition as
-// local_extrema3_kernel — x by shuffles, y through a double-buffered shared tile, z in registers,
-// one block barrier per plane — but
-//  * the raw planes arrive by TMA: per plane one elected thread issues two 3-D bulk tensor loads
-//    (box {136 x, TY+2 y, 1 z} of each array, starting 4 columns / 1 row outside the tile so the
-//    halo comes with it) into a ring of E4_NST shared-memory stages; E4_NST-1 planes are in flight
-//    while one is reduced, without costing registers.  Elements outside the cube are filled with
-//    NaN by the TMA unit: fmaxf / fminf ignore NaN operands, which is exactly scipy's 'reflect'
-//    maximum filter (out-of-range neighbours never win) — no edge tests in the kernel;
-//  * every lane owns FOUR consecutive x (one LDS.128 per array and plane), so a warp covers 128
-//    voxels of a row and the instruction count per voxel is ~6x below the scalar kernel: the pass
-//    is limited by HBM, not by issue slots.
-// Flag words keep the layout of the scalar kernels (one 32-bit word per 32 consecutive x): the
-// 4-bit nibbles of 8 neighbouring lanes are OR-ed with three shuffles.
-constexpr int E4_TY = 14;    // output rows per block; 16 warps with the two halo rows
-constexpr int E4_CZ = 64;    // planes per block (E4_CZ + 2 is a multiple of E4_NST)
-constexpr int E4_NST = 3;    // raw-plane stages (= unroll factor of the plane loop)
+// TMA-staged, vectorised, barrier-free 3 x 3 x 3 pass (the default when nx % 4 == 0).
+//  * The raw planes arrive by TMA: a producer warp issues, per plane, two 3-D bulk tensor loads (box
+//    {136 x, TY+2 y, 1 z} of each array, starting 4 columns / 1 row outside the tile so the halo comes
+//    with it) into a ring of E4_NST shared-memory stages guarded by full / empty mbarriers.  Elements
+//    outside the cube are filled with NaN by the TMA unit: fmaxf / fminf ignore NaN operands, which is
+//    exactly scipy's 'reflect' maximum filter (out-of-range neighbours never win) — no edge tests.
+//  * Every consumer warp owns one image row of the tile and is independent of the others (no block
+//    barrier, no exchange buffer): per plane it reads rows y-1, y, y+1 of both arrays (three LDS.128
+//    per array: every lane owns FOUR consecutive x, a warp covers 128 voxels), takes the vertical max
+//    in registers, the horizontal max with two shuffles (lanes 0 / 31 fetch the halo column), and keeps
+//    the 3x3 plane extrema of z-1, z, z+1 in registers.  Warps drift up to E4_NST - 1 planes apart, so
+//    the HBM latency of one is hidden by the arithmetic of the others.
+// Flag words keep the layout of the scalar kernels (one 32-bit word per 32 consecutive x): the 4-bit
+// nibbles of 8 neighbouring lanes are OR-ed with three shuffles.
+constexpr int E4_TY = 14;    // output rows per block = consumer warps (+ 1 producer warp)
+constexpr int E4_CZ = 64;    // planes per block
+constexpr int E4_NST = 4;    // raw-plane stages
 constexpr int E4_BX = 136;   // TMA box width: 128 + 4 columns either side (16-byte granularity)
 constexpr int E4_ROWS = E4_TY + 2;
 constexpr int E4_STAGE_FLOATS = 2 * E4_ROWS * E4_BX;   // a rows, then b rows
-constexpr int E4_XROWS = E4_ROWS + 2;                  // exchange tile rows (one pad row either side)
-constexpr int E4_SMEM = E4_NST * E4_STAGE_FLOATS * 4 + 2 * 2 * E4_XROWS * 32 * 16 + E4_NST * 8;
+constexpr int E4_THREADS = 32 * (E4_TY + 1);
+constexpr int E4_SMEM = E4_NST * E4_STAGE_FLOATS * 4 + 2 * E4_NST * 8;
 
 __device__ __forceinline__ float max3(float x, float y, float z) { return fmaxf(fmaxf(x, y), z); }
 __device__ __forceinline__ float min3(float x, float y, float z) { return fminf(fminf(x, y), z); }
@@ -340,30 +340,70 @@ __device__ __forceinline__ float4 max3v(float4 p, float4 q, float4 r) {
 __device__ __forceinline__ float4 min3v(float4 p, float4 q, float4 r) {
     return make_float4(min3(p.x, q.x, r.x), min3(p.y, q.y, r.y), min3(p.z, q.z, r.z), min3(p.w, q.w, r.w));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma::smem_u32(bar)) : "memory");
+}
+// bit i of the result: p_i == q_i
+__device__ __forceinline__ uint32_t eq4(float4 p, float4 q) {
+    uint32_t k = 0;
+    if (p.x == q.x) k |= 1u;
+    if (p.y == q.y) k |= 2u;
+    if (p.z == q.z) k |= 4u;
+    if (p.w == q.w) k |= 8u;
+    return k;
+}
 
 template <bool DENSE>
-__global__ void __launch_bounds__(32 * E4_ROWS, 2)
+__global__ void __launch_bounds__(E4_THREADS, 2)
 local_extrema3_tma_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap b_map,
                           const uint8_t *__restrict__ mask, int nz, int ny, int nx, int oy0, int oy1, int ox0a,
                           int ox0, int ox1, float *__restrict__ dense_max, float *__restrict__ dense_min,
                           uint32_t *__restrict__ flag_max, uint32_t *__restrict__ flag_min, int nxw) {
     using namespace tma;
     extern __shared__ __align__(128) unsigned char e4_smem[];
-    float *raw = reinterpret_cast<float *>(e4_smem);                                  // [NST][2][ROWS][BX]
-    float4 *xa = reinterpret_cast<float4 *>(e4_smem + E4_NST * E4_STAGE_FLOATS * 4);  // [2][XROWS][32]
-    float4 *xb = xa + 2 * E4_XROWS * 32;                                              // [2][XROWS][32]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(xb + 2 * E4_XROWS * 32);            // [NST]
+    float *raw = reinterpret_cast<float *>(e4_smem);                                      // [NST][2][ROWS][BX]
+    uint64_t *full = reinterpret_cast<uint64_t *>(e4_smem + E4_NST * E4_STAGE_FLOATS * 4);  // [NST]
+    uint64_t *empty = full + E4_NST;                                                      // [NST]
 
-    const int lane = threadIdx.x, row = threadIdx.y;  // rows 0 and E4_TY+1 are halo rows
-    const int tid = row * 32 + lane;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // warp E4_TY is the producer
     const int x0 = ox0a + blockIdx.x * 128, x = x0 + 4 * lane;
-    const int ty0 = oy0 + blockIdx.y * E4_TY;         // first output row of the block
-    const int y = ty0 + row - 1;
+    const int ty0 = oy0 + blockIdx.y * E4_TY;                    // first output row of the block
     const int zc0 = blockIdx.z * E4_CZ, zc1 = min(nz, zc0 + E4_CZ);
+    // planes zc0-1 .. zc1 are needed (NaN outside [0, nz)); the loop walks a multiple of E4_NST planes,
+    // the extra ones are loaded and reduced but never output
+    const int nplanes = (zc1 - zc0 + 2 + E4_NST - 1) / E4_NST * E4_NST;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < E4_NST; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], E4_TY);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == E4_TY) {  // ---- producer ---------------------------------------------------------------
+        if (lane == 0) {
+            for (int it = 0; it < nplanes; ++it) {
+                const int st = it % E4_NST;
+                if (it >= E4_NST) mbar_wait(&empty[st], ((it / E4_NST) - 1) & 1);  // every consumer has read the stage
+                float *dst = raw + st * E4_STAGE_FLOATS;
+                mbar_expect_tx(&full[st], E4_STAGE_FLOATS * 4);
+                tma_load_3d(dst, &a_map, &full[st], x0 - 4, ty0 - 1, zc0 - 1 + it);
+                tma_load_3d(dst + E4_ROWS * E4_BX, &b_map, &full[st], x0 - 4, ty0 - 1, zc0 - 1 + it);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: warp w owns output row ty0 + w (box row w + 1) ----------------------------------
+    const int y = ty0 + warp;
     const bool is_l = lane == 0, is_r = lane == 31;
-    const bool out_row = row >= 1 && row <= E4_TY && y < oy1;
+    const bool out_row = y < oy1;
     const bool m_ok = mask != nullptr && out_row && x < nx;
-    uint32_t colbits = 0;  // voxels of this lane that are outputs (none for the halo warps)
+    uint32_t colbits = 0;  // voxels of this lane that are outputs
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         if (out_row && x + i >= ox0 && x + i < ox1) colbits |= 1u << i;
@@ -373,99 +413,76 @@ local_extrema3_tma_kernel(const __grid_constant__ CUtensorMap a_map, const __gri
     const uint32_t yx = out_row ? (uint32_t)y * nx + x : 0u;   // offset inside a plane
     const uint32_t wyx = (out_row ? (uint32_t)(y - oy0) : 0u) * nxw + wcol;
     const uint32_t wstride = (uint32_t)(oy1 - oy0) * nxw;
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < E4_NST; ++s) mbar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-
-    // Planes zc0-1 .. zc1 are needed; the loop walks a multiple of 2 E4_NST planes (extra planes are
-    // loaded and reduced but never output).  Plane indices outside [0, nz) are legal: NaN fill.
-    const int nplanes = (zc1 - zc0 + 2 + 2 * E4_NST - 1) / (2 * E4_NST) * (2 * E4_NST);
-    auto issue = [&](int it) {  // elected thread: plane zc0 - 1 + it into stage it % NST
-        float *dst = raw + (it % E4_NST) * E4_STAGE_FLOATS;
-        uint64_t *bar = &bars[it % E4_NST];
-        mbar_expect_tx(bar, E4_STAGE_FLOATS * 4);
-        tma_load_3d(dst, &a_map, bar, x0 - 4, ty0 - 1, zc0 - 1 + it);
-        tma_load_3d(dst + E4_ROWS * E4_BX, &b_map, bar, x0 - 4, ty0 - 1, zc0 - 1 + it);
-    };
-    if (tid == 0)
-        for (int it = 0; it < E4_NST; ++it) issue(it);
-
-    // mask words are prefetched two planes ahead in registers (4 bytes per thread and plane)
-    uint32_t m_use = 0, m_nxt = 0;
-    if (m_ok) m_use = __ldg(reinterpret_cast<const uint32_t *>(mask + (size_t)zc0 * plane + yx));
-    if (m_ok && zc0 + 1 < zc1) m_nxt = __ldg(reinterpret_cast<const uint32_t *>(mask + (size_t)(zc0 + 1) * plane + yx));
+    const int nib = 4 * (lane & 7);
 
     const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     const float4 pinf4 = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
     float4 pa_prev = ninf4, pa_cur = ninf4, ca_cur = ninf4;
     float4 pb_prev = pinf4, pb_cur = pinf4, cb_cur = pinf4;
-    const float *ra0 = raw + row * E4_BX, *rb0 = ra0 + E4_ROWS * E4_BX;
-    float4 *ea0 = xa + (row + 1) * 32 + lane, *eb0 = xb + (row + 1) * 32 + lane;
+    // this lane's float4 in box row `warp` (the row above the output row) of array a, stage 0; the halo
+    // column is read by every lane (column 132 by lane 31, column 3 by the others: two addresses, no
+    // conflict) and used by lanes 0 / 31 only
+    const float *base = raw + warp * E4_BX + 4 + 4 * lane;
+    const float *ebase = raw + warp * E4_BX + (is_r ? 132 : 3);
+    // iteration `it` reduces plane zc0-1+it and outputs plane q = zc0-2+it; the mask word of plane q+2 is
+    // requested in the same iteration (two planes ahead)
+    const uint8_t *mptr = mask + (size_t)zc0 * plane + yx;
+    uint32_t m_use = 0, m_a = 0, m_b = 0, phase = 0;
 
 #pragma unroll 1
-    for (int it0 = 0; it0 < nplanes; it0 += 2 * E4_NST) {
+    for (int it0 = 0; it0 < nplanes; it0 += E4_NST) {
 #pragma unroll
-        for (int s = 0; s < 2 * E4_NST; ++s) {   // unrolled by 2 x NST: stage and exchange buffer are static
-            const int it = it0 + s;
-            const int p = zc0 - 1 + it, st = s % E4_NST, buf = s & 1;
-            mbar_wait(&bars[st], (s / E4_NST) & 1);  // it0 is a multiple of 2 NST: the parity is static
-            const float *ra = ra0 + st * E4_STAGE_FLOATS, *rb = rb0 + st * E4_STAGE_FLOATS;
-            const float4 va = *reinterpret_cast<const float4 *>(ra + 4 + 4 * lane);
-            const float4 vb = *reinterpret_cast<const float4 *>(rb + 4 + 4 * lane);
-            float l = __shfl_up_sync(0xffffffffu, va.w, 1), r = __shfl_down_sync(0xffffffffu, va.x, 1);
-            if (is_l) l = ra[3];
-            if (is_r) r = ra[132];
-            const float4 ha = make_float4(max3(l, va.x, va.y), max3(va.x, va.y, va.z), max3(va.y, va.z, va.w),
-                                          max3(va.z, va.w, r));
-            l = __shfl_up_sync(0xffffffffu, vb.w, 1);
-            r = __shfl_down_sync(0xffffffffu, vb.x, 1);
-            if (is_l) l = rb[3];
-            if (is_r) r = rb[132];
-            const float4 hb = make_float4(min3(l, vb.x, vb.y), min3(vb.x, vb.y, vb.z), min3(vb.y, vb.z, vb.w),
-                                          min3(vb.z, vb.w, r));
-            float4 *ea = ea0 + buf * E4_XROWS * 32, *eb = eb0 + buf * E4_XROWS * 32;
-            *ea = ha;
-            *eb = hb;
-            __syncthreads();
-            // every thread has read its raw row: the stage can be refilled
-            if (tid == 0 && it + E4_NST < nplanes) issue(it + E4_NST);
-            // the halo warps run the same code on the pad rows of the exchange tile; they own no outputs
-            const float4 m9a = max3v(ea[-32], ha, ea[32]);
-            const float4 m9b = min3v(eb[-32], hb, eb[32]);
-            const float4 wa = max3v(pa_prev, pa_cur, m9a);
-            const float4 wb = min3v(pb_prev, pb_cur, m9b);
-            const bool emit = p > zc0 && p <= zc1;  // output plane p - 1 in [zc0, zc1); block-uniform
-            const uint32_t m_cur = m_use;
-            if (emit) {
-                m_use = m_nxt;
-                m_nxt = 0;
-                if (m_ok && p + 1 < zc1)
-                    m_nxt = __ldg(reinterpret_cast<const uint32_t *>(mask + (size_t)(p + 1) * plane + yx));
+        for (int st = 0; st < E4_NST; ++st) {
+            const int q = zc0 - 2 + it0 + st;
+            m_use = m_a;
+            m_a = m_b;
+            m_b = 0;
+            if (m_ok && q + 2 < zc1) m_b = __ldg(reinterpret_cast<const uint32_t *>(mptr));
+            mptr += plane;
+            mbar_wait(&full[st], phase);
+            const float *ra = base + st * E4_STAGE_FLOATS, *rb = ra + E4_ROWS * E4_BX;
+            const float *qa = ebase + st * E4_STAGE_FLOATS, *qb = qa + E4_ROWS * E4_BX;
+            // array a, then array b (keeps the live registers low): vertical extremum of the three rows,
+            // horizontal extremum by shuffles, then the window extremum over the three planes
+            float4 wa, wb, na, nb;  // window extrema, new centre rows
+            {
+                const float4 r0 = *reinterpret_cast<const float4 *>(ra);
+                na = *reinterpret_cast<const float4 *>(ra + E4_BX);
+                const float4 r2 = *reinterpret_cast<const float4 *>(ra + 2 * E4_BX);
+                const float e = max3(qa[0], qa[E4_BX], qa[2 * E4_BX]);  // halo column
+                const float4 v = max3v(r0, na, r2);
+                float l = __shfl_up_sync(0xffffffffu, v.w, 1), r = __shfl_down_sync(0xffffffffu, v.x, 1);
+                l = is_l ? e : l;
+                r = is_r ? e : r;
+                const float4 m9 = make_float4(max3(l, v.x, v.y), max3(v.x, v.y, v.z), max3(v.y, v.z, v.w), max3(v.z, v.w, r));
+                wa = max3v(pa_prev, pa_cur, m9);
+                pa_prev = pa_cur;
+                pa_cur = m9;
             }
-            uint32_t free4 = 0;  // bit i set: voxel i is an output and not masked
-            free4 |= (m_cur & 0x000000ffu) ? 0u : 1u;
-            free4 |= (m_cur & 0x0000ff00u) ? 0u : 2u;
-            free4 |= (m_cur & 0x00ff0000u) ? 0u : 4u;
-            free4 |= (m_cur & 0xff000000u) ? 0u : 8u;
-            free4 &= colbits;
-            uint32_t ka = 0, kb = 0;
-            ka |= ca_cur.x == wa.x ? 1u : 0u;
-            ka |= ca_cur.y == wa.y ? 2u : 0u;
-            ka |= ca_cur.z == wa.z ? 4u : 0u;
-            ka |= ca_cur.w == wa.w ? 8u : 0u;
-            kb |= cb_cur.x == wb.x ? 1u : 0u;
-            kb |= cb_cur.y == wb.y ? 2u : 0u;
-            kb |= cb_cur.z == wb.z ? 4u : 0u;
-            kb |= cb_cur.w == wb.w ? 8u : 0u;
-            ka &= free4;
-            kb &= free4;
+            {
+                const float4 r0 = *reinterpret_cast<const float4 *>(rb);
+                nb = *reinterpret_cast<const float4 *>(rb + E4_BX);
+                const float4 r2 = *reinterpret_cast<const float4 *>(rb + 2 * E4_BX);
+                const float e = min3(qb[0], qb[E4_BX], qb[2 * E4_BX]);
+                const float4 v = min3v(r0, nb, r2);
+                float l = __shfl_up_sync(0xffffffffu, v.w, 1), r = __shfl_down_sync(0xffffffffu, v.x, 1);
+                if (lane == 0) mbar_arrive(&empty[st]);  // the shuffles above made every lane's samples land
+                l = is_l ? e : l;
+                r = is_r ? e : r;
+                const float4 m9 = make_float4(min3(l, v.x, v.y), min3(v.x, v.y, v.z), min3(v.y, v.z, v.w), min3(v.z, v.w, r));
+                wb = min3v(pb_prev, pb_cur, m9);
+                pb_prev = pb_cur;
+                pb_cur = m9;
+            }
+            uint32_t free4 = colbits;  // bit i set: voxel i is an output and not masked
+            if (m_use & 0x000000ffu) free4 &= ~1u;
+            if (m_use & 0x0000ff00u) free4 &= ~2u;
+            if (m_use & 0x00ff0000u) free4 &= ~4u;
+            if (m_use & 0xff000000u) free4 &= ~8u;
+            const uint32_t ka = eq4(ca_cur, wa) & free4, kb = eq4(cb_cur, wb) & free4;
+            const bool emit = q >= zc0 && q < zc1;  // block-uniform
             if (DENSE && emit && colbits) {
-                const size_t oidx = (size_t)(p - 1) * plane + yx;
+                const size_t oidx = (size_t)q * plane + yx;
                 const float4 da = make_float4((ka & 1u) ? ca_cur.x : 0.f, (ka & 2u) ? ca_cur.y : 0.f,
                                               (ka & 4u) ? ca_cur.z : 0.f, (ka & 8u) ? ca_cur.w : 0.f);
                 const float4 db = make_float4((kb & 1u) ? -cb_cur.x : 0.f, (kb & 2u) ? -cb_cur.y : 0.f,
@@ -484,18 +501,19 @@ local_extrema3_tma_kernel(const __grid_constant__ CUtensorMap a_map, const __gri
                 }
             }
             // nibbles of 8 neighbouring lanes -> one flag word (bit = x offset inside the word)
-            uint32_t fa = ka << (4 * (lane & 7)), fb = kb << (4 * (lane & 7));
+            uint32_t fa = ka << nib, fb = kb << nib;
             fa |= __shfl_xor_sync(0xffffffffu, fa, 1); fb |= __shfl_xor_sync(0xffffffffu, fb, 1);
             fa |= __shfl_xor_sync(0xffffffffu, fa, 2); fb |= __shfl_xor_sync(0xffffffffu, fb, 2);
             fa |= __shfl_xor_sync(0xffffffffu, fa, 4); fb |= __shfl_xor_sync(0xffffffffu, fb, 4);
             if (emit && w_ok) {
-                const size_t widx = (size_t)(p - 1) * wstride + wyx;
+                const size_t widx = (size_t)q * wstride + wyx;
                 flag_max[widx] = fa;
                 flag_min[widx] = fb;
             }
-            pa_prev = pa_cur; pa_cur = m9a; ca_cur = va;
-            pb_prev = pb_cur; pb_cur = m9b; cb_cur = vb;
+            ca_cur = na;
+            cb_cur = nb;
         }
+        phase ^= 1u;
     }
 }
 
@@ -555,37 +573,12 @@ __global__ void scan_block_offsets_kernel(int64_t *__restrict__ block_tot, int n
     if (threadIdx.x == 0) *grand = carry;
 }
 
-// phase 3 (extrema): scatter the set bits of every flag word, in order
+// geometry of the flag words (phase 3 of the compaction turns set bits into voxel indices)
 struct ExMap {
     int ny, nx;            // dims of the arrays the flags were computed on (the sub-cube)
     int oy0, ony, ox0a;    // flag rows cover y in [oy0, oy0+ony), flag word k starts at x = ox0a + 32 k
     int gny, gnx, gy0, gx0;  // placement of the sub-cube in the whole field (indices reported globally)
 };
-
-__global__ void scatter_flags_kernel(const uint32_t *__restrict__ flags, size_t nwords,
-                                     const int64_t *__restrict__ block_off, const float *__restrict__ src,
-                                     float sign, ExMap m, int nxw, int64_t *__restrict__ out_index,
-                                     float *__restrict__ out_value, int64_t capacity) {
-    const size_t i = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
-    uint32_t w = i < nwords ? flags[i] : 0u;
-    int ex = block_exclusive_scan(__popc(w), nullptr);
-    if (!w) return;
-    int64_t pos = block_off[blockIdx.x] + ex;
-    const size_t rowid = i / nxw;  // z*ony + (y - oy0)
-    const int xw = (int)(i - rowid * nxw);
-    const int z = (int)(rowid / m.ony), y = (int)(rowid - (size_t)z * m.ony) + m.oy0;
-    const size_t lbase = ((size_t)z * m.ny + y) * m.nx + m.ox0a + (size_t)xw * 32;
-    const int64_t gbase = ((int64_t)z * m.gny + (y + m.gy0)) * m.gnx + m.gx0 + m.ox0a + (int64_t)xw * 32;
-    while (w) {
-        const int bit = __ffs(w) - 1;
-        w &= w - 1;
-        if (pos < capacity) {
-            out_index[pos] = gbase + bit;
-            out_value[pos] = sign * src[lbase + bit];
-        }
-        ++pos;
-    }
-}
 
 // ---- K4 -----------------------------------------------------------------------------------
 __device__ __forceinline__ void atomic_max_f32(float *addr, float v) {
@@ -659,21 +652,116 @@ __global__ void threshold_scatter_kernel(const uint32_t *__restrict__ flag, size
 
 // -------------------------------------------------------------------------------------------
 
-static int compact_flags(ogn_ctx *ctx, const char *tag, const uint32_t *flags, size_t nwords, const float *src,
-                         float sign, ExMap emap, int nxw, int64_t *out_index, float *out_value, int64_t capacity,
-                         int64_t *d_count) {
-    const int nblocks = ogn_div_up((int64_t)nwords, SCAN_BLOCK);
-    int64_t *block_tot = nullptr;
-    std::string name = std::string("scan_tot_") + tag;
-    OGN_TRY(ogn_scratch_t(ctx, name.c_str(), (size_t)nblocks + 1, &block_tot));
-    scan_block_totals_kernel<true><<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, nwords, block_tot);
-    OGN_LAUNCH_CHECK("scan_block_totals_kernel");
-    scan_block_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(block_tot, nblocks, d_count);
-    OGN_LAUNCH_CHECK("scan_block_offsets_kernel");
-    if (out_index && out_value && capacity > 0) {
-        scatter_flags_kernel<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(flags, nwords, block_tot, src, sign, emap, nxw,
-                                                                      out_index, out_value, capacity);
-        OGN_LAUNCH_CHECK("scatter_flags_kernel");
+// ---- compaction of the two flag arrays (maxima, minima) in three launches ------------------
+// A thread owns CF_ITEMS consecutive flag words (two 16-byte loads), a block CF_THREADS * CF_ITEMS;
+// blockIdx.y selects the list.  Phase 1: set bits per block; phase 2: one block per list turns the
+// block totals into exclusive offsets; phase 3: every thread re-reads its words and writes its
+// entries at offset(block) + exclusive prefix inside the block, which keeps C order = np.where order.
+constexpr int CF_THREADS = 256;
+constexpr int CF_ITEMS = 8;
+constexpr int CF_WORDS = CF_THREADS * CF_ITEMS;
+
+__device__ __forceinline__ void cf_load(const uint32_t *__restrict__ flags, size_t nwords, size_t base, uint32_t (&w)[CF_ITEMS]) {
+    if (base + CF_ITEMS <= nwords) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(flags + base));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(flags + base) + 1);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < CF_ITEMS; ++j) w[j] = base + j < nwords ? flags[base + j] : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(CF_THREADS)
+flag_totals_kernel(const uint32_t *__restrict__ fa, const uint32_t *__restrict__ fb, size_t nwords,
+                   int64_t *__restrict__ tot, int nblocks) {
+    const uint32_t *flags = blockIdx.y ? fb : fa;
+    uint32_t w[CF_ITEMS];
+    cf_load(flags, nwords, (size_t)blockIdx.x * CF_WORDS + (size_t)threadIdx.x * CF_ITEMS, w);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < CF_ITEMS; ++j) c += __popc(w[j]);
+    int total;
+    block_exclusive_scan(c, &total);
+    if (threadIdx.x == 0) tot[(size_t)blockIdx.y * nblocks + blockIdx.x] = total;
+}
+
+__global__ void flag_offsets_kernel(int64_t *__restrict__ tot, int nblocks, int64_t *__restrict__ grand) {
+    int64_t *t = tot + (size_t)blockIdx.x * nblocks;
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < nblocks ? (int)t[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, &total);
+        if (i < nblocks) t[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) grand[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(CF_THREADS)
+flag_scatter_kernel(const uint32_t *__restrict__ fa, const uint32_t *__restrict__ fb, size_t nwords,
+                    const int64_t *__restrict__ tot, int nblocks, const float *__restrict__ src_a,
+                    const float *__restrict__ src_b, ExMap m, int nxw, int64_t *__restrict__ idx_a,
+                    float *__restrict__ val_a, int64_t *__restrict__ idx_b, float *__restrict__ val_b, int64_t capacity) {
+    const bool second = blockIdx.y != 0;
+    const uint32_t *flags = second ? fb : fa;
+    const float *src = second ? src_b : src_a;
+    const float sign = second ? -1.f : 1.f;
+    int64_t *out_index = second ? idx_b : idx_a;
+    float *out_value = second ? val_b : val_a;
+    const size_t base = (size_t)blockIdx.x * CF_WORDS + (size_t)threadIdx.x * CF_ITEMS;
+    uint32_t w[CF_ITEMS];
+    cf_load(flags, nwords, base, w);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < CF_ITEMS; ++j) c += __popc(w[j]);
+    const int ex = block_exclusive_scan(c, nullptr);
+    if (!c) return;
+    int64_t pos = tot[(size_t)blockIdx.y * nblocks + blockIdx.x] + ex;
+#pragma unroll 1
+    for (int j = 0; j < CF_ITEMS; ++j) {
+        uint32_t v = w[j];
+        if (!v) continue;
+        const size_t i = base + j;
+        const size_t rowid = i / nxw;  // z*ony + (y - oy0)
+        const int xw = (int)(i - rowid * nxw);
+        const int z = (int)(rowid / m.ony), y = (int)(rowid - (size_t)z * m.ony) + m.oy0;
+        const size_t lbase = ((size_t)z * m.ny + y) * m.nx + m.ox0a + (size_t)xw * 32;
+        const int64_t gbase = ((int64_t)z * m.gny + (y + m.gy0)) * m.gnx + m.gx0 + m.ox0a + (int64_t)xw * 32;
+        while (v) {
+            const int bit = __ffs(v) - 1;
+            v &= v - 1;
+            if (pos < capacity) {
+                out_index[pos] = gbase + bit;
+                out_value[pos] = sign * src[lbase + bit];
+            }
+            ++pos;
+        }
+    }
+}
+
+// counts -> d_counts[0..1]; lists (when given) in C order
+static int compact_flags2(ogn_ctx *ctx, const uint32_t *flag_max, const uint32_t *flag_min, size_t nwords,
+                          const float *a, const float *b, ExMap emap, int nxw, int64_t *max_index, float *max_value,
+                          int64_t *min_index, float *min_value, int64_t capacity, int64_t *d_counts) {
+    const int nblocks = ogn_div_up((int64_t)nwords, CF_WORDS);
+    int64_t *tot = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, "scan_tot2", (size_t)2 * nblocks + 2, &tot));
+    flag_totals_kernel<<<dim3(nblocks, 2), CF_THREADS, 0, ctx->stream>>>(flag_max, flag_min, nwords, tot, nblocks);
+    OGN_LAUNCH_CHECK("flag_totals_kernel");
+    flag_offsets_kernel<<<2, 1024, 0, ctx->stream>>>(tot, nblocks, d_counts);
+    OGN_LAUNCH_CHECK("flag_offsets_kernel");
+    if (max_index && max_value && min_index && min_value && capacity > 0) {
+        flag_scatter_kernel<<<dim3(nblocks, 2), CF_THREADS, 0, ctx->stream>>>(flag_max, flag_min, nwords, tot, nblocks, a, b,
+                                                                             emap, nxw, max_index, max_value, min_index,
+                                                                             min_value, capacity);
+        OGN_LAUNCH_CHECK("flag_scatter_kernel");
     }
     return OGN_OK;
 }
@@ -728,7 +816,7 @@ int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t 
         OGN_TRY(ogn_make_tile_map(ctx, &b_map, (const float *)db, nz, ny, nx, nx, E4_BX, E4_ROWS, 1, true));
         auto kern = (d_dmax || d_dmin) ? local_extrema3_tma_kernel<true> : local_extrema3_tma_kernel<false>;
         OGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, E4_SMEM));
-        dim3 block(32, E4_ROWS);
+        dim3 block(E4_THREADS);
         dim3 grid(ogn_div_up(nxw, 4), ogn_div_up(ony, E4_TY), ogn_div_up(nz, E4_CZ));
         kern<<<grid, block, E4_SMEM, ctx->stream>>>(a_map, b_map, (const uint8_t *)dm, nz, ny, nx,
                                                                         owned.y0, owned.y1, ox0a, owned.x0, owned.x1,
@@ -777,10 +865,9 @@ int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t 
     int64_t *d_counts = nullptr;
     OGN_TRY(ogn_scratch_t(ctx, "ext_counts", (size_t)2, &d_counts));
     const ExMap emap{ny, nx, owned.y0, ony, ox0a, place.gny, place.gnx, place.gy0, place.gx0};
-    OGN_TRY(compact_flags(ctx, "max", flag_max, nwords, (const float *)da, 1.f, emap, nxw, (int64_t *)d_maxi,
-                          (float *)d_maxv, want_lists ? capacity : 0, d_counts));
-    OGN_TRY(compact_flags(ctx, "min", flag_min, nwords, (const float *)db, -1.f, emap, nxw, (int64_t *)d_mini,
-                          (float *)d_minv, want_lists ? capacity : 0, d_counts + 1));
+    OGN_TRY(compact_flags2(ctx, flag_max, flag_min, nwords, (const float *)da, (const float *)db, emap, nxw,
+                           want_lists ? (int64_t *)d_maxi : nullptr, (float *)d_maxv, (int64_t *)d_mini, (float *)d_minv,
+                           want_lists ? capacity : 0, d_counts));
 
     int64_t h_counts[2] = {0, 0};
     OGN_HT("extrema enqueued");
