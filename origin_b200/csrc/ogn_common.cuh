@@ -147,12 +147,12 @@ constexpr int ZB = 8;       // wavelengths per thread and pass
 constexpr int GMAX = 10;    // profiles sharing one set of folded samples
 constexpr int MAXG = 16;    // groups
 constexpr int MAXT = 2048;  // tap table entries
+constexpr int MAXB = 32;    // blocks of ZB tap distances per group (half-lengths up to 248)
 struct FoldDict {
-    float4 t4[MAXT / 4];           // [group][distance j][slot, padded to 4]: tap d_k[h_k + j] (0 beyond h_k)
-    unsigned char na[MAXG][256];   // [group][j]: profiles of the group with h_k >= j (a suffix of the slots)
+    unsigned char nab[MAXG][MAXB]; // [group][block]: profiles of the group active in the block (a suffix of the slots)
     int k[MAXG][GMAX];             // [group][slot]: profile index, -1 = empty slot
-    int toff[MAXG], H[MAXG];       // tap table offset and largest half-length of the group
-    int ngroups, G, hmax, nprof;
+    int toff[MAXG], nblk[MAXG];    // tap table offset (floats) and number of blocks of the group
+    int ngroups, G, hmax, nprof;   // hmax: largest half-length, padded to a multiple of ZB
 };
 }  // namespace k2f
 
@@ -167,7 +167,7 @@ struct ogn_tglr_setup_t {
     const void *d_desc = nullptr;
     int ntaps_total = 0, reach = 0, woff_min = 0;
     std::vector<const double *> w_dev;
-    std::shared_ptr<k2f::FoldDict> fold;   // set when the dictionary qualifies for K2f
+    std::shared_ptr<k2f::FoldDict> fold;   // set when the dictionary qualifies for K2f (taps already in constant memory)
 };
 
 int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place, int nfields,
@@ -176,7 +176,8 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
 int ogn_tglr_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, const float *dcube,
                     const uint8_t *dmask, ogn_window w, float *d_correl, float *d_cmin, uint8_t *d_prof,
                     float *d_maxmap, float *d_minmap);
-bool ogn_k2f_prepare(const double *taps, const int *tap_offsets, int nprof, k2f::FoldDict *d);
+bool ogn_k2f_prepare(const double *taps, const int *tap_offsets, int nprof, k2f::FoldDict *d, std::vector<float> *table);
+int ogn_k2f_upload(ogn_ctx *ctx, const std::vector<float> &table);
 int ogn_k2f_launch(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, ogn_window w, const float *cube_fsf,
                    int pitch, const uint8_t *mask, float *correl, float *correl_min, uint8_t *profile, float *maxmap,
                    float *minmap);

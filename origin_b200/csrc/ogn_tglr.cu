@@ -712,7 +712,9 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
     st->fold.reset();
     if (need_spectral && !st->pervoxel) {
         st->fold = std::make_shared<k2f::FoldDict>();
-        if (!ogn_k2f_prepare(taps, tap_offsets, nprof, st->fold.get())) st->fold.reset();
+        std::vector<float> ftable;
+        if (!ogn_k2f_prepare(taps, tap_offsets, nprof, st->fold.get(), &ftable)) st->fold.reset();
+        else OGN_TRY(ogn_k2f_upload(ctx, ftable));
     }
     const int P = psize, WP = st->WP, nf = nfields;
     constexpr int ZB = 32;

@@ -15,12 +15,14 @@
 // convolution) arrives by TMA into one of two shared-memory stages while the previous chunk is being
 // reduced.  A warp owns `np` consecutive passes of ZB = 8 wavelengths per chunk.  Per pass and profile
 // group a thread keeps two register rings of 8 window samples (forward c[z+m], backward c[z-m]); a tap
-// distance costs two LDS (prefetched one step ahead), 8 FADDs and 8 FFMAs per active profile whose tap
-// is a uniform-register operand read from the kernel parameter bank.  Profiles are grouped by width
-// (groups of G = 10, or 3 for Dico_3FWHM) and sorted inside the group, so the set of profiles that
-// still have a tap at distance m is a suffix of the group: one table lookup and one indexed branch
-// per distance.  Normalisation (table lookup), max / first-wins argmax / min, mask, maxmap / minmap
-// are fused exactly as in K2 (lib_origin.py:1197-1217, steps.py:781-793).
+// distance costs two LDS (prefetched one step ahead), 8 FADDs and 8 FFMAs per profile, whose tap is a
+// uniform-register operand read from constant memory (LDCU.64).  Profiles are grouped by width (groups
+// of G = 10, or 3 for tiny dictionaries) and every half-length is padded with zero taps to a multiple
+// of ZB, so the code of one turn of the rings (8 distances, all slots of the group) is a single
+// straight-line block that loops — it stays in the instruction cache, which measured faster than
+// skipping the zero taps through per-width code variants (11.0 ms against 13.4 ms, Dico_FWHM_2_12).
+// Normalisation (table lookup), max / first-wins argmax / min, mask, maxmap / minmap are fused exactly
+// as in K2 (lib_origin.py:1197-1217, steps.py:781-793).
 #include <math.h>
 #include <stdlib.h>
 
@@ -55,52 +57,64 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src, bool vali
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// one tap distance for the top `na` slots of the group (slots are sorted by half-length, slot G-1 is
-// the widest profile): a dense switch that falls through from the first active slot to the last,
-// i.e. one indexed branch per distance instead of a test per profile
-template <int S, int G, int GP>
-__device__ __forceinline__ void fold_slot(const float (&t)[GP], const float (&s)[ZB], float (&acc)[G][ZB]) {
-    if (S < G) {
+// Tap table in constant memory, read as float4 through the uniform datapath (LDCU.64 pairs): the taps
+// enter the FFMAs as uniform-register operands and cost no vector registers.
+//   c_ftaps[(toff + j * GP) / 4 + q] = taps of slots 4q .. 4q+3 at distance j (0 beyond a profile's h_k)
+__constant__ float4 c_ftaps[MAXT / 4];
+
+// Eight consecutive tap distances (one turn of the register rings) for the NA widest slots of the
+// group.  Everything is static: ring indices, the slots touched, the tap offsets relative to t4.
+//   wj points at row (jb - 1) of the forward window of this lane, i.e. wj[(ZB + jj) * 32] is c[zb+ZB-1+j]
+template <int NA, int G>
+__device__ __forceinline__ void fold_block(const float *__restrict__ wf, const float *__restrict__ wb,
+                                           const float4 *__restrict__ t4, float (&F)[ZB], float (&B)[ZB],
+                                           float &fn, float &bn, float (&acc)[G][ZB]) {
+    constexpr int GP = (G + 3) / 4 * 4;
+    constexpr int Q0 = (G - NA) / 4;   // first float4 of the row that holds an active slot
 #pragma unroll
-        for (int i = 0; i < ZB; ++i) acc[S < G ? S : 0][i] = fmaf(t[S < G ? S : 0], s[i], acc[S < G ? S : 0][i]);
-    }
-}
-template <int G, int GP>
-__device__ __forceinline__ void fold_fma(int na, const float (&t)[GP], const float (&s)[ZB], float (&acc)[G][ZB]) {
-    static_assert(G <= 10, "fold_fma handles up to 10 slots");
-    switch (G - na) {  // first active slot
-        case 0: fold_slot<0, G, GP>(t, s, acc); [[fallthrough]];
-        case 1: fold_slot<1, G, GP>(t, s, acc); [[fallthrough]];
-        case 2: fold_slot<2, G, GP>(t, s, acc); [[fallthrough]];
-        case 3: fold_slot<3, G, GP>(t, s, acc); [[fallthrough]];
-        case 4: fold_slot<4, G, GP>(t, s, acc); [[fallthrough]];
-        case 5: fold_slot<5, G, GP>(t, s, acc); [[fallthrough]];
-        case 6: fold_slot<6, G, GP>(t, s, acc); [[fallthrough]];
-        case 7: fold_slot<7, G, GP>(t, s, acc); [[fallthrough]];
-        case 8: fold_slot<8, G, GP>(t, s, acc); [[fallthrough]];
-        case 9: fold_slot<9, G, GP>(t, s, acc); [[fallthrough]];
-        default: break;
+    for (int jj = 0; jj < ZB; ++jj) {
+        // ring slot of absolute sample m is m mod ZB; the block starts at j = 1 mod ZB: static indices
+        F[jj % ZB] = fn;                       // c[zb + ZB - 1 + j]
+        B[(ZB - 1 - jj) % ZB] = bn;            // c[zb - j]
+        fn = wf[(jj + 1) * 32];                // samples of distance j + 1, requested a step ahead
+        bn = wb[-(jj + 1) * 32];
+        float t[GP];
+#pragma unroll
+        for (int q = Q0; q < GP / 4; ++q) {
+            const float4 v = t4[jj * (GP / 4) + q];
+            t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+        }
+        float s[ZB];
+#pragma unroll
+        for (int i = 0; i < ZB; ++i) s[i] = F[(i + 1 + jj) % ZB] + B[(i + ZB - 1 - jj) % ZB];
+#pragma unroll
+        for (int g = G - NA; g < G; ++g)
+#pragma unroll
+            for (int i = 0; i < ZB; ++i) acc[g][i] = fmaf(t[g], s[i], acc[g][i]);
     }
 }
 
-// acc[g][i] = num_{slot g}[zb + i] for the profiles of group `grp`; wrow points at c[zb] of this lane
+// acc[g][i] = num_{slot g}[zb + i] for the profiles of group `grp`; wrow points at c[zb] of this lane.
+// The half-lengths are padded to multiples of ZB with zero taps (host side), so the number of active
+// slots is constant over a block of ZB distances: one table lookup and one switch per block.
 template <int G>
 __device__ __forceinline__ void fold_group(const float *__restrict__ wrow, const FoldDict &d, int grp,
                                            float (&acc)[G][ZB]) {
     constexpr int GP = (G + 3) / 4 * 4;
-    const int toff = d.toff[grp];
+    constexpr bool FULL_ONLY = G > 3;
+    const float4 *t4 = c_ftaps + (d.toff[grp] >> 2);
     float F[ZB], B[ZB];
 #pragma unroll
     for (int i = 0; i < ZB; ++i) {
         F[i] = wrow[i * 32];
         B[i] = F[i];
     }
-    float fn = wrow[ZB * 32], bn = wrow[-32];  // samples of distance 1, requested a step ahead
+    float fn = wrow[ZB * 32], bn = wrow[-32];  // samples of distance 1
     {
         float t[GP];
 #pragma unroll
         for (int q = 0; q < GP / 4; ++q) {
-            const float4 v = d.t4[(toff >> 2) + q];
+            const float4 v = t4[q];
             t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
         }
 #pragma unroll
@@ -108,30 +122,25 @@ __device__ __forceinline__ void fold_group(const float *__restrict__ wrow, const
 #pragma unroll
             for (int i = 0; i < ZB; ++i) acc[g][i] = t[g] * F[i];  // centre tap (0 for empty slots)
     }
-    const unsigned char *na_tab = d.na[grp];
+    t4 += GP / 4;  // distance 1
+    const float *wf = wrow + ZB * 32, *wb = wrow - 32;
+    const int nblk = d.nblk[grp];
 #pragma unroll 1
-    for (int jb = 1;; jb += ZB) {
-#pragma unroll
-        for (int jj = 0; jj < ZB; ++jj) {
-            const int j = jb + jj;
-            const int na = na_tab[j];  // profiles of the group that reach distance j (0 past the widest)
-            if (na == 0) return;
-            // ring slot of absolute sample m is m mod ZB; jb = 1 mod ZB makes every index static
-            F[jj % ZB] = fn;                 // c[zb + ZB - 1 + j]
-            B[(ZB - 1 - jj) % ZB] = bn;      // c[zb - j]
-            fn = wrow[(ZB + j) * 32];        // distance j + 1 (one row of slack past the widest profile)
-            bn = wrow[-(j + 1) * 32];
-            float t[GP];
-#pragma unroll
-            for (int q = 0; q < GP / 4; ++q) {
-                const float4 v = d.t4[((toff + j * GP) >> 2) + q];
-                t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+    for (int blk = 0; blk < nblk; ++blk) {
+        if (FULL_ONLY) {
+            // one code path (all slots; taps past a profile's half-length are zero): the loop body stays
+            // resident in the instruction cache, which matters more than the ~15 % extra FFMAs
+            fold_block<G, G>(wf, wb, t4, F, B, fn, bn, acc);
+        } else {
+            switch (d.nab[grp][blk]) {  // active slots in this block of distances (uniform)
+                case 1: fold_block<1, G>(wf, wb, t4, F, B, fn, bn, acc); break;
+                case 2: fold_block<(G >= 2 ? 2 : G), G>(wf, wb, t4, F, B, fn, bn, acc); break;
+                default: fold_block<G, G>(wf, wb, t4, F, B, fn, bn, acc); break;
             }
-            float s[ZB];
-#pragma unroll
-            for (int i = 0; i < ZB; ++i) s[i] = F[(i + 1 + jj) % ZB] + B[(i + ZB - 1 - jj) % ZB];
-            fold_fma<G, GP>(na, t, s, acc);
         }
+        wf += ZB * 32;
+        wb -= ZB * 32;
+        t4 += ZB * (GP / 4);
     }
 }
 
@@ -148,7 +157,7 @@ folded_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_cons
                   float *__restrict__ maxmap, float *__restrict__ minmap) {
     // shared memory: [2 stages of window rows][mbarriers][2 x NW warps of mask rows][2 x NW warps of rs rows]
     extern __shared__ __align__(128) float smem[];
-    const int nprof = dict.nprof, hmax = dict.hmax;
+    const int nprof = dict.nprof, hmax = dict.hmax;   // hmax: padded to a multiple of ZB
     const int wz = np * ZB;       // planes per warp and chunk
     const int cz = NW * wz;       // planes per chunk
     const int win_rows = box_rows * nbox;
@@ -319,11 +328,12 @@ folded_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_cons
 // Builds the folded dictionary when every profile has odd length, is symmetric (to 1e-12 of its
 // largest tap; the two halves are averaged) and the profiles come in non-decreasing width, so that
 // walking the groups in order visits k = 0, 1, ... like the reference's loop (lib_origin.py:1207).
-bool ogn_k2f_prepare(const double *taps, const int *tap_offsets, int nprof, k2f::FoldDict *d) {
+bool ogn_k2f_prepare(const double *taps, const int *tap_offsets, int nprof, k2f::FoldDict *d, std::vector<float> *table) {
     using namespace k2f;
-    // measured on B200 at 3681x320x320: 12.4 ms against 13.4 ms for K2 with the 20 profiles of
-    // Dico_FWHM_2_12, but 5.4 ms against 2.6 ms with the 3 of Dico_3FWHM (too little work per tap
-    // distance to pay for the per-distance bookkeeping): small dictionaries stay on K2
+    // Measured on B200 at 3681x320x320: 11.0 ms against 13.4 ms for K2 with the 20 profiles of
+    // Dico_FWHM_2_12, but 2.8 ms against 2.5 ms with the 3 of Dico_3FWHM (the fold saves 53 + 29 against 103
+    // FP32 instructions per voxel there, less than the bookkeeping costs): small dictionaries stay on K2.
+    // OGN_K2_NOFOLD=1 forces K2, OGN_K2_FOLD=1 forces K2f.
     static const bool disabled = getenv("OGN_K2_NOFOLD") != nullptr;
     static const bool forced = getenv("OGN_K2_FOLD") != nullptr;
     if (disabled || nprof < 1 || (nprof <= 3 && !forced)) return false;
@@ -335,7 +345,7 @@ bool ogn_k2f_prepare(const double *taps, const int *tap_offsets, int nprof, k2f:
         const int L = tap_offsets[k + 1] - tap_offsets[k];
         if (L < 1 || L % 2 == 0) return false;
         const int h = (L - 1) / 2;
-        if (h < prev_h || h > 254) return false;
+        if (h < prev_h || h > 8 * MAXB - 8) return false;
         prev_h = h;
         const double *p = taps + tap_offsets[k];
         double amax = 0;
@@ -344,36 +354,44 @@ bool ogn_k2f_prepare(const double *taps, const int *tap_offsets, int nprof, k2f:
             if (fabs(p[j] - p[L - 1 - j]) > 1e-12 * amax) return false;
     }
     memset(d, 0, sizeof(*d));
-    d->nprof = nprof; d->ngroups = ngroups; d->G = G; d->hmax = prev_h;
-    int off = 0;
+    table->clear();
+    d->nprof = nprof; d->ngroups = ngroups; d->G = G;
+    auto hpad_of = [&](int k) {   // half-length padded to a multiple of ZB (zero taps), at least ZB
+        const int h = (tap_offsets[k + 1] - tap_offsets[k] - 1) / 2;
+        return std::max(ZB, (h + ZB - 1) / ZB * ZB);
+    };
+    d->hmax = hpad_of(nprof - 1);
     for (int grp = 0; grp < ngroups; ++grp) {
         const int k0 = grp * G, nact = std::min(G, nprof - k0);
-        const int kl = k0 + nact - 1;
-        const int H = (tap_offsets[kl + 1] - tap_offsets[kl] - 1) / 2;   // the widest of the group
+        const int H = hpad_of(k0 + nact - 1);   // the widest of the group
+        const int off = (int)table->size();
         if (off + (H + 1) * GP > MAXT) return false;
         d->toff[grp] = off;
-        d->H[grp] = H;
-        for (int g = 0; g < G; ++g) {
-            const int k = k0 + g - (G - nact);   // active profiles sit in the top slots, widest last
-            d->k[grp][g] = (g >= G - nact) ? k : -1;
-        }
-        for (int j = 0; j <= H + 1 && j < 256; ++j) {
+        d->nblk[grp] = H / ZB;
+        table->resize(off + (size_t)(H + 1) * GP, 0.f);
+        for (int g = 0; g < G; ++g) d->k[grp][g] = (g >= G - nact) ? k0 + g - (G - nact) : -1;   // widest last
+        for (int blk = 0; blk < H / ZB; ++blk) {
             int na = 0;
-            for (int g = 0; g < G; ++g) {
-                const int k = d->k[grp][g];
-                if (k < 0) continue;
-                const int L = tap_offsets[k + 1] - tap_offsets[k], h = (L - 1) / 2;
-                if (j <= h) {
-                    ++na;
-                    const double *p = taps + tap_offsets[k];
-                    if (j <= H) reinterpret_cast<float *>(d->t4)[off + j * GP + g] = (float)(0.5 * (p[h + j] + p[h - j]));
-                }
-            }
-            d->na[grp][j] = (unsigned char)na;
+            for (int g = 0; g < G; ++g)
+                if (d->k[grp][g] >= 0 && hpad_of(d->k[grp][g]) > blk * ZB) ++na;
+            d->nab[grp][blk] = (unsigned char)na;
         }
-        off += (H + 1) * GP;
+        for (int g = 0; g < G; ++g) {
+            const int k = d->k[grp][g];
+            if (k < 0) continue;
+            const int L = tap_offsets[k + 1] - tap_offsets[k], h = (L - 1) / 2;
+            const double *p = taps + tap_offsets[k];
+            for (int j = 0; j <= h; ++j) (*table)[off + j * GP + g] = (float)(0.5 * (p[h + j] + p[h - j]));
+        }
     }
     return true;
+}
+
+// host -> constant memory (synchronous with respect to the pageable source vector)
+int ogn_k2f_upload(ogn_ctx *ctx, const std::vector<float> &table) {
+    OGN_CUDA(cudaMemcpyToSymbolAsync(k2f::c_ftaps, table.data(), table.size() * sizeof(float), 0, cudaMemcpyHostToDevice,
+                                     ctx->stream));
+    return OGN_OK;
 }
 
 template <int G, int NW>
