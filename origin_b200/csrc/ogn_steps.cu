@@ -32,8 +32,14 @@ int get_event(ogn_ctx *ctx, size_t i, cudaEvent_t *ev) {
 int step05_streamed(ogn_ctx *ctx, const Step05Args &a, const ogn_tglr_setup_t &st) {
     const int nz = a.nz, ny = a.ny, nx = a.nx;
     const size_t vol = (size_t)nz * ny * nx, img = (size_t)ny * nx, plane_b = img * 4;
-    constexpr int SLAB = 64;
-    const int nslab = ogn_div_up(ny, SLAB);
+    // Rows per slab.  The call is PCIe-bound (measured 57 GB/s one way, 46 GB/s each way when both directions
+    // are busy), so what matters is the pipeline ramp — the first upload and the last download — which
+    // shrinks with the slab: 82 / 76 / 73.5 ms at 64 / 32 / 16 rows for 3681x320x320.  16 still covers the
+    // FSF halo (the P/2 rows below a slab arrive with the next one); K1 runs half-empty 32-row warp patches
+    // on such slabs, which stays hidden behind the copies.
+    static const int SLAB = getenv("OGN_SLAB") ? std::max(16, atoi(getenv("OGN_SLAB"))) : 16;
+    const int slab = std::max(SLAB, a.psize / 2 + 1);
+    const int nslab = ogn_div_up(ny, slab);
     if (!ctx->h2d_stream) OGN_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
     if (!ctx->d2h_stream) OGN_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
     float *d_cube = nullptr, *d_correl = nullptr, *d_cmin = nullptr, *d_maxmap = nullptr, *d_minmap = nullptr;
@@ -54,7 +60,7 @@ int step05_streamed(ogn_ctx *ctx, const Step05Args &a, const ogn_tglr_setup_t &s
     OGN_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ev, 0));
     const float *h_cube = static_cast<const float *>(a.cube);
     for (int s = 0; s < nslab; ++s) {
-        const int y0 = s * SLAB, rows = std::min(SLAB, ny - y0);
+        const int y0 = s * slab, rows = std::min(slab, ny - y0);
         const size_t off = (size_t)y0 * nx;
         OGN_CUDA(cudaMemcpy2DAsync(d_cube + off, plane_b, h_cube + off, plane_b, (size_t)rows * nx * 4, nz,
                                    cudaMemcpyHostToDevice, ctx->h2d_stream));
@@ -65,8 +71,8 @@ int step05_streamed(ogn_ctx *ctx, const Step05Args &a, const ogn_tglr_setup_t &s
         OGN_CUDA(cudaEventRecord(ev, ctx->h2d_stream));
     }
     for (int s = 0; s < nslab; ++s) {
-        const int y0 = s * SLAB, rows = std::min(SLAB, ny - y0);
-        // slab s needs input rows up to y0 + rows + P/2: they arrive with slab s+1 (SLAB >= P/2)
+        const int y0 = s * slab, rows = std::min(slab, ny - y0);
+        // slab s needs input rows up to y0 + rows + P/2: they arrive with slab s+1 (slab > P/2)
         OGN_TRY(get_event(ctx, 1 + std::min(s + 1, nslab - 1), &ev));
         OGN_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
         OGN_TRY(ogn_tglr_window(ctx, ctx->stream, st, d_cube, d_mask, ogn_window{y0, y0 + rows, 0, nx}, d_correl,
