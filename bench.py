@@ -286,6 +286,8 @@ def main_gpu(args):
         i = state['i']
         state['i'] = i + 1
         t0 = time.perf_counter()
+        if gather is not None and not os.environ.get('OGN_BENCH_NO_GATHER'):
+            gather.attach(slot=i % 2)      # rank 0's own tile is stored by K2 itself
         res = lib_origin.step05(cube, fsf, None, profs, mask, 3, 1e-8, True, out=out_sets[i % len(out_sets)], ctx=ctx,
                                 tile=(tile, (ny, nx)) if world > 1 else None)
         t0 = tick('step05', t0)
@@ -298,7 +300,9 @@ def main_gpu(args):
             t0 = tick('allreduce', t0)
             # correl -> rank 0.  Enqueued last: the bulk stores would otherwise sit in front of the small
             # allreduce on the NVLink queues; this way they overlap the kernels of the next step instead.
-            if gather is not None:
+            if os.environ.get('OGN_BENCH_NO_GATHER') or (os.environ.get('OGN_BENCH_SKIP_LOCAL') and rank == 0):
+                pass                                      # diagnostics only: isolate the cost of the gather
+            elif gather is not None:
                 gather.scatter(res['correl'], tile, (ny, nx), slot=i % 2)
             else:
                 state['correl_full'] = ogd.gather_owned(res['correl'], tile, all_tiles, (nz, ny, nx))

@@ -213,6 +213,10 @@ OGN_API int ogn_peer_free(ogn_ctx *ctx, void *dev_ptr);
 OGN_API int ogn_peer_open(ogn_ctx *ctx, const unsigned char *handle64, void **dev_ptr);
 OGN_API int ogn_peer_close(ogn_ctx *ctx, void *dev_ptr);
 OGN_API int ogn_scatter_tile(ogn_ctx *ctx, const float *src, int nz, int ny, int nx, const int *tile, float *dst);
+/* On the rank that owns the gathered cube: make the next ogn_step05_tile call store the window it owns
+ * of correl into `dst` as well (fused into the spectral kernel), so that rank needs no ogn_scatter_tile of
+ * its own tile.  One-shot. */
+OGN_API int ogn_set_local_gather(ogn_ctx *ctx, float *dst);
 OGN_API int ogn_peer_join(ogn_ctx *ctx);
 OGN_API int ogn_peer_sync(ogn_ctx *ctx);
 

@@ -33,6 +33,7 @@ SIGNATURES = {
     'ogn_peer_open': (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_void_p)]),
     'ogn_peer_close': (c_int, [c_void_p, c_void_p]),
     'ogn_scatter_tile': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'ogn_set_local_gather': (c_int, [c_void_p, c_void_p]),
     'ogn_peer_join': (c_int, [c_void_p]),
     'ogn_peer_sync': (c_int, [c_void_p]),
     'ogn_timing_enable': (c_int, [c_void_p, c_int]),

@@ -1,5 +1,7 @@
 // libogn context, scratch arena and staging helpers.
 #include <stdarg.h>
+
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -99,6 +101,9 @@ extern "C" int ogn_trim(ogn_ctx *ctx) {
 extern "C" void ogn_destroy(ogn_ctx *ctx) {
     if (!ctx) return;
     ogn_trim(ctx);
+    if (ctx->stage_h) cudaFreeHost(ctx->stage_h);
+    if (ctx->res_h) cudaFreeHost(ctx->res_h);
+    if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
     for (void *p : ctx->peer_mapped) cudaIpcCloseMemHandle(p);
     for (void *p : ctx->peer_owned) cudaFree(p);
     delete ctx;
@@ -165,6 +170,91 @@ extern "C" int ogn_host_alloc(size_t bytes, void **out) {
 
 extern "C" int ogn_host_free(void *ptr) {
     return cudaFreeHost(ptr) == cudaSuccess ? OGN_OK : OGN_ERR_CUDA;
+}
+
+// ---- zero-copy staging ------------------------------------------------------------------------
+__global__ void upload_kernel(const unsigned char *__restrict__ src, const ogn_upload_table tab) {
+    const ogn_upload_item it = tab.item[blockIdx.x];
+    const unsigned *s = reinterpret_cast<const unsigned *>(src + it.off);
+    unsigned *d = reinterpret_cast<unsigned *>(it.dst);
+    for (unsigned i = threadIdx.x; i < it.bytes / 4; i += blockDim.x) d[i] = s[i];
+}
+
+__global__ void fill_words_kernel(unsigned *__restrict__ p, unsigned word, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = word;
+}
+
+int ogn_fill_words(ogn_ctx *ctx, cudaStream_t stream, void *p, unsigned word, size_t bytes) {
+    if (bytes == 0) return OGN_OK;
+    const size_t n = bytes / 4;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 8);
+    fill_words_kernel<<<blocks, 256, 0, stream>>>(static_cast<unsigned *>(p), word, n);
+    OGN_LAUNCH_CHECK("fill_words_kernel");
+    return OGN_OK;
+}
+
+static int stage_reserve(ogn_ctx *ctx, size_t bytes) {
+    if (ctx->stage_cap >= bytes) return OGN_OK;
+    if (ctx->stage_h) {
+        OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+        OGN_CUDA(cudaFreeHost(ctx->stage_h));
+        ctx->stage_h = ctx->stage_d = nullptr;
+        ctx->stage_cap = 0;
+    }
+    const size_t cap = std::max<size_t>(bytes, 256 * 1024);
+    void *hp = nullptr, *dp = nullptr;
+    cudaError_t e = cudaHostAlloc(&hp, cap, cudaHostAllocMapped);
+    if (e != cudaSuccess) return ogn_fail(ctx, OGN_ERR_NOMEM, "cudaHostAlloc(mapped, %zu) failed: %s", cap, cudaGetErrorString(e));
+    OGN_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+    ctx->stage_h = static_cast<unsigned char *>(hp);
+    ctx->stage_d = static_cast<unsigned char *>(dp);
+    ctx->stage_cap = cap;
+    return OGN_OK;
+}
+
+int ogn_uploader::add(void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return OGN_OK;
+    if (bytes % 4 || tab.n >= OGN_UPLOAD_MAX) return ogn_fail(ctx, OGN_ERR_ARG, "ogn_uploader: bad item");
+    if (used == 0 && ctx->stage_pending) {  // the previous batch may still be read by its kernel
+        OGN_CUDA(cudaEventSynchronize(ctx->stage_ev));
+        ctx->stage_pending = false;
+    }
+    const size_t off = (used + 15) / 16 * 16;
+    if (off + bytes > ctx->stage_cap) {
+        if (tab.n) return ogn_fail(ctx, OGN_ERR_NOMEM, "ogn_uploader: staging buffer too small");
+        OGN_TRY(stage_reserve(ctx, off + bytes));
+    }
+    memcpy(ctx->stage_h + off, src, bytes);
+    tab.item[tab.n++] = ogn_upload_item{dst, (unsigned)off, (unsigned)bytes};
+    used = off + bytes;
+    return OGN_OK;
+}
+
+int ogn_uploader::flush(cudaStream_t stream) {
+    if (tab.n == 0) return OGN_OK;
+    upload_kernel<<<tab.n, 256, 0, stream>>>(ctx->stage_d, tab);
+    OGN_LAUNCH_CHECK("upload_kernel");
+    if (!ctx->stage_ev) OGN_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming));
+    OGN_CUDA(cudaEventRecord(ctx->stage_ev, stream));
+    ctx->stage_pending = true;
+    tab.n = 0;
+    used = 0;
+    return OGN_OK;
+}
+
+int ogn_result_slots(ogn_ctx *ctx, int64_t **dev, int64_t **host) {
+    if (!ctx->res_h) {
+        void *hp = nullptr, *dp = nullptr;
+        cudaError_t e = cudaHostAlloc(&hp, 32 * sizeof(int64_t), cudaHostAllocMapped);
+        if (e != cudaSuccess) return ogn_fail(ctx, OGN_ERR_NOMEM, "cudaHostAlloc(mapped) failed: %s", cudaGetErrorString(e));
+        OGN_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+        ctx->res_h = static_cast<int64_t *>(hp);
+        ctx->res_d = static_cast<int64_t *>(dp);
+    }
+    *dev = ctx->res_d;
+    *host = ctx->res_h;
+    return OGN_OK;
 }
 
 int ogn_scratch(ogn_ctx *ctx, const char *name, size_t bytes, void **out) {

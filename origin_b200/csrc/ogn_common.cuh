@@ -53,7 +53,33 @@ struct ogn_ctx {
     cudaEvent_t peer_ev_begin = nullptr, peer_ev_end = nullptr;
     std::vector<void *> peer_owned, peer_mapped;
     std::map<const void *, cudaEvent_t> readers;   // source buffer -> event of the last scatter reading it
+    // zero-copy staging (ogn_api.cu): small host -> device tables and device -> host scalars travel through
+    // mapped pinned memory read / written by kernels, so the hot path never queues on a copy engine
+    unsigned char *stage_h = nullptr, *stage_d = nullptr;
+    size_t stage_cap = 0;
+    cudaEvent_t stage_ev = nullptr;
+    bool stage_pending = false;
+    int64_t *res_h = nullptr, *res_d = nullptr;    // 32 mapped int64 result slots
+    float *local_gather = nullptr;                 // ogn_set_local_gather: consumed by the next ogn_step05_tile
 };
+
+// Batches small host -> device copies into ONE kernel that reads a mapped pinned staging buffer over
+// PCIe and writes every destination (no copy-engine operation, one launch instead of one memcpy each).
+struct ogn_upload_item { void *dst; unsigned off, bytes; };
+constexpr int OGN_UPLOAD_MAX = 16;
+struct ogn_upload_table { ogn_upload_item item[OGN_UPLOAD_MAX]; int n; };
+struct ogn_uploader {
+    ogn_ctx *ctx;
+    size_t used = 0;
+    ogn_upload_table tab;
+    explicit ogn_uploader(ogn_ctx *c) : ctx(c) { tab.n = 0; }
+    int add(void *dst, const void *src, size_t bytes);   // bytes: multiple of 4
+    int flush(cudaStream_t stream);
+};
+// p[0 .. bytes) = repeated 32-bit `word` (bytes: multiple of 4), by a kernel on `stream`
+int ogn_fill_words(ogn_ctx *ctx, cudaStream_t stream, void *p, unsigned word, size_t bytes);
+// mapped result slots (device pointer, host pointer); valid after the stream that wrote them is synchronised
+int ogn_result_slots(ogn_ctx *ctx, int64_t **dev, int64_t **host);
 
 int ogn_fail(ogn_ctx *ctx, int code, const char *fmt, ...);
 
@@ -156,6 +182,15 @@ struct FoldDict {
 };
 }  // namespace k2f
 
+// Second destination of K2's correl stores (multi-GPU): the rank that owns the gathered cube writes the
+// voxels it owns straight into it, instead of copying them afterwards.
+struct ogn_gather2 {
+    float *dst = nullptr;          // [nz][ny][nx] on this device, or nullptr
+    int ny = 0, nx = 0;            // field size
+    int dy = 0, dx = 0;            // sub-cube origin in the field
+    int y0 = 0, y1 = 0, x0 = 0, x1 = 0;   // owned window, sub-cube coordinates
+};
+
 struct ogn_tglr_setup_t {
     int nz = 0, ny = 0, nx = 0, P = 0, WP = 0, nfields = 0, nprof = 0;
     bool pervoxel = false;
@@ -167,6 +202,7 @@ struct ogn_tglr_setup_t {
     const void *d_desc = nullptr;
     int ntaps_total = 0, reach = 0, woff_min = 0;
     std::vector<const double *> w_dev;
+    ogn_gather2 gather2;
     std::shared_ptr<k2f::FoldDict> fold;   // set when the dictionary qualifies for K2f (taps already in constant memory)
 };
 
@@ -177,7 +213,7 @@ int ogn_tglr_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &s
                     const uint8_t *dmask, ogn_window w, float *d_correl, float *d_cmin, uint8_t *d_prof,
                     float *d_maxmap, float *d_minmap);
 bool ogn_k2f_prepare(const double *taps, const int *tap_offsets, int nprof, k2f::FoldDict *d, std::vector<float> *table);
-int ogn_k2f_upload(ogn_ctx *ctx, const std::vector<float> &table);
+int ogn_k2f_upload(ogn_ctx *ctx, ogn_uploader *up, const std::vector<float> &table);
 int ogn_k2f_launch(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, ogn_window w, const float *cube_fsf,
                    int pitch, const uint8_t *mask, float *correl, float *correl_min, uint8_t *profile, float *maxmap,
                    float *minmap);

@@ -686,7 +686,9 @@ flag_totals_kernel(const uint32_t *__restrict__ fa, const uint32_t *__restrict__
     if (threadIdx.x == 0) tot[(size_t)blockIdx.y * nblocks + blockIdx.x] = total;
 }
 
-__global__ void flag_offsets_kernel(int64_t *__restrict__ tot, int nblocks, int64_t *__restrict__ grand) {
+// grand totals go to device memory and (optionally) to mapped pinned host memory / a caller's device array
+__global__ void flag_offsets_kernel(int64_t *__restrict__ tot, int nblocks, int64_t *__restrict__ grand,
+                                    int64_t *__restrict__ grand_mapped, int64_t *__restrict__ grand_user) {
     int64_t *t = tot + (size_t)blockIdx.x * nblocks;
     __shared__ int64_t carry;
     if (threadIdx.x == 0) carry = 0;
@@ -701,7 +703,11 @@ __global__ void flag_offsets_kernel(int64_t *__restrict__ tot, int nblocks, int6
         if (threadIdx.x == 0) carry += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) grand[blockIdx.x] = carry;
+    if (threadIdx.x == 0) {
+        grand[blockIdx.x] = carry;
+        if (grand_mapped) grand_mapped[blockIdx.x] = carry;
+        if (grand_user) grand_user[blockIdx.x] = carry;
+    }
 }
 
 __global__ void __launch_bounds__(CF_THREADS)
@@ -749,13 +755,14 @@ flag_scatter_kernel(const uint32_t *__restrict__ fa, const uint32_t *__restrict_
 // counts -> d_counts[0..1]; lists (when given) in C order
 static int compact_flags2(ogn_ctx *ctx, const uint32_t *flag_max, const uint32_t *flag_min, size_t nwords,
                           const float *a, const float *b, ExMap emap, int nxw, int64_t *max_index, float *max_value,
-                          int64_t *min_index, float *min_value, int64_t capacity, int64_t *d_counts) {
+                          int64_t *min_index, float *min_value, int64_t capacity, int64_t *d_counts,
+                          int64_t *mapped_counts, int64_t *user_counts) {
     const int nblocks = ogn_div_up((int64_t)nwords, CF_WORDS);
     int64_t *tot = nullptr;
     OGN_TRY(ogn_scratch_t(ctx, "scan_tot2", (size_t)2 * nblocks + 2, &tot));
     flag_totals_kernel<<<dim3(nblocks, 2), CF_THREADS, 0, ctx->stream>>>(flag_max, flag_min, nwords, tot, nblocks);
     OGN_LAUNCH_CHECK("flag_totals_kernel");
-    flag_offsets_kernel<<<2, 1024, 0, ctx->stream>>>(tot, nblocks, d_counts);
+    flag_offsets_kernel<<<2, 1024, 0, ctx->stream>>>(tot, nblocks, d_counts, mapped_counts, user_counts);
     OGN_LAUNCH_CHECK("flag_offsets_kernel");
     if (max_index && max_value && min_index && min_value && capacity > 0) {
         flag_scatter_kernel<<<dim3(nblocks, 2), CF_THREADS, 0, ctx->stream>>>(flag_max, flag_min, nwords, tot, nblocks, a, b,
@@ -865,19 +872,19 @@ int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t 
     int64_t *d_counts = nullptr;
     OGN_TRY(ogn_scratch_t(ctx, "ext_counts", (size_t)2, &d_counts));
     const ExMap emap{ny, nx, owned.y0, ony, ox0a, place.gny, place.gnx, place.gy0, place.gx0};
+    // the two counts come back through mapped pinned memory written by the kernel (no copy-engine read-back,
+    // which would queue behind a peer gather in flight)
+    int64_t *res_d = nullptr, *res_h = nullptr;
+    OGN_TRY(ogn_result_slots(ctx, &res_d, &res_h));
+    int64_t *user_counts = counts && ogn_is_device_ptr(counts) ? counts : nullptr;
     OGN_TRY(compact_flags2(ctx, flag_max, flag_min, nwords, (const float *)da, (const float *)db, emap, nxw,
                            want_lists ? (int64_t *)d_maxi : nullptr, (float *)d_maxv, (int64_t *)d_mini, (float *)d_minv,
-                           want_lists ? capacity : 0, d_counts));
-
-    int64_t h_counts[2] = {0, 0};
+                           want_lists ? capacity : 0, d_counts, res_d, user_counts));
     OGN_HT("extrema enqueued");
-    OGN_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost, ctx->stream));
     OGN_CUDA(cudaStreamSynchronize(ctx->stream));
     OGN_HT("extrema counts back");
-    if (counts) {
-        if (ogn_is_device_ptr(counts)) OGN_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToDevice, ctx->stream));
-        else { counts[0] = h_counts[0]; counts[1] = h_counts[1]; }
-    }
+    const int64_t h_counts[2] = {res_h[0], res_h[1]};
+    if (counts && !user_counts) { counts[0] = h_counts[0]; counts[1] = h_counts[1]; }
     OGN_TRY(ogn_output_commit(ctx, dense_max, d_dmax, vol * 4));
     OGN_TRY(ogn_output_commit(ctx, dense_min, d_dmin, vol * 4));
     if (want_lists) {
@@ -948,7 +955,7 @@ extern "C" int ogn_purity_stats(ogn_ctx *ctx, const int64_t *max_index, const fl
     void *d_sp = nullptr;
     if (spaxel_max) {
         OGN_TRY(ogn_output(ctx, "pur_spaxel_max", spaxel_max, img * 4, &d_sp));
-        OGN_CUDA(cudaMemsetAsync(d_sp, 0, img * 4, ctx->stream));
+        OGN_TRY(ogn_fill_words(ctx, ctx->stream, d_sp, 0u, img * 4));
     }
     if (nmax > 0) {
         list_stats_kernel<<<ogn_div_up(nmax, 256), 256, 0, ctx->stream>>>(L.maxi, L.maxv, nmax, nullptr, (int64_t)img,
@@ -985,8 +992,8 @@ extern "C" int ogn_purity_counts(ogn_ctx *ctx, const int64_t *max_index, const f
     void *d_n1 = nullptr, *d_n0 = nullptr;
     OGN_TRY(ogn_output(ctx, "pur_n1", n1, (size_t)nthresh * 8, &d_n1));
     OGN_TRY(ogn_output(ctx, "pur_n0", n0, (size_t)nthresh * 8, &d_n0));
-    OGN_CUDA(cudaMemsetAsync(d_n1, 0, (size_t)nthresh * 8, ctx->stream));
-    OGN_CUDA(cudaMemsetAsync(d_n0, 0, (size_t)nthresh * 8, ctx->stream));
+    OGN_TRY(ogn_fill_words(ctx, ctx->stream, d_n1, 0u, (size_t)nthresh * 8));
+    OGN_TRY(ogn_fill_words(ctx, ctx->stream, d_n0, 0u, (size_t)nthresh * 8));
     const size_t sm = (size_t)nthresh * sizeof(unsigned int);
     if (nmax > 0) {
         list_counts_kernel<<<ogn_div_up(nmax, 256), 256, sm, ctx->stream>>>(L.maxi, L.maxv, nmax, nullptr, (int64_t)img,

@@ -173,6 +173,16 @@ extern "C" int ogn_scatter_tile(ogn_ctx *ctx, const float *src, int nz, int ny, 
     return OGN_OK;
 }
 
+// The next ogn_step05_tile call on this context also stores the window it owns of `correl` into `dst`
+// (the [nz][gny][gnx] cube of ogn_peer_alloc on THIS device): the owner of the gathered cube needs no
+// copy of its own tile.  One-shot; pass NULL to cancel.
+extern "C" int ogn_set_local_gather(ogn_ctx *ctx, float *dst) {
+    if (!ctx) return OGN_ERR_ARG;
+    if (dst && !ogn_is_device_ptr(dst)) return ogn_fail(ctx, OGN_ERR_ARG, "ogn_set_local_gather: dst must be device memory");
+    ctx->local_gather = dst;
+    return OGN_OK;
+}
+
 // Main stream waits for every scatter enqueued so far (no host synchronisation).
 extern "C" int ogn_peer_join(ogn_ctx *ctx) {
     if (!ctx) return OGN_ERR_ARG;

@@ -125,6 +125,12 @@ int step05_run(ogn_ctx *ctx, const Step05Args &a, const int *tile) {
     OGN_TRY(ogn_tglr_setup(ctx, nz, ny, nx, &place, a.nfields, a.fsf, a.psize, a.weights, a.taps, a.tap_offsets,
                            a.nprof, true, &st));
     OGN_HT("setup done");
+    if (tile && ctx->local_gather) {   // this rank owns the gathered cube: K2 stores its owned voxels there as well
+        st.gather2.dst = ctx->local_gather;
+        st.gather2.ny = place.gny; st.gather2.nx = place.gnx; st.gather2.dy = place.gy0; st.gather2.dx = place.gx0;
+        st.gather2.y0 = owned.y0; st.gather2.y1 = owned.y1; st.gather2.x0 = owned.x0; st.gather2.x1 = owned.x1;
+    }
+    ctx->local_gather = nullptr;
     const size_t vol = (size_t)nz * ny * nx, img = (size_t)ny * nx;
 
     const bool host_in = !ogn_is_device_ptr(a.cube);
@@ -147,8 +153,11 @@ int step05_run(ogn_ctx *ctx, const Step05Args &a, const int *tile) {
     OGN_TRY(ogn_input_cube_f32(ctx, "cube", a.cube, a.cube_dtype, vol, &d_cube));
     OGN_TRY(ogn_tglr_init_maps(ctx, ctx->stream, (float *)d_maxmap, (float *)d_minmap, img));
     // TGLR on the owned window grown by the extremum radius (clipped to the sub-cube)
+    // ... and to the left down to a multiple of 4 columns: K1's TMA box starts P/2 = 12 columns left of the
+    // window and a TMA box must start on a 16-byte boundary (the few extra columns lie inside the sub-cube
+    // and belong to a neighbour; computing them is harmless)
     const ogn_window w{std::max(0, owned.y0 - a.sy / 2), std::min(ny, owned.y1 + a.sy / 2),
-                       std::max(0, owned.x0 - a.sx / 2), std::min(nx, owned.x1 + a.sx / 2)};
+                       std::max(0, owned.x0 - a.sx / 2) / 4 * 4, std::min(nx, owned.x1 + a.sx / 2)};
     OGN_TRY(ogn_tglr_window(ctx, ctx->stream, st, d_cube, (const uint8_t *)d_mask, w, (float *)d_correl,
                             (float *)d_cmin, (uint8_t *)d_prof, (float *)d_maxmap, (float *)d_minmap));
     OGN_HT("tglr enqueued");

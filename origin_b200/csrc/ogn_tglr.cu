@@ -428,7 +428,7 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
                     const float *__restrict__ rs, int nzp, int ncls, int ncx, int P, int stage_rs, int stage_mask,
                     const uint8_t *__restrict__ mask,
                     float *__restrict__ correl, float *__restrict__ correl_min, uint8_t *__restrict__ profile,
-                    float *__restrict__ maxmap, float *__restrict__ minmap) {
+                    float *__restrict__ maxmap, float *__restrict__ minmap, const ogn_gather2 g2) {
     // shared memory: [2 stages of window rows][taps (+ squares)][mbarriers]
     //                [2 stages x NW warps of mask rows][2 stages x NW warps of rs rows]
     extern __shared__ __align__(128) float smem[];
@@ -447,6 +447,7 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
     const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int x0 = blockIdx.x * 32, x = x0 + lane, y = blockIdx.y;   // window coordinates
     const int oy = y + oy_off, ox = x + ox_off;                       // coordinates in the product cubes
+    const bool own2 = g2.dst != nullptr && oy >= g2.y0 && oy < g2.y1 && ox >= g2.x0 && ox < g2.x1;
     const int nchunk = (nz + NW * ZB - 1) / (NW * ZB);
     const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
 
@@ -600,6 +601,7 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
                         const bool masked = (mbits >> i) & 1u;
                         const float c = masked ? 0.f : mx[i];
                         if (correl) correl[o] = c;
+                        if (own2) g2.dst[((size_t)z * g2.ny + oy + g2.dy) * g2.nx + ox + g2.dx] = c;
                         if (correl_min) correl_min[o] = mn[i];
                         if (profile) profile[o] = masked ? (uint8_t)0 : (uint8_t)arg[i];
                         cmax = fmaxf(cmax, c);
@@ -709,18 +711,20 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
         return ogn_fail(ctx, OGN_ERR_ARG, "sub-cube (%d,%d)+(%d,%d) does not fit the %dx%d field", st->place.gy0,
                         st->place.gx0, ny, nx, st->place.gny, st->place.gnx);
     st->pervoxel = weights != nullptr || nfields > 1 || !need_spectral;
+    std::vector<float> fold_table;
     st->fold.reset();
     if (need_spectral && !st->pervoxel) {
         st->fold = std::make_shared<k2f::FoldDict>();
-        std::vector<float> ftable;
-        if (!ogn_k2f_prepare(taps, tap_offsets, nprof, st->fold.get(), &ftable)) st->fold.reset();
-        else OGN_TRY(ogn_k2f_upload(ctx, ftable));
+        if (!ogn_k2f_prepare(taps, tap_offsets, nprof, st->fold.get(), &fold_table)) st->fold.reset();
     }
     const int P = psize, WP = st->WP, nf = nfields;
     constexpr int ZB = 32;
     st->nzp = (int)ogn_round_up(nz, ZB) + ZB;
     st->ncy = std::min(st->place.gny, P);
     st->ncx = std::min(st->place.gnx, P);
+
+    // every small host table of the setup goes through ONE zero-copy upload kernel (ogn_uploader)
+    ogn_uploader up(ctx);
 
     // ---- profiles: reversed, zero-padded to a multiple of U, float32 ----------------
     std::vector<k2::ProfDesc> desc(std::max(nprof, 1));
@@ -759,20 +763,23 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
         st->d_desc = d_desc;
         OGN_TRY(ogn_scratch_t(ctx, "taps64", (size_t)ntaps_in, &d_taps64));
         OGN_TRY(ogn_scratch_t(ctx, "tap_off", (size_t)nprof + 1, &d_tapoff));
-        OGN_CUDA(cudaMemcpyAsync(st->d_taps, tp.data(), st->ntaps_total * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-        OGN_CUDA(cudaMemcpyAsync(st->d_taps_sq, tpsq.data(), st->ntaps_total * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-        OGN_CUDA(cudaMemcpyAsync(d_desc, desc.data(), nprof * sizeof(k2::ProfDesc), cudaMemcpyHostToDevice, ctx->stream));
-        OGN_CUDA(cudaMemcpyAsync(d_taps64, taps, ntaps_in * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        OGN_CUDA(cudaMemcpyAsync(d_tapoff, tap_offsets, (nprof + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        // K2's uniform-datapath variant reads the taps from constant memory.  Host -> symbol here (not a
-        // device-to-device copy at launch time, which would queue behind a peer gather on the copy engine).
+        OGN_TRY(up.add(st->d_taps, tp.data(), st->ntaps_total * sizeof(float)));
+        OGN_TRY(up.add(st->d_taps_sq, tpsq.data(), st->ntaps_total * sizeof(float)));
+        OGN_TRY(up.add(d_desc, desc.data(), nprof * sizeof(k2::ProfDesc)));
+        OGN_TRY(up.add(d_taps64, taps, ntaps_in * sizeof(double)));
+        OGN_TRY(up.add(d_tapoff, tap_offsets, (nprof + 1) * sizeof(int)));
+        // K2's uniform-datapath variant reads the taps from constant memory: the symbols are written
+        // through their global addresses by the same upload kernel (the constant cache is invalidated
+        // between launches)
         if (st->ntaps_total + 4 <= k2::CONST_TAPS) {
-            OGN_CUDA(cudaMemcpyToSymbolAsync(k2::c_taps4, tp.data(), (size_t)st->ntaps_total * sizeof(float), 0,
-                                             cudaMemcpyHostToDevice, ctx->stream));
-            OGN_CUDA(cudaMemcpyToSymbolAsync(k2::c_desc, desc.data(), (size_t)nprof * sizeof(k2::ProfDesc), 0,
-                                             cudaMemcpyHostToDevice, ctx->stream));
+            void *sym_taps = nullptr, *sym_desc = nullptr;
+            OGN_CUDA(cudaGetSymbolAddress(&sym_taps, k2::c_taps4));
+            OGN_CUDA(cudaGetSymbolAddress(&sym_desc, k2::c_desc));
+            OGN_TRY(up.add(sym_taps, tp.data(), (size_t)st->ntaps_total * sizeof(float)));
+            OGN_TRY(up.add(sym_desc, desc.data(), (size_t)nprof * sizeof(k2::ProfDesc)));
         }
     }
+    if (st->fold) OGN_TRY(ogn_k2f_upload(ctx, &up, fold_table));
 
     // ---- FSF cubes / weight maps -> device, pointer table ------------------------------
     const size_t fsf_bytes = (size_t)nz * P * P * sizeof(double);
@@ -806,15 +813,13 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
         for (int a : rc)
             for (int b : cc) cls_list.push_back(a * st->ncx + b);
         OGN_TRY(ogn_scratch_t(ctx, "cls_list", cls_list.size(), &d_cls_list));
-        OGN_CUDA(cudaMemcpyAsync(d_cls_list, cls_list.data(), cls_list.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        OGN_TRY(up.add(d_cls_list, cls_list.data(), cls_list.size() * sizeof(int)));
     }
     const double **fsf_tab = nullptr;
     OGN_TRY(ogn_scratch_t(ctx, "fsf_tab", (size_t)nf, &fsf_tab));
-    OGN_CUDA(cudaMemcpyAsync(fsf_tab, fsf_dev.data(), nf * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
-    OGN_HT("setup copies enqueued");
-    // the pageable host vectors above die at return: make sure the copies have been staged
-    OGN_CUDA(cudaStreamSynchronize(ctx->stream));
-    OGN_HT("setup sync");
+    OGN_TRY(up.add(fsf_tab, fsf_dev.data(), nf * sizeof(double *)));
+    OGN_TRY(up.flush(ctx->stream));   // the host tables were copied into the staging buffer: no sync needed
+    OGN_HT("setup tables enqueued");
 
     // ---- K0: weights (+ squares) and the edge-class norm table ---------------------------
     OGN_TRY(ogn_scratch_t(ctx, "w32", (size_t)nf * nz * P * WP, &st->w32));
@@ -824,11 +829,11 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
         OGN_TRY(ogn_scratch_t(ctx, "w32sq", (size_t)nf * nz * P * WP, &st->w32sq));
     } else {
         OGN_TRY(ogn_scratch_t(ctx, "normcls", (size_t)st->ncy * st->ncx * st->nzp, &normcls));
-        OGN_CUDA(cudaMemsetAsync(normcls, 0, (size_t)st->ncy * st->ncx * st->nzp * sizeof(double), ctx->stream));
+        OGN_TRY(ogn_fill_words(ctx, ctx->stream, normcls, 0u, (size_t)st->ncy * st->ncx * st->nzp * sizeof(double)));
     }
     OGN_TRY(ogn_scratch_t(ctx, "fsf_asym", (size_t)1, &st->asym));
     static const bool no_fold = getenv("OGN_K1_NOFOLD") != nullptr;
-    OGN_CUDA(cudaMemsetAsync(st->asym, no_fold ? 0xff : 0, sizeof(int), ctx->stream));
+    OGN_TRY(ogn_fill_words(ctx, ctx->stream, st->asym, no_fold ? 0xffffffffu : 0u, sizeof(int)));
     {
         ogn_timer t_(ctx, "fsf_prep");
         dim3 grid(nz, nf);
@@ -930,7 +935,7 @@ static int launch_spectral(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_set
                                               st.d_taps, st.d_taps_sq, st.ntaps_total,
                                               static_cast<const k2::ProfDesc *>(st.d_desc), st.nprof, box_rows, nbox,
                                               st.woff_min, st.rs, st.nzp, st.ncy * st.ncx, st.ncx, st.P, stage_rs,
-                                              stage_mask, mask, correl, correl_min, profile, maxmap, minmap);
+                                              stage_mask, mask, correl, correl_min, profile, maxmap, minmap, st.gather2);
     OGN_LAUNCH_CHECK("spectral_glr_kernel");
     return OGN_OK;
 }

@@ -154,7 +154,7 @@ folded_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_cons
                   const float *__restrict__ rs, int nzp, int ncls, int ncx, int P, int stage_rs, int stage_mask,
                   const uint8_t *__restrict__ mask,
                   float *__restrict__ correl, float *__restrict__ correl_min, uint8_t *__restrict__ profile,
-                  float *__restrict__ maxmap, float *__restrict__ minmap) {
+                  float *__restrict__ maxmap, float *__restrict__ minmap, const ogn_gather2 g2) {
     // shared memory: [2 stages of window rows][mbarriers][2 x NW warps of mask rows][2 x NW warps of rs rows]
     extern __shared__ __align__(128) float smem[];
     const int nprof = dict.nprof, hmax = dict.hmax;   // hmax: padded to a multiple of ZB
@@ -169,6 +169,7 @@ folded_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_cons
     const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int x0 = blockIdx.x * 32, x = x0 + lane, y = blockIdx.y;   // window coordinates
     const int oy = y + oy_off, ox = x + ox_off;                       // coordinates in the product cubes
+    const bool own2 = g2.dst != nullptr && oy >= g2.y0 && oy < g2.y1 && ox >= g2.x0 && ox < g2.x1;
     const int nchunk = (nz + cz - 1) / cz;
     const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
 
@@ -305,6 +306,7 @@ folded_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_cons
                         const bool masked = (mbits >> i) & 1u;
                         const float c = masked ? 0.f : mx[i];
                         if (correl) correl[o] = c;
+                        if (own2) g2.dst[((size_t)z * g2.ny + oy + g2.dy) * g2.nx + ox + g2.dx] = c;
                         if (correl_min) correl_min[o] = mn[i];
                         if (profile) profile[o] = masked ? (uint8_t)0 : (uint8_t)arg[i];
                         cmax = fmaxf(cmax, c);
@@ -387,11 +389,11 @@ bool ogn_k2f_prepare(const double *taps, const int *tap_offsets, int nprof, k2f:
     return true;
 }
 
-// host -> constant memory (synchronous with respect to the pageable source vector)
-int ogn_k2f_upload(ogn_ctx *ctx, const std::vector<float> &table) {
-    OGN_CUDA(cudaMemcpyToSymbolAsync(k2f::c_ftaps, table.data(), table.size() * sizeof(float), 0, cudaMemcpyHostToDevice,
-                                     ctx->stream));
-    return OGN_OK;
+// host table -> constant memory, through the setup's zero-copy upload kernel
+int ogn_k2f_upload(ogn_ctx *ctx, ogn_uploader *up, const std::vector<float> &table) {
+    void *sym = nullptr;
+    OGN_CUDA(cudaGetSymbolAddress(&sym, k2f::c_ftaps));
+    return up->add(sym, table.data(), table.size() * sizeof(float));
 }
 
 template <int G, int NW>
@@ -437,7 +439,7 @@ static int launch_folded(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup
     kern<<<grid, NW * 32, smem, stream>>>(num_map, d, st.nz, wny, wnx, w.y0, w.x0, st.ny, st.nx, w.y0 + st.place.gy0,
                                           w.x0 + st.place.gx0, st.place.gny, st.place.gnx, np, box_rows, nbox, st.rs,
                                           st.nzp, st.ncy * st.ncx, st.ncx, st.P, stage_rs, stage_mask, mask, correl,
-                                          correl_min, profile, maxmap, minmap);
+                                          correl_min, profile, maxmap, minmap, st.gather2);
     OGN_LAUNCH_CHECK("folded_glr_kernel");
     return OGN_OK;
 }

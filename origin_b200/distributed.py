@@ -172,10 +172,22 @@ class PeerGather:
             raise err if err is not None else RuntimeError('peer mapping failed on another rank')
         self._torch = torch
 
+    def attach(self, slot=0):
+        """Call before ``step05(..., tile=...)``: on the destination rank the spectral kernel then stores the
+        voxels that rank owns straight into slot ``slot`` (``ogn_set_local_gather``) and :meth:`scatter` has
+        nothing left to do there; a no-op on the other ranks."""
+        self._attached = None
+        if self.rank == self.dst:
+            self.ctx.check(self.ctx.lib.ogn_set_local_gather(self.ctx.handle, self.ptrs[slot]))
+            self._attached = slot
+
     def scatter(self, cube_tile, tile, global_hw, slot=0):
         """Enqueue the copy of the owned window of ``cube_tile`` (``[nz][th][tw]`` float32 device tensor)
         into slot ``slot`` of the destination; returns immediately."""
         from ._lib import ptr
+        if getattr(self, '_attached', None) == slot and self.rank == self.dst:
+            self._attached = None      # already written by the fused stores of this step
+            return
         nz, th, tw = cube_tile.shape
         gny, gnx = global_hw
         desc = np.array([gny, gnx, tile.py0, tile.px0, tile.y0 - tile.py0, tile.y1 - tile.py0, tile.x0 - tile.px0,

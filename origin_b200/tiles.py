@@ -59,9 +59,30 @@ def grid_shape(n, ny, nx):
     return best[1], best[2]
 
 
+def _padded_columns(x0, x1, nx, halo):
+    """Column range ``[px0, px1)`` of a tile's sub-cube: at least ``halo`` columns either side of the
+    owned ``[x0, x1)`` (clipped to the image), widened by a few columns so that the kernels find their
+    fast paths — a sub-cube width that is a multiple of 16 (at least of 4: TMA tensor maps, float4 /
+    uchar4 accesses and 16-byte mask rows need it; otherwise the library stages padded copies and falls
+    back to scalar kernels) and, when possible, a computed window (owned minus one ring column) that
+    starts on a 16-column boundary of the sub-cube.  Extra halo columns are real data and change no
+    result."""
+    best = None
+    for a in range(20):
+        p0 = max(0, x0 - halo - a)
+        for b in range(20):
+            p1 = min(nx, x1 + halo + b)
+            w = p1 - p0
+            wx0 = max(0, x0 - 1 - p0)                     # first column of the computed window
+            score = (4 * (w % 16 == 0) + 2 * (w % 4 == 0) + (wx0 % 16 == 0), -(w))
+            if best is None or score > best[0]:
+                best = (score, p0, p1)
+    return best[1], best[2]
+
+
 def plan_tiles(ny, nx, n, halo):
-    """``n`` tiles covering a (ny, nx) field, each padded by ``halo`` pixels
-    where the image continues."""
+    """``n`` tiles covering a (ny, nx) field, each padded by at least ``halo`` pixels where the image
+    continues (columns a little more, see :func:`_padded_columns`)."""
     gy, gx = grid_shape(n, ny, nx)
     ys = np.linspace(0, ny, gy + 1).round().astype(int)
     xs = np.linspace(0, nx, gx + 1).round().astype(int)
@@ -69,8 +90,8 @@ def plan_tiles(ny, nx, n, halo):
     for r in range(n):
         iy, ix = divmod(r, gx)
         y0, y1, x0, x1 = int(ys[iy]), int(ys[iy + 1]), int(xs[ix]), int(xs[ix + 1])
-        tiles.append(Tile(r, y0, y1, x0, x1, max(0, y0 - halo), min(ny, y1 + halo), max(0, x0 - halo),
-                          min(nx, x1 + halo)))
+        px0, px1 = _padded_columns(x0, x1, nx, halo)
+        tiles.append(Tile(r, y0, y1, x0, x1, max(0, y0 - halo), min(ny, y1 + halo), px0, px1))
     return tiles
 
 

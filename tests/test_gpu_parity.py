@@ -409,11 +409,13 @@ def test_tglr_tile_consistency_and_spot_oracle(lo):
 # tiled and streamed execution
 # --------------------------------------------------------------------------
 
-def test_step05_tiles_reproduce_the_full_cube(lo):
-    """The multi-GPU decomposition run serially on one GPU: four tiles with 13-pixel halos give
-    bit-identical products on their owned windows and the same global extremum lists."""
+@pytest.mark.parametrize('shape,ntiles', [((300, 100, 150), 4), ((200, 120, 176), 2), ((150, 96, 320), 8)])
+def test_step05_tiles_reproduce_the_full_cube(lo, shape, ntiles):
+    """The multi-GPU decomposition run serially on one GPU: tiles with >= 13-pixel halos give
+    bit-identical products on their owned windows and the same global extremum lists.  The second case
+    splits columns so that a tile's window starts at a column that is not a multiple of 4 (the library
+    has to widen it: TMA boxes start on 16-byte boundaries)."""
     from origin_b200 import tiles
-    shape = (300, 100, 150)
     nz, ny, nx = shape
     fsf = synthetic.moffat_fsf(nz)
     cube, _ = synthetic.faint_cube(shape, fsf, n_src=8, seed=31)
@@ -421,7 +423,7 @@ def test_step05_tiles_reproduce_the_full_cube(lo):
     profs = dictionaries.dico_3fwhm()[0]
     full = lo.step05(cube, fsf, None, profs, mask, 3, 1e-8, True)
     got_max, got_min, val_max = [], [], []
-    for t in tiles.plan_tiles(ny, nx, 4, 13):
+    for t in tiles.plan_tiles(ny, nx, ntiles, 13):
         sl = (slice(None),) + t.padded
         part = lo.step05(np.ascontiguousarray(cube[sl]), fsf, None, profs, np.ascontiguousarray(mask[sl]), 3, 1e-8,
                          True, tile=(t, (ny, nx)))

@@ -23,7 +23,11 @@ def test_plan_tiles_partitions_the_field(n, ny, nx):
     for t in plan:
         cover[t.global_owned] += 1
         assert t.py0 == max(0, t.y0 - 13) and t.py1 == min(ny, t.y1 + 13)
-        assert t.px0 == max(0, t.x0 - 13) and t.px1 == min(nx, t.x1 + 13)
+        # columns: at least the halo (clipped to the image), at most 19 extra columns for alignment
+        assert t.px0 <= max(0, t.x0 - 13) and t.px1 >= min(nx, t.x1 + 13)
+        assert t.px0 >= max(0, t.x0 - 13 - 19) and t.px1 <= min(nx, t.x1 + 13 + 19)
+        if nx % 4 == 0:
+            assert (t.px1 - t.px0) % 4 == 0
         oy, ox = t.owned
         assert oy.stop - oy.start == t.y1 - t.y0 and ox.stop - ox.start == t.x1 - t.x0
     assert np.all(cover == 1)

@@ -54,8 +54,10 @@ def main():
     correl_full = ogd.gather_owned(res['correl'], t, plan, shape)
     # the same gather through NVLink peer memory (ogn_scatter_tile) must assemble the identical cube
     pg = ogd.PeerGather(lib_origin.default_context(), shape, dst=0, slots=2)
-    for slot in (0, 1):
-        pg.scatter(res['correl'], t, (ny, nx), slot=slot)
+    pg.scatter(res['correl'], t, (ny, nx), slot=0)            # slot 0: every rank copies its tile
+    pg.attach(slot=1)                                         # slot 1: the destination rank's tile is stored by K2
+    res_b = lib_origin.step05(cube_std, fsf, None, profs, msk, 3, 1e-8, True, tile=(t, (ny, nx)))
+    pg.scatter(res_b['correl'], t, (ny, nx), slot=1)
     pg.wait()
     peer_same = True
     if rank == 0:
