@@ -447,7 +447,8 @@ def main_gpu(args):
         k3_local_extrema=dict(ms=k3_ms, gbs=9.0 * vol_tile / (k3_ms * 1e-3) / 1e9, bound='hbm',
                               frac_of_measured_hbm=(9.0 * vol_tile / (k3_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None),
         other_ms={k: float(np.mean(v)) for k, v in stages.items()
-                  if k not in ('k1_fsf_correlate', 'k2_spectral_glr', 'k3_local_extrema')},
+                  if k not in ('k1_fsf_correlate', 'k2_spectral_glr', 'k3_local_extrema', 'step05_span')},
+        step05_span_ms=float(np.mean(stages.get('step05_span', [np.nan]))),
     )
     total_flops = (2.0 * PSF_SIZE ** 2 + 2.0 * sum_taps(profs)) * nz * ny * nx
     line = dict(

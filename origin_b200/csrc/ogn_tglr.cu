@@ -416,7 +416,7 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src, bool vali
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int ZB, int NW, bool PERVOXEL, bool CTAPS>
+template <int ZB, int NW, bool PERVOXEL, bool CTAPS, bool G2>
 // no minBlocksPerSM here: with it ptxas (12.9) stops using uniform registers for the taps
 __global__ void __launch_bounds__(NW * 32)
 spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_constant__ CUtensorMap den_map,
@@ -447,7 +447,8 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
     const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int x0 = blockIdx.x * 32, x = x0 + lane, y = blockIdx.y;   // window coordinates
     const int oy = y + oy_off, ox = x + ox_off;                       // coordinates in the product cubes
-    const bool own2 = g2.dst != nullptr && oy >= g2.y0 && oy < g2.y1 && ox >= g2.x0 && ox < g2.x1;
+    // G2: this rank owns the gathered cube and stores the voxels it owns there as well (multi-GPU)
+    const bool own2 = G2 && oy >= g2.y0 && oy < g2.y1 && ox >= g2.x0 && ox < g2.x1;
     const int nchunk = (nz + NW * ZB - 1) / (NW * ZB);
     const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
 
@@ -601,7 +602,7 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
                         const bool masked = (mbits >> i) & 1u;
                         const float c = masked ? 0.f : mx[i];
                         if (correl) correl[o] = c;
-                        if (own2) g2.dst[((size_t)z * g2.ny + oy + g2.dy) * g2.nx + ox + g2.dx] = c;
+                        if (G2 && own2) g2.dst[((size_t)z * g2.ny + oy + g2.dy) * g2.nx + ox + g2.dx] = c;
                         if (correl_min) correl_min[o] = mn[i];
                         if (profile) profile[o] = masked ? (uint8_t)0 : (uint8_t)arg[i];
                         cmax = fmaxf(cmax, c);
@@ -897,11 +898,14 @@ static int run_fsf_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setu
     return OGN_OK;
 }
 
-template <int ZB, int NW, bool PV, bool CT>
+template <int ZB, int NW, bool PV, bool CT, bool G2 = false>
 static int launch_spectral(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, ogn_window w,
                            const float *cube_fsf, const float *norm_fsf, int pitch, const uint8_t *mask,
                            float *correl, float *correl_min, uint8_t *profile, float *maxmap, float *minmap) {
-    auto kern = k2::spectral_glr_kernel<ZB, NW, PV, CT>;
+    if (!G2 && st.gather2.dst)   // second destination requested: the variant with the extra store
+        return launch_spectral<ZB, NW, PV, CT, true>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, mask, correl, correl_min,
+                                                     profile, maxmap, minmap);
+    auto kern = k2::spectral_glr_kernel<ZB, NW, PV, CT, G2>;
     const int wny = w.y1 - w.y0, wnx = w.x1 - w.x0;
     // window rows per chunk: the chunk itself, the longest profile, and the ring's read-ahead
     const int need_rows = NW * ZB + st.reach + 2 * k2::U;

@@ -144,7 +144,7 @@ __device__ __forceinline__ void fold_group(const float *__restrict__ wrow, const
     }
 }
 
-template <int G, int NW>
+template <int G, int NW, bool G2>
 __global__ void __launch_bounds__(NW * 32, (G <= 3 ? 5 : 3))
 folded_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_constant__ FoldDict dict,
                   int nz, int wny, int wnx,                    // window (= K1 output) dims
@@ -169,7 +169,8 @@ folded_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_cons
     const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int x0 = blockIdx.x * 32, x = x0 + lane, y = blockIdx.y;   // window coordinates
     const int oy = y + oy_off, ox = x + ox_off;                       // coordinates in the product cubes
-    const bool own2 = g2.dst != nullptr && oy >= g2.y0 && oy < g2.y1 && ox >= g2.x0 && ox < g2.x1;
+    // G2: this rank owns the gathered cube and stores the voxels it owns there as well (multi-GPU)
+    const bool own2 = G2 && oy >= g2.y0 && oy < g2.y1 && ox >= g2.x0 && ox < g2.x1;
     const int nchunk = (nz + cz - 1) / cz;
     const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
 
@@ -306,7 +307,7 @@ folded_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_cons
                         const bool masked = (mbits >> i) & 1u;
                         const float c = masked ? 0.f : mx[i];
                         if (correl) correl[o] = c;
-                        if (own2) g2.dst[((size_t)z * g2.ny + oy + g2.dy) * g2.nx + ox + g2.dx] = c;
+                        if (G2 && own2) g2.dst[((size_t)z * g2.ny + oy + g2.dy) * g2.nx + ox + g2.dx] = c;
                         if (correl_min) correl_min[o] = mn[i];
                         if (profile) profile[o] = masked ? (uint8_t)0 : (uint8_t)arg[i];
                         cmax = fmaxf(cmax, c);
@@ -396,12 +397,14 @@ int ogn_k2f_upload(ogn_ctx *ctx, ogn_uploader *up, const std::vector<float> &tab
     return up->add(sym, table.data(), table.size() * sizeof(float));
 }
 
-template <int G, int NW>
+template <int G, int NW, bool G2 = false>
 static int launch_folded(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, ogn_window w,
                          const float *cube_fsf, int pitch, const uint8_t *mask, float *correl, float *correl_min,
                          uint8_t *profile, float *maxmap, float *minmap) {
     using namespace k2f;
-    auto kern = folded_glr_kernel<G, NW>;
+    if (!G2 && st.gather2.dst)
+        return launch_folded<G, NW, true>(ctx, stream, st, w, cube_fsf, pitch, mask, correl, correl_min, profile, maxmap, minmap);
+    auto kern = folded_glr_kernel<G, NW, G2>;
     const FoldDict &d = *st.fold;
     const int wny = w.y1 - w.y0, wnx = w.x1 - w.x0;
     const size_t limit = 100 * 1024;
