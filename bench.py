@@ -38,6 +38,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PSF_SIZE = 25
+ASYNC_STEP = not os.environ.get('OGN_BENCH_SYNC_STEP')     # diagnostic switch: host-synchronous steps
 SHAPE = (3681, 320, 320)
 CPU_TILE = (64, 96)          # spatial sample of the workload for the CPU baseline
 
@@ -288,8 +289,11 @@ def main_gpu(args):
         t0 = time.perf_counter()
         if gather is not None and not os.environ.get('OGN_BENCH_NO_GATHER'):
             gather.attach(slot=i % 2)      # rank 0's own tile is stored by K2 itself
+        # sync=False: nothing of the step comes back to the host (the extremum list lengths stay on the device),
+        # so the host runs ahead and the GPU never idles between steps; the final synchronisation of the timed
+        # region waits for everything
         res = lib_origin.step05(cube, fsf, None, profs, mask, 3, 1e-8, True, out=out_sets[i % len(out_sets)], ctx=ctx,
-                                tile=(tile, (ny, nx)) if world > 1 else None)
+                                tile=(tile, (ny, nx)) if world > 1 else None, sync=not ASYNC_STEP)
         t0 = tick('step05', t0)
         ext = res['extrema']                                                      # owned voxels, global indices
         # step06 counting loop on the device lists; the counts stay on the device ...

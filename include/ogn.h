@@ -144,7 +144,10 @@ OGN_API int ogn_fsf_stage(ogn_ctx *ctx,
  * value (for the minima list: -b, as in the reference).  `capacity` is the
  * size of each list; counts[0], counts[1] always receive the true counts and
  * OGN_ERR_OVERFLOW is returned when a list did not fit.  Lists may be NULL
- * (counts only). */
+ * (counts only).  When `counts` is a DEVICE array and all products are device
+ * buffers the call does not synchronise and cannot report an overflow: the
+ * lists are then truncated at `capacity` and the caller compares counts with
+ * capacity once it reads them (same for ogn_step05 / ogn_step05_tile). */
 OGN_API int ogn_local_extrema(ogn_ctx *ctx,
                       const float *a, const float *b, const uint8_t *mask,
                       int nz, int ny, int nx, int sz, int sy, int sx,
@@ -246,6 +249,17 @@ OGN_API int ogn_purity_counts(ogn_ctx *ctx,
                       const uint8_t *segmask, int ny, int nx,
                       const double *thresholds, int nthresh,
                       int64_t *n1, int64_t *n0);
+
+/* Synchronisation-free variant for device-resident pipelines (multi-GPU steps): every pointer is a device
+ * pointer; the lists are the capacity-sized buffers of an ogn_step05 / ogn_step05_tile / ogn_local_extrema
+ * call whose `counts` output was a DEVICE array (such a call does not synchronise either), and
+ * list_counts is that array: the kernels read the true list lengths from it.  n1 / n0 can be handed to
+ * an NCCL allreduce without the host ever seeing them. */
+OGN_API int ogn_purity_counts_dev(ogn_ctx *ctx,
+                          const int64_t *max_index, const float *max_value,
+                          const int64_t *min_index, const float *min_value, int64_t capacity,
+                          const int64_t *list_counts, const uint8_t *segmask, int ny, int nx,
+                          const double *thresholds, int nthresh, int64_t *n1, int64_t *n0);
 
 /* ---- step07: thresholding ------------------------------------------------ */
 

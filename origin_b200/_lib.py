@@ -58,6 +58,8 @@ SIGNATURES = {
                                  c_int, c_int, c_void_p, c_void_p]),
     'ogn_purity_counts': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                   c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    'ogn_purity_counts_dev': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                      c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'ogn_threshold_extract': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_int64, c_void_p]),
     'ogn_dct_residual': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -604,10 +604,13 @@ __global__ void list_stats_kernel(const int64_t *__restrict__ index, const float
 
 // counts[t] += #{entries (background only when segmask) with value > thresholds[t]}
 __global__ void list_counts_kernel(const int64_t *__restrict__ index, const float *__restrict__ value, int64_t n,
+                                   const int64_t *__restrict__ n_dev,   // optional: true length (device), n = bound
                                    const uint8_t *__restrict__ segmask, int64_t img,
                                    const double *__restrict__ thresholds, int nthresh,
                                    unsigned long long *__restrict__ counts) {
     extern __shared__ unsigned int sm_counts[];
+    if (n_dev) n = min(n, *n_dev);
+    if ((int64_t)blockIdx.x * blockDim.x >= n) return;   // whole block past the end (uniform)
     for (int t = threadIdx.x; t < nthresh; t += blockDim.x) sm_counts[t] = 0;
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -881,6 +884,13 @@ int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t 
                            want_lists ? (int64_t *)d_maxi : nullptr, (float *)d_maxv, (int64_t *)d_mini, (float *)d_minv,
                            want_lists ? capacity : 0, d_counts, res_d, user_counts));
     OGN_HT("extrema enqueued");
+    // Asynchronous mode: the caller gave a DEVICE counts array and every list / dense product is a device
+    // buffer, so nothing has to come back to the host: no synchronisation, the call returns with the
+    // kernels still in flight (lists are truncated at `capacity`; the caller compares counts and capacity
+    // when it eventually reads them).
+    const bool dev_lists = !want_lists || (ogn_is_device_ptr(max_index) && ogn_is_device_ptr(max_value) &&
+                                           ogn_is_device_ptr(min_index) && ogn_is_device_ptr(min_value));
+    if (user_counts && dev_lists && (!dense_max || d_dmax == dense_max) && (!dense_min || d_dmin == dense_min)) return OGN_OK;
     OGN_CUDA(cudaStreamSynchronize(ctx->stream));
     OGN_HT("extrema counts back");
     const int64_t h_counts[2] = {res_h[0], res_h[1]};
@@ -996,13 +1006,13 @@ extern "C" int ogn_purity_counts(ogn_ctx *ctx, const int64_t *max_index, const f
     OGN_TRY(ogn_fill_words(ctx, ctx->stream, d_n0, 0u, (size_t)nthresh * 8));
     const size_t sm = (size_t)nthresh * sizeof(unsigned int);
     if (nmax > 0) {
-        list_counts_kernel<<<ogn_div_up(nmax, 256), 256, sm, ctx->stream>>>(L.maxi, L.maxv, nmax, nullptr, (int64_t)img,
+        list_counts_kernel<<<ogn_div_up(nmax, 256), 256, sm, ctx->stream>>>(L.maxi, L.maxv, nmax, nullptr, nullptr, (int64_t)img,
                                                                             (const double *)d_thr, nthresh,
                                                                             (unsigned long long *)d_n1);
         OGN_LAUNCH_CHECK("list_counts_kernel");
     }
     if (nmin > 0) {
-        list_counts_kernel<<<ogn_div_up(nmin, 256), 256, sm, ctx->stream>>>(L.mini, L.minv, nmin, L.seg, (int64_t)img,
+        list_counts_kernel<<<ogn_div_up(nmin, 256), 256, sm, ctx->stream>>>(L.mini, L.minv, nmin, nullptr, L.seg, (int64_t)img,
                                                                             (const double *)d_thr, nthresh,
                                                                             (unsigned long long *)d_n0);
         OGN_LAUNCH_CHECK("list_counts_kernel");
@@ -1010,6 +1020,41 @@ extern "C" int ogn_purity_counts(ogn_ctx *ctx, const int64_t *max_index, const f
     OGN_TRY(ogn_output_commit(ctx, n1, d_n1, (size_t)nthresh * 8));
     OGN_TRY(ogn_output_commit(ctx, n0, d_n0, (size_t)nthresh * 8));
     return ogn_finish_call(ctx);
+}
+
+// Device-only, synchronisation-free variant: the lists are the capacity-sized device buffers an
+// asynchronous ogn_step05* call filled, their true lengths are read on the device from list_counts
+// ({#maxima, #minima}, the `counts` output of that call).
+extern "C" int ogn_purity_counts_dev(ogn_ctx *ctx, const int64_t *max_index, const float *max_value,
+                                     const int64_t *min_index, const float *min_value, int64_t capacity,
+                                     const int64_t *list_counts, const uint8_t *segmask, int ny, int nx,
+                                     const double *thresholds, int nthresh, int64_t *n1, int64_t *n0) {
+    if (!ctx) return OGN_ERR_ARG;
+    if (capacity < 0 || ny <= 0 || nx <= 0 || nthresh < 1 || nthresh > 8192 || !thresholds || !n1 || !n0 || !list_counts)
+        return ogn_fail(ctx, OGN_ERR_ARG, "invalid arguments (nthresh must be in 1..8192)");
+    const void *ptrs[] = {max_index, max_value, min_index, min_value, list_counts, thresholds, n1, n0};
+    for (const void *p : ptrs)
+        if (!p || !ogn_is_device_ptr(p)) return ogn_fail(ctx, OGN_ERR_ARG, "ogn_purity_counts_dev takes device pointers only");
+    if (segmask && !ogn_is_device_ptr(segmask)) return ogn_fail(ctx, OGN_ERR_ARG, "ogn_purity_counts_dev takes device pointers only");
+    OGN_CUDA(cudaSetDevice(ctx->device));
+    if (n0 == n1 + nthresh) {   // one contiguous [2][nthresh] array: one fill
+        OGN_TRY(ogn_fill_words(ctx, ctx->stream, n1, 0u, (size_t)nthresh * 16));
+    } else {
+        OGN_TRY(ogn_fill_words(ctx, ctx->stream, n1, 0u, (size_t)nthresh * 8));
+        OGN_TRY(ogn_fill_words(ctx, ctx->stream, n0, 0u, (size_t)nthresh * 8));
+    }
+    if (capacity == 0) return OGN_OK;
+    const size_t sm = (size_t)nthresh * sizeof(unsigned int);
+    const int64_t img = (int64_t)ny * nx;
+    list_counts_kernel<<<ogn_div_up(capacity, 256), 256, sm, ctx->stream>>>(max_index, max_value, capacity, list_counts,
+                                                                            nullptr, img, thresholds, nthresh,
+                                                                            (unsigned long long *)n1);
+    OGN_LAUNCH_CHECK("list_counts_kernel");
+    list_counts_kernel<<<ogn_div_up(capacity, 256), 256, sm, ctx->stream>>>(min_index, min_value, capacity, list_counts + 1,
+                                                                            segmask, img, thresholds, nthresh,
+                                                                            (unsigned long long *)n0);
+    OGN_LAUNCH_CHECK("list_counts_kernel");
+    return OGN_OK;
 }
 
 extern "C" int ogn_threshold_extract(ogn_ctx *ctx, const int64_t *index, const float *value, int64_t n,

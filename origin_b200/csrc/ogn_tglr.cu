@@ -819,6 +819,11 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
     const double **fsf_tab = nullptr;
     OGN_TRY(ogn_scratch_t(ctx, "fsf_tab", (size_t)nf, &fsf_tab));
     OGN_TRY(up.add(fsf_tab, fsf_dev.data(), nf * sizeof(double *)));
+    // the mirror-symmetry flag K0 ORs into starts at 0 (or stays set when folding is switched off)
+    OGN_TRY(ogn_scratch_t(ctx, "fsf_asym", (size_t)1, &st->asym));
+    static const bool no_fold = getenv("OGN_K1_NOFOLD") != nullptr;
+    const int asym0 = no_fold ? -1 : 0;
+    OGN_TRY(up.add(st->asym, &asym0, sizeof(int)));
     OGN_TRY(up.flush(ctx->stream));   // the host tables were copied into the staging buffer: no sync needed
     OGN_HT("setup tables enqueued");
 
@@ -830,11 +835,8 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
         OGN_TRY(ogn_scratch_t(ctx, "w32sq", (size_t)nf * nz * P * WP, &st->w32sq));
     } else {
         OGN_TRY(ogn_scratch_t(ctx, "normcls", (size_t)st->ncy * st->ncx * st->nzp, &normcls));
-        OGN_TRY(ogn_fill_words(ctx, ctx->stream, normcls, 0u, (size_t)st->ncy * st->ncx * st->nzp * sizeof(double)));
+        // no clearing needed: K0 writes every (class, z < nz) entry and K0b never reads z >= nz
     }
-    OGN_TRY(ogn_scratch_t(ctx, "fsf_asym", (size_t)1, &st->asym));
-    static const bool no_fold = getenv("OGN_K1_NOFOLD") != nullptr;
-    OGN_TRY(ogn_fill_words(ctx, ctx->stream, st->asym, no_fold ? 0xffffffffu : 0u, sizeof(int)));
     {
         ogn_timer t_(ctx, "fsf_prep");
         dim3 grid(nz, nf);
@@ -981,14 +983,18 @@ int ogn_tglr_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &s
 #undef OGN_K2
 }
 
-int ogn_tglr_init_maps(ogn_ctx *ctx, cudaStream_t stream, float *d_maxmap, float *d_minmap, size_t img) {
-    if (d_maxmap) {
-        fill_f32_kernel<<<ogn_div_up(img, 256), 256, 0, stream>>>(d_maxmap, img, -INFINITY);
-        OGN_LAUNCH_CHECK("fill_f32_kernel");
+__global__ void init_maps_kernel(float *__restrict__ maxmap, float *__restrict__ minmap, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        if (maxmap) maxmap[i] = -INFINITY;
+        if (minmap) minmap[i] = INFINITY;
     }
-    if (d_minmap) {
-        fill_f32_kernel<<<ogn_div_up(img, 256), 256, 0, stream>>>(d_minmap, img, INFINITY);
-        OGN_LAUNCH_CHECK("fill_f32_kernel");
+}
+
+int ogn_tglr_init_maps(ogn_ctx *ctx, cudaStream_t stream, float *d_maxmap, float *d_minmap, size_t img) {
+    if (d_maxmap || d_minmap) {
+        init_maps_kernel<<<ogn_div_up(img, 256), 256, 0, stream>>>(d_maxmap, d_minmap, img);
+        OGN_LAUNCH_CHECK("init_maps_kernel");
     }
     return OGN_OK;
 }

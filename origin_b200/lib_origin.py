@@ -20,7 +20,7 @@ from . import _lib
 from ._lib import OGN_F32, OGN_F64, OgnError, default_context, ptr
 
 __all__ = ['DCTMAT', 'dct_residual', 'O2test', 'Correlation_GLR_test', 'compute_local_max',
-           'Compute_threshold_purity', 'prepare_profiles', 'tglr', 'local_extrema', 'LocalExtrema',
+           'Compute_threshold_purity', 'prepare_profiles', 'tglr', 'local_extrema', 'LocalExtrema', 'DeviceExtrema',
            'purity_counts', 'threshold_rows', 'preprocess', 'PurityTable', 'step05', 'fsf_stage']
 
 
@@ -294,7 +294,8 @@ def _tglr_args(cube, fsf, weights, profiles, mask, pcut, pmeansub):
 
 
 def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True, out=None, dense=False,
-           capacity=None, want=('correl', 'profile', 'correl_min', 'maxmap', 'minmap'), tile=None, ctx=None):
+           capacity=None, want=('correl', 'profile', 'correl_min', 'maxmap', 'minmap'), tile=None, ctx=None,
+           sync=True):
     """The array part of ``ComputeTGLR.run`` (reference steps.py:768-802) in one
     device pass: TGLR, masking, maxmap / minmap and the local extrema.
 
@@ -310,6 +311,10 @@ def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True,
     sub-cube, only the owned window (grown by the extremum radius) is computed,
     the products are sub-cube shaped, and ``extrema`` holds the owned voxels with
     linear indices of the whole ``(nz, gny, gnx)`` field.
+
+    ``sync=False`` (CUDA tensors in and out only): the call returns with the kernels in flight and
+    ``extrema`` is a :class:`DeviceExtrema` — the list lengths stay on the device until somebody reads
+    them, so a pipeline of steps never stalls the GPU on the host.
     """
     cube, fsfs, fsf_ptrs, w_ptrs, taps, offs, nprof, m = _tglr_args(cube, fsf, weights, profiles, mask, pcut, pmeansub)
     if np.isscalar(size):
@@ -335,6 +340,10 @@ def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True,
     if capacity is None:
         capacity = len(out['max_index']) if out.get('max_index') is not None else max(4096, vol // 40)
     counts = np.zeros(2, dtype=np.int64)
+    if not sync:
+        if not (_is_torch(cube) and cube.is_cuda) or dense:
+            raise ValueError('sync=False needs CUDA tensors and dense=False')
+        counts = _torch().zeros(2, dtype=_torch().int64, device=cube.device)
     tdesc, ext_shape = None, cube.shape
     if tile is not None:
         if dense:
@@ -367,6 +376,9 @@ def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True,
                 ptr(res.get('maxmap')), ptr(res.get('minmap')), ptr(lists['max_index']), ptr(lists['max_value']),
                 ptr(lists['min_index']), ptr(lists['min_value']), capacity, ptr(counts))
         rc = ctx.check(rc, allow_overflow=True)
+        if not sync:
+            res['extrema'] = DeviceExtrema(ext_shape, lists, counts, capacity)
+            return res
         if rc == 0:
             break
         capacity = int(counts.max())
@@ -444,6 +456,33 @@ class LocalExtrema:
     def coords(self, which='max'):
         idx = self._host(self.max_index if which == 'max' else self.min_index)
         return np.unravel_index(idx, self.shape)
+
+
+class DeviceExtrema(LocalExtrema):
+    """:class:`LocalExtrema` whose lists are still being written by the GPU: the capacity-sized device buffers
+    of an asynchronous :func:`step05` call plus the device array holding the two list lengths.  Nothing
+    here touches the host until ``counts`` / ``max_index`` / ... are read (that synchronises and checks
+    for overflow); :func:`purity_counts` consumes it without synchronising."""
+
+    def __init__(self, shape, bufs, counts_dev, capacity):
+        self.shape = tuple(int(s) for s in shape)
+        self._bufs, self.counts_dev, self.capacity = bufs, counts_dev, int(capacity)
+        self._counts = None
+
+    @property
+    def counts(self):
+        if self._counts is None:
+            n1, n0 = (int(v) for v in self.counts_dev.cpu())
+            if max(n1, n0) > self.capacity:
+                raise OverflowError('extremum lists need %d / %d entries, capacity was %d: call step05 again with '
+                                    'capacity >= %d' % (n1, n0, self.capacity, max(n1, n0)))
+            self._counts = (n1, n0)
+        return self._counts
+
+    max_index = property(lambda self: self._bufs['max_index'][:self.counts[0]])
+    max_value = property(lambda self: self._bufs['max_value'][:self.counts[0]])
+    min_index = property(lambda self: self._bufs['min_index'][:self.counts[1]])
+    min_value = property(lambda self: self._bufs['min_value'][:self.counts[1]])
 
 
 def local_extrema(correl, correl_min, mask, size=3, dense=False, capacity=None, ctx=None):
@@ -559,9 +598,23 @@ def purity_counts(ext, segmask, thresholds, ctx=None, out=None):
     tensor the counts are written to ``out`` (an int64 CUDA tensor of ``2 * len(thresholds)`` entries,
     ``n1`` then ``n0``; allocated when None) and the call returns without synchronising, so a
     multi-GPU caller can hand ``out`` straight to an NCCL allreduce."""
-    ctx = _ctx_for(ext.max_value, ctx)
     nz, ny, nx = ext.shape
     seg = _as_u8(segmask)
+    if isinstance(ext, DeviceExtrema) and ext._counts is None and _is_torch(thresholds) and thresholds.is_cuda:
+        # lists still in flight: device-only entry point, lengths read on the device
+        torch = _torch()
+        b = ext._bufs
+        ctx = _ctx_for(b['max_value'], ctx)
+        nt = thresholds.numel()
+        if out is None:
+            out = torch.empty(2 * nt, dtype=torch.int64, device=thresholds.device)
+        if seg is not None and not _is_torch(seg):
+            seg = torch.from_numpy(seg).to(thresholds.device)
+        ctx.check(ctx.lib.ogn_purity_counts_dev(ctx.handle, ptr(b['max_index']), ptr(b['max_value']), ptr(b['min_index']),
+                                                ptr(b['min_value']), ext.capacity, ext.counts_dev.data_ptr(), ptr(seg), ny, nx,
+                                                ptr(thresholds), nt, out.data_ptr(), out.data_ptr() + 8 * nt))
+        return out[:nt], out[nt:]
+    ctx = _ctx_for(ext.max_value, ctx)
     c1, c0 = ext.counts
     if _is_torch(thresholds) and thresholds.is_cuda:
         torch = _torch()

@@ -506,3 +506,35 @@ def test_scatter_tile_assembles_the_field(lo):
         ctx.check(ctx.lib.ogn_peer_join(ctx.handle))
         torch.cuda.synchronize()
         assert torch.equal(dst, full)
+
+
+def test_step05_async_matches_sync(lo):
+    """sync=False: no host synchronisation inside the call, list lengths stay on the device
+    (DeviceExtrema), the device-only purity counts read them there; everything must equal the
+    synchronous call."""
+    import torch
+    shape = (120, 48, 64)
+    fsf = synthetic.moffat_fsf(shape[0])
+    cube_h, _ = synthetic.faint_cube(shape, fsf, n_src=5, seed=51)
+    mask_h = synthetic.footprint_mask(shape, seed=51)
+    profs = dictionaries.dico_3fwhm()[0]
+    cube, mask = torch.from_numpy(cube_h).cuda(), torch.from_numpy(mask_h.view(np.uint8)).cuda()
+    ref = lo.step05(cube, fsf, None, profs, mask, 3, 1e-8, True)
+    got = lo.step05(cube, fsf, None, profs, mask, 3, 1e-8, True, sync=False)
+    ext = got['extrema']
+    assert isinstance(ext, lo.DeviceExtrema) and ext._counts is None
+    thr = torch.linspace(1.0, 6.0, 50, dtype=torch.float64, device='cuda')
+    n1, n0 = lo.purity_counts(ext, None, thr)                 # device-only entry point, still no sync
+    assert ext._counts is None
+    r1, r0 = lo.purity_counts(ref['extrema'], None, thr)
+    torch.cuda.synchronize()
+    assert torch.equal(n1, r1) and torch.equal(n0, r0) and int(r1[0]) > 0
+    assert ext.counts == ref['extrema'].counts
+    for k in ('max_index', 'max_value', 'min_index', 'min_value'):
+        assert torch.equal(getattr(ext, k), getattr(ref['extrema'], k)), k
+    for k in ('correl', 'correl_min', 'profile', 'maxmap', 'minmap'):
+        assert torch.equal(got[k], ref[k]), k
+    # a capacity that is too small is detected when the lengths are finally read
+    small = lo.step05(cube, fsf, None, profs, mask, 3, 1e-8, True, sync=False, capacity=16)
+    with pytest.raises(OverflowError):
+        small['extrema'].counts
