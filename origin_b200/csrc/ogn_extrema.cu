@@ -1,10 +1,11 @@
 // 3-D local extrema (compute_local_max, lib_origin.py:1220-1256), ordered compaction,
 // step06 purity counts (lib_origin.py:1424-1449) and step07 thresholding (steps.py:956-974).
 //
-//   K3  local_extrema_kernel   window max of a / window min of b, equality test, mask,
-//                              dense products, one ballot word per 32 voxels
-//   K3b scan + scatter         order-preserving compaction of the flag words into
-//                              (linear index, value) lists = np.where order
+//   K3  local_extrema3_tma_kernel  3x3x3: TMA-staged (NaN out-of-bounds fill), float4 lanes, one warp
+//                                  per image row, no block barrier; flag words = one bit per voxel
+//       local_extrema3_kernel      3x3x3 scalar fallback (nx % 4 != 0), local_extrema_kernel any odd window
+//   K3b flag_totals / flag_offsets / flag_scatter   order-preserving compaction of both flag arrays
+//                                  into (linear index, value) lists = np.where order, 3 launches
 //   K4  purity_stats / purity_counts kernels over the lists
 //   K6  threshold_select       order-preserving selection value > threshold
 #include <math.h>
@@ -179,133 +180,6 @@ local_extrema3_kernel(const float *__restrict__ a, const float *__restrict__ b, 
         m_cur = cur.m;
         cur = nxt;
         buf ^= 1;
-    }
-}
-
-// Barrier-free variant of the 3 x 3 x 3 pass: every warp owns a brick of 32 x BR_R spaxels and walks
-// BR_CZ planes on its own.  Lane = x; the BR_R + 2 rows of a plane live in registers, so the x-max is
-// two shuffles per row, the y-max and the z-max are register-to-register FMNMX3, and there is no
-// shared memory and no block barrier: latency is hidden by the ~40 independent loads per warp-plane.
-constexpr int BR_R = 8;
-constexpr int BR_CZ = 64;
-constexpr int BR_WARPS = 8;
-
-__global__ void __launch_bounds__(32 * BR_WARPS, 2)
-local_extrema3_brick_kernel(const float *__restrict__ a, const float *__restrict__ b,
-                            const uint8_t *__restrict__ mask, int nz, int ny, int nx, int oy0, int oy1, int ox0a,
-                            int ox0, int ox1, int nbrick_y, float *__restrict__ dense_max,
-                            float *__restrict__ dense_min, uint32_t *__restrict__ flag_max,
-                            uint32_t *__restrict__ flag_min, int nxw) {
-    const int lane = threadIdx.x & 31;
-    const int wid = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-    // brick id -> (x group, y brick, z chunk)
-    const long long brick = (long long)blockIdx.x * BR_WARPS + wid;
-    const int bx = (int)(brick % nxw);
-    const long long rest = brick / nxw;
-    const int by = (int)(rest % nbrick_y);
-    const int bz = (int)(rest / nbrick_y);
-    const int zc0 = bz * BR_CZ;
-    if (zc0 >= nz) return;
-    const int zc1 = min(nz, zc0 + BR_CZ);
-    const int x0 = ox0a + bx * 32, x = x0 + lane;
-    const int yb = oy0 + by * BR_R;              // first output row of the brick
-    const bool x_ok = x < nx;
-    const bool is_l = lane == 0, is_r = lane == 31;
-    const bool edge_lane = (is_l && x0 > 0) || (is_r && x0 + 32 < nx);
-    const int xe = is_l ? x0 - 1 : x0 + 32;
-    const bool out_col = x >= ox0 && x < ox1;
-    const size_t plane = (size_t)ny * nx;
-    const int ony = oy1 - oy0;
-
-    // per-row validity and offsets (rows yb-1 .. yb+BR_R)
-    uint32_t row_ok_bits = 0;
-#pragma unroll
-    for (int r = 0; r < BR_R + 2; ++r) {
-        const int y = yb - 1 + r;
-        if (y >= 0 && y < ny) row_ok_bits |= 1u << r;
-    }
-    const int yclamp0 = min(max(yb - 1, 0), ny - 1);
-    const float *pa = a + (size_t)yclamp0 * nx;      // row pointers are derived per use: pa + r*nx
-    const float *pb = b + (size_t)yclamp0 * nx;
-    const uint8_t *pm = mask ? mask + (size_t)yclamp0 * nx : nullptr;
-    const int rbase = yclamp0 - (yb - 1);            // rows below the array start are skipped via row_ok
-
-    float pa_prev[BR_R], pa_cur[BR_R], ca_cur[BR_R], pb_prev[BR_R], pb_cur[BR_R], cb_cur[BR_R];
-#pragma unroll
-    for (int r = 0; r < BR_R; ++r) {
-        pa_prev[r] = pa_cur[r] = -INFINITY; ca_cur[r] = 0.f;
-        pb_prev[r] = pb_cur[r] = INFINITY; cb_cur[r] = 0.f;
-    }
-    uint32_t m_cur = 0;
-
-#pragma unroll 1
-    for (int p = zc0 - 1; p <= zc1; ++p) {
-        const bool pok = p >= 0 && p < nz;  // warp-uniform
-        float ca[BR_R + 2], cb[BR_R + 2], ea[BR_R + 2], eb[BR_R + 2];
-        uint8_t mv[BR_R];
-        const size_t pbase = (size_t)(pok ? p : 0) * plane;
-        // phase 1: every load of the plane is issued before anything consumes one
-#pragma unroll
-        for (int r = 0; r < BR_R + 2; ++r) {
-            const bool rok = pok && ((row_ok_bits >> r) & 1u);
-            const size_t ro = pbase + (size_t)(r - rbase) * nx;   // only dereferenced when rok
-            ca[r] = ea[r] = -INFINITY;
-            cb[r] = eb[r] = INFINITY;
-            if (r >= 1 && r <= BR_R) mv[r - 1] = 0;
-            if (rok) {  // warp-uniform
-                if (x_ok) { ca[r] = __ldg(pa + ro + x); cb[r] = __ldg(pb + ro + x); }
-                if (edge_lane) { ea[r] = __ldg(pa + ro + xe); eb[r] = __ldg(pb + ro + xe); }
-                if (pm && r >= 1 && r <= BR_R && x_ok) mv[r - 1] = pm[ro + x];
-            }
-        }
-        // phase 2: 3-wide max / min along x with two shuffles per row
-        float rxa[BR_R + 2], rxb[BR_R + 2], va[BR_R], vb[BR_R];
-        uint32_t m_new = 0;
-#pragma unroll
-        for (int r = 0; r < BR_R + 2; ++r) {
-            float l = __shfl_up_sync(0xffffffffu, ca[r], 1), rr = __shfl_down_sync(0xffffffffu, ca[r], 1);
-            l = is_l ? ea[r] : l;
-            rr = is_r ? ea[r] : rr;
-            rxa[r] = fmaxf(ca[r], fmaxf(l, rr));
-            l = __shfl_up_sync(0xffffffffu, cb[r], 1);
-            rr = __shfl_down_sync(0xffffffffu, cb[r], 1);
-            l = is_l ? eb[r] : l;
-            rr = is_r ? eb[r] : rr;
-            rxb[r] = fminf(cb[r], fminf(l, rr));
-            if (r >= 1 && r <= BR_R) {
-                va[r - 1] = ca[r];
-                vb[r - 1] = cb[r];
-                if (mv[r - 1]) m_new |= 1u << (r - 1);
-            }
-        }
-        const int q = p - 1;
-        const bool emit = q >= zc0 && q < zc1;  // warp-uniform
-#pragma unroll
-        for (int r = 0; r < BR_R; ++r) {
-            const float m9a = fmaxf(rxa[r], fmaxf(rxa[r + 1], rxa[r + 2]));
-            const float m9b = fminf(rxb[r], fminf(rxb[r + 1], rxb[r + 2]));
-            const int y = yb + r;
-            if (emit && y < oy1) {
-                const bool free_voxel = !((m_cur >> r) & 1u);
-                const bool keep_a = out_col && free_voxel && ca_cur[r] == fmaxf(pa_prev[r], fmaxf(pa_cur[r], m9a));
-                const bool keep_b = out_col && free_voxel && cb_cur[r] == fminf(pb_prev[r], fminf(pb_cur[r], m9b));
-                if (out_col && (dense_max || dense_min)) {
-                    const size_t idx = (size_t)q * plane + (size_t)y * nx + x;
-                    if (dense_max) dense_max[idx] = keep_a ? ca_cur[r] : 0.f;
-                    if (dense_min) dense_min[idx] = keep_b ? -cb_cur[r] : 0.f;
-                }
-                const uint32_t wa = __ballot_sync(0xffffffffu, keep_a);
-                const uint32_t wb = __ballot_sync(0xffffffffu, keep_b);
-                if (is_l) {
-                    const size_t w = ((size_t)q * ony + (y - oy0)) * nxw + bx;
-                    flag_max[w] = wa;
-                    flag_min[w] = wb;
-                }
-            }
-            pa_prev[r] = pa_cur[r]; pa_cur[r] = m9a; ca_cur[r] = va[r];
-            pb_prev[r] = pb_cur[r]; pb_cur[r] = m9b; cb_cur[r] = vb[r];
-        }
-        m_cur = m_new;
     }
 }
 
@@ -812,15 +686,13 @@ int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t 
     OGN_TRY(ogn_scratch_t(ctx, "ext_flag_min", nwords, &flag_min));
 
     ogn_timer *t_k3 = new ogn_timer(ctx, "k3_local_extrema");
-    // the barrier-free brick kernel is kept for experiments (OGN_K3_BRICK=1); the shared-memory
-    // tile kernel is faster on B200 as measured (2.4 ms vs 3.4 ms at 3681x320x320)
-    static const bool use_brick_kernel = getenv("OGN_K3_BRICK") != nullptr;
+    // OGN_K3_SCALAR=1 forces the scalar shared-memory kernel (also used when nx % 4 != 0)
     static const bool no_v4_kernel = getenv("OGN_K3_SCALAR") != nullptr;
     const bool vec_ok = nx % 4 == 0 && ((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(db)) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(dm) & 3) == 0 &&
                         (!d_dmax || (reinterpret_cast<uintptr_t>(d_dmax) & 15) == 0) &&
                         (!d_dmin || (reinterpret_cast<uintptr_t>(d_dmin) & 15) == 0);
-    if (sz == 3 && sy == 3 && sx == 3 && vec_ok && !use_brick_kernel && !no_v4_kernel) {
+    if (sz == 3 && sy == 3 && sx == 3 && vec_ok && !no_v4_kernel) {
         CUtensorMap a_map, b_map;
         OGN_TRY(ogn_make_tile_map(ctx, &a_map, (const float *)da, nz, ny, nx, nx, E4_BX, E4_ROWS, 1, true));
         OGN_TRY(ogn_make_tile_map(ctx, &b_map, (const float *)db, nz, ny, nx, nx, E4_BX, E4_ROWS, 1, true));
@@ -834,15 +706,6 @@ int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t 
                                                                         flag_min, nxw);
         delete t_k3;
         OGN_LAUNCH_CHECK("local_extrema3_tma_kernel");
-    } else if (sz == 3 && sy == 3 && sx == 3 && use_brick_kernel) {
-        const int nby = ogn_div_up(ony, BR_R), nbz = ogn_div_up(nz, BR_CZ);
-        const long long nbrick = (long long)nxw * nby * nbz;
-        const unsigned blocks = (unsigned)((nbrick + BR_WARPS - 1) / BR_WARPS);
-        local_extrema3_brick_kernel<<<blocks, 32 * BR_WARPS, 0, ctx->stream>>>(
-            (const float *)da, (const float *)db, (const uint8_t *)dm, nz, ny, nx, owned.y0, owned.y1, ox0a, owned.x0,
-            owned.x1, nby, (float *)d_dmax, (float *)d_dmin, flag_max, flag_min, nxw);
-        delete t_k3;
-        OGN_LAUNCH_CHECK("local_extrema3_brick_kernel");
     } else if (sz == 3 && sy == 3 && sx == 3) {
         dim3 block(32, EX_TY + 2);
         dim3 grid(nxw, ogn_div_up(ony, EX_TY), ogn_div_up(nz, EX_CZ));

@@ -621,11 +621,6 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
 // ---------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------
-__global__ void fill_f32_kernel(float *p, size_t n, float v) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-
 // dst[z][y][dpitch] = src[z][y][nx] * (w ? w[y][x] : 1), zero in the pad columns
 __global__ void pitch_copy_kernel(const float *__restrict__ src, const double *__restrict__ w,
                                   float *__restrict__ dst, int nz, int ny, int nx, int dpitch, int src_z_invariant) {
