@@ -538,3 +538,33 @@ def test_step05_async_matches_sync(lo):
     small = lo.step05(cube, fsf, None, profs, mask, 3, 1e-8, True, sync=False, capacity=16)
     with pytest.raises(OverflowError):
         small['extrema'].counts
+
+
+@pytest.mark.parametrize('case', ['seven_sorted', 'twelve_sorted_short_cube', 'unsorted_falls_back', 'asymmetric_falls_back'])
+def test_tglr_folded_spectral_kernel_cases(lo, case):
+    """K2f (folded spectral kernel) takes symmetric, width-sorted dictionaries with more than 3 profiles:
+    partially filled groups, two groups, a cube shorter than the widest profile's reach; dictionaries it
+    must refuse (widths not sorted: the argmax is first-wins in dictionary order; an asymmetric profile)
+    go through K2.  All against the float64 oracle."""
+    full = dictionaries.dico_fwhm_2_12()[0]
+    rng = np.random.default_rng(61)
+    shape = (140, 20, 45)
+    if case == 'seven_sorted':
+        profs = [full[i] for i in (0, 3, 5, 8, 12, 15, 19)]
+    elif case == 'twelve_sorted_short_cube':
+        profs, shape = list(full[4:16]), (40, 18, 37)
+    elif case == 'unsorted_falls_back':
+        profs = [full[i] for i in (10, 2, 19, 7, 14)]
+    else:
+        profs = [np.array(p, dtype=np.float64) for p in full[:6]]
+        profs[3] = profs[3] * (1.0 + 0.2 * np.linspace(-1, 1, len(profs[3])))     # skewed line
+    fsf = synthetic.moffat_fsf(shape[0])
+    cube, _ = synthetic.faint_cube(shape, fsf, n_src=4, seed=62)
+    mask = rng.random(shape) < 0.02
+    ref = orc.tglr_step(cube, fsf, None, profs, mask, 3, 1, 1e-8, True)
+    out = lo.tglr(cube, fsf, None, profs, mask=mask, pcut=1e-8)
+    assert_close(out['correl'], ref['cube_correl'], case + ' correl')
+    assert_close(out['correl_min'], ref['cube_correl_min'], case + ' correl_min')
+    tk = oracle_tk(cube, fsf, None, profs, 1e-8, True)
+    check_profile(np.where(mask, 0, out['profile']), np.where(mask, 0, ref['cube_profile']), tk, case + ' profile',
+                  max_frac=3e-3)
