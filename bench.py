@@ -7,21 +7,28 @@ purity counts) in Gvoxel.profiles/s on a synthetic MUSE-shaped cube.
 
 Prints ONE JSON line (see DESIGN.md "Measurement" for every field).
 
-* ``value``  device-resident: inputs already in HBM, CUDA events around K steps.
+* ``value``  device-resident: inputs already in HBM, CUDA events around K steps.  Steps are
+             asynchronous (``step05(sync=False)``): nothing of a step returns to the host, the
+             final synchronisation of the timed region waits for all of them.
 * ``e2e``    the same step through the public host API (``lib_origin.step05`` ->
              ``ogn_step05``) with pinned HOST buffers: every step copies the cube and
              mask host->device and every product device->host inside the timed region.
 * ``roofline`` dominant kernel (K1, per-lambda FSF correlation): algorithmic FLOPs /
              CUDA-event duration on the launching stream, against the FP32 FFMA peak
-             measured on this device by ``tools/fma_peak`` in the same run.
+             measured on this device by ``tools/fma_peak`` in the same run; ``executed`` gives
+             the FP32 issue slots the row-folded kernel really uses, ``traffic`` its DRAM bytes
+             per launch from the committed ncu capture (``profiles/ncu_summary.json``).
 * ``cpu_baseline`` the float64 oracle port of the reference algorithm
              (``oracle/origin_oracle.py``) timed on the host cores on a bounded spatial
              tile of the same workload (rank 0, N=1 only).
 * ``--impl reference``: that CPU port alone, in the same JSON shape.
 
-N > 1 (launched by torchrun): the cube is split into spatial tiles with (P//2 + 1)-pixel
+N > 1 (launched by torchrun): the cube is split into spatial tiles with >= (P//2 + 1)-pixel
 halos, one per rank (strong scaling of the fixed cube); the step adds the NCCL allreduce
-of the per-threshold purity counts and the gather of the owned correl tiles to rank 0.
+of the per-threshold purity counts (device-resident, in place) and the gather of the owned
+correl tiles into rank 0's cube over NVLink peer memory (``ogn_scatter_tile`` on a side
+stream; rank 0's own tile is stored by its spectral kernel).  Environment switches
+``OGN_BENCH_NO_GATHER`` / ``OGN_BENCH_SKIP_LOCAL`` / ``OGN_BENCH_SYNC_STEP`` are diagnostics.
 """
 
 import argparse
