@@ -20,7 +20,11 @@
  *    the message.  There is no CPU fallback: without a usable CUDA device
  *    ogn_create fails.
  *  - One context per (process, device, stream).  Calls on one context must be
- *    serialised by the caller; all work is enqueued on the context's stream and
+ *    serialised by the caller, and so must TGLR calls (ogn_tglr, ogn_step05*)
+ *    of different contexts on the same device: the profile taps of the call in
+ *    flight live in __constant__ memory, which the device's contexts share
+ *    (multi-GPU runs use one process per GPU and are not affected).  All work
+ *    is enqueued on the context's stream and
  *    every entry point that returns data to host memory synchronises that
  *    stream before returning.  Calls whose outputs are all device pointers
  *    return without synchronising.
