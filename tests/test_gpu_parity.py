@@ -409,8 +409,9 @@ def test_tglr_tile_consistency_and_spot_oracle(lo):
 # tiled and streamed execution
 # --------------------------------------------------------------------------
 
-@pytest.mark.parametrize('shape,ntiles', [((300, 100, 150), 4), ((200, 120, 176), 2), ((150, 96, 320), 8)])
-def test_step05_tiles_reproduce_the_full_cube(lo, shape, ntiles):
+@pytest.mark.parametrize('shape,ntiles,dico', [((300, 100, 150), 4, '3FWHM'), ((200, 120, 176), 2, '3FWHM'),
+                                               ((150, 96, 320), 8, '3FWHM'), ((120, 100, 150), 4, '2_12')])
+def test_step05_tiles_reproduce_the_full_cube(lo, shape, ntiles, dico):
     """The multi-GPU decomposition run serially on one GPU: tiles with >= 13-pixel halos give
     bit-identical products on their owned windows and the same global extremum lists.  The second case
     splits columns so that a tile's window starts at a column that is not a multiple of 4 (the library
@@ -420,7 +421,7 @@ def test_step05_tiles_reproduce_the_full_cube(lo, shape, ntiles):
     fsf = synthetic.moffat_fsf(nz)
     cube, _ = synthetic.faint_cube(shape, fsf, n_src=8, seed=31)
     mask = synthetic.footprint_mask(shape, seed=31)
-    profs = dictionaries.dico_3fwhm()[0]
+    profs = dictionaries.dico_3fwhm()[0] if dico == '3FWHM' else dictionaries.dico_fwhm_2_12()[0]   # K2 / K2f
     full = lo.step05(cube, fsf, None, profs, mask, 3, 1e-8, True)
     got_max, got_min, val_max = [], [], []
     for t in tiles.plan_tiles(ny, nx, ntiles, 13):
