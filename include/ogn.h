@@ -294,11 +294,13 @@ OGN_API int ogn_dct_residual(ogn_ctx *ctx,
  * phases so that the per-wavelength mean (np.nanmean over all spaxels,
  * steps.py:442) can be reduced across ranks in between.
  *
- * begin : continuum fit, data = raw - cont kept on the device, and the
- *         per-wavelength partial sums lambda_sum[nz] / lambda_cnt[nz] (float64,
- *         host or device) of the unmasked data of THIS cube (tile).  `owned`
- *         is NULL or {y0, y1, x0, x1}: only spaxels of that window of the
- *         given cube enter the sums (a tile's halo belongs to its neighbours).
+ * begin : continuum fit (the order+1 coefficients per spaxel stay on the device;
+ *         the continuum itself is re-synthesised where needed, never stored),
+ *         and the per-wavelength partial sums lambda_sum[nz] / lambda_cnt[nz]
+ *         (float64, host or device) of the unmasked data = raw - cont of THIS
+ *         cube (tile).  `owned` is NULL or {y0, y1, x0, x1}: only spaxels of that
+ *         window of the given cube enter the sums (a tile's halo belongs to its
+ *         neighbours).  Device inputs must stay valid until ogn_preprocess_finish.
  * finish: given the global per-wavelength mean, standardise and reduce:
  *         cube_std [nz][ny][nx] f32, cont_dct [nz][ny][nx] f32 (= cont/sqrt(var)),
  *         ima_std, ima_dct, cont_sumsq (= sum_z cont_dct^2), o2map

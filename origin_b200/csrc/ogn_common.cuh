@@ -22,10 +22,12 @@ struct ogn_buf {
 struct ogn_prep_state {
     bool active = false;
     int nz = 0, ny = 0, nx = 0, in_dtype = 0;
+    const void *raw = nullptr;      // device
     const void *var = nullptr;      // device
     const uint8_t *mask = nullptr;  // device
-    float *data = nullptr;          // device: raw - cont (f32)
-    double *cont = nullptr;         // device: continuum (f64)
+    const double *coef = nullptr;   // device: DCT coefficients [M][S]; the continuum is re-synthesised, never stored
+    const double *d0 = nullptr;     // device: DCTMAT [nz][M]
+    int M = 0;
 };
 
 struct ogn_timing_entry {

@@ -3,17 +3,26 @@
 //
 // Everything that feeds the subtraction raw - cont is FP64: the continuum can be
 // 10^3 times the noise, so an FP32 fit would leave residuals above the 1e-5
-// parity bound.  B200 has a full-rate FP64 pipe, and the whole
-// fit is ~100 DFMA per voxel.
+// parity bound.
 //
-//   K5a dct_fit_kernel    one thread per spaxel walks lambda once: weighted Gram
-//                         matrix D^T W D (upper triangle in registers), D^T W s
-//                         and D^T s, "any masked voxel" flag; then an in-register
-//                         Cholesky solve -> order+1 coefficients per spaxel
+// Parallelisation: a thread owns one spaxel (threads of a warp = consecutive
+// spaxels: coalesced) and ONE OF DCT_NSEG WAVELENGTH SEGMENTS (blockIdx.y), so a
+// 320x320 field gives 1.6 M threads instead of 102 400, and the loads of the
+// next wavelengths are requested ahead of the arithmetic.
+//
+//   K5a dct_accum_kernel  per (spaxel, segment): the sums the weighted normal
+//                         equations need.  With D0[z][i] = s_i cos(i theta_z) the Gram
+//                         matrix D^T W D is G_ij = s_i s_j (C_|i-j| + C_i+j) / 2 with
+//                         C_m = sum_z w_z cos(m theta_z): 2M-1 = 21 sums instead of 66,
+//                         plus R_i = sum w v cos(i theta), B_i = sum v cos(i theta) and
+//                         the "any masked voxel" flag
+//       dct_solve_kernel  per spaxel: adds the segments in fixed order, builds G,
+//                         Cholesky solve in registers -> order+1 coefficients
+//       dct_fit_generic_kernel  any order (one thread per spaxel, Gram matrix in memory)
 //   K5b dct_synth_kernel  cont = D0 coef; optionally data = raw - cont (f32) and
 //                         per-wavelength partial sums / counts of unmasked data
-//   K5c standardise_kernel (data - mean)/sqrt(var), cont/sqrt(var) and the four
-//                         per-spaxel reductions
+//   K5c standardise_kernel (data - mean)/sqrt(var), cont/sqrt(var) and per-segment
+//                         partial sums of the four per-spaxel reductions, reduce_maps_kernel
 #include <math.h>
 
 #include <vector>
@@ -23,52 +32,105 @@
 template <typename T>
 __device__ __forceinline__ double ld_as_f64(const T *p, size_t i) { return (double)p[i]; }
 
-// coef layout: [M][S] (spaxel fastest) so that warps read/write it coalesced.
+constexpr int DCT_NSEG = 16;   // wavelength segments per spaxel
+
+// part[seg][q][S], q = 0 .. 4M-2: C_0..C_{2M-2}, R_0..R_{M-1}, B_0..B_{M-1}; anym[seg][S]
 template <int M, typename T>
 __global__ void __launch_bounds__(128)
-dct_fit_kernel(const T *__restrict__ raw, const T *__restrict__ var, const uint8_t *__restrict__ mask,
-               const double *__restrict__ d0,  // [nz][M]
-               int nz, size_t S, int approx, double *__restrict__ coef) {
+dct_accum_kernel(const T *__restrict__ raw, const T *__restrict__ var, const uint8_t *__restrict__ mask,
+                 const double *__restrict__ ctab,  // [nz][2M-1]: cos(m theta_z)
+                 int nz, size_t S, int approx, int zseg, double *__restrict__ part, uint8_t *__restrict__ anym) {
+    constexpr int NC = 2 * M - 1, NQ = NC + 2 * M;
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    constexpr int NG = M * (M + 1) / 2;
-    double G[NG], bw[M], b0[M];
+    const int z0 = blockIdx.y * zseg, z1 = min(nz, z0 + zseg);
+    double C[NC], R[M], B[M];
 #pragma unroll
-    for (int i = 0; i < NG; ++i) G[i] = 0.0;
+    for (int i = 0; i < NC; ++i) C[i] = 0.0;
 #pragma unroll
-    for (int i = 0; i < M; ++i) { bw[i] = 0.0; b0[i] = 0.0; }
+    for (int i = 0; i < M; ++i) { R[i] = 0.0; B[i] = 0.0; }
     bool any_masked = false;
-    for (int z = 0; z < nz; ++z) {
-        const size_t o = (size_t)z * S + s;
-        const double v = ld_as_f64(raw, o);
-        double d[M];
+    // software pipeline: the samples of the next wavelength are in flight during the arithmetic
+    T nv = T(0), nw = T(1);
+    uint8_t nm = 0;
+    if (z0 < z1) {
+        const size_t o = (size_t)z0 * S + s;
+        nv = raw[o];
+        if (!approx) { nw = var[o]; nm = mask[o]; }
+    }
+    for (int z = z0; z < z1; ++z) {
+        const double v = (double)nv, vr = (double)nw;
+        any_masked |= nm != 0;
+        if (z + 1 < z1) {
+            const size_t o = (size_t)(z + 1) * S + s;
+            nv = raw[o];
+            if (!approx) { nw = var[o]; nm = mask[o]; }
+        }
+        const double *t = ctab + (size_t)z * NC;
+        if (approx) {
 #pragma unroll
-        for (int i = 0; i < M; ++i) d[i] = __ldg(d0 + (size_t)z * M + i);
+            for (int i = 0; i < M; ++i) B[i] = fma(__ldg(t + i), v, B[i]);
+        } else {
+            const double w = 1.0 / vr, vw = v * w;
 #pragma unroll
-        for (int i = 0; i < M; ++i) b0[i] = fma(d[i], v, b0[i]);
-        if (!approx) {
-            const double w = 1.0 / ld_as_f64(var, o);
-            any_masked |= mask[o] != 0;
-            const double vw = v * w;
-            int g = 0;
-#pragma unroll
-            for (int i = 0; i < M; ++i) {
-                const double dw = d[i] * w;
-                bw[i] = fma(d[i], vw, bw[i]);
-#pragma unroll
-                for (int j = i; j < M; ++j) { G[g] = fma(dw, d[j], G[g]); ++g; }
+            for (int m = 0; m < NC; ++m) {
+                const double c = __ldg(t + m);
+                C[m] = fma(c, w, C[m]);
+                if (m < M) {
+                    R[m] = fma(c, vw, R[m]);
+                    B[m] = fma(c, v, B[m]);
+                }
             }
         }
     }
+    double *dst = part + (size_t)blockIdx.y * NQ * S + s;
+#pragma unroll
+    for (int m = 0; m < NC; ++m) dst[(size_t)m * S] = C[m];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        dst[(size_t)(NC + i) * S] = R[i];
+        dst[(size_t)(NC + M + i) * S] = B[i];
+    }
+    anym[(size_t)blockIdx.y * S + s] = any_masked ? 1 : 0;
+}
+
+// coef layout: [M][S] (spaxel fastest) so that warps read/write it coalesced.
+template <int M>
+__global__ void __launch_bounds__(128)
+dct_solve_kernel(const double *__restrict__ part, const uint8_t *__restrict__ anym, int nseg, size_t S, int nz,
+                 int approx, double *__restrict__ coef) {
+    constexpr int NC = 2 * M - 1, NQ = NC + 2 * M, NG = M * (M + 1) / 2;
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double Q[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) Q[q] = 0.0;
+    bool any_masked = false;
+    for (int seg = 0; seg < nseg; ++seg) {   // fixed order: deterministic sums
+        const double *src = part + (size_t)seg * NQ * S + s;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) Q[q] += src[(size_t)q * S];
+        any_masked |= anym[(size_t)seg * S + s] != 0;
+    }
+    // DCTMAT scales (lib_origin.py:143-145): s_0 = sqrt(1/nz), s_i = sqrt(2/nz)
+    const double s0 = sqrt(1.0 / nz), s1 = sqrt(2.0 / nz);
     double c[M];
     if (approx || any_masked) {
         // unweighted projection, D0 has orthonormal columns (lib_origin.py:192, :237)
 #pragma unroll
-        for (int i = 0; i < M; ++i) c[i] = b0[i];
+        for (int i = 0; i < M; ++i) c[i] = (i ? s1 : s0) * Q[NC + M + i];
     } else {
+        double G[NG], bw[M];
+        auto at = [](int i, int j) { return i * M - i * (i - 1) / 2 + (j - i); };  // i <= j
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            bw[i] = (i ? s1 : s0) * Q[NC + i];
+#pragma unroll
+            for (int j = i; j < M; ++j)
+                G[at(i, j)] = 0.5 * (i ? s1 : s0) * (j ? s1 : s0) * (Q[j - i] + Q[i + j]);
+        }
         // Cholesky G = L L^T on the packed upper triangle, then two triangular solves
         // (the reference inverts G, lib_origin.py:233-235; same solution to round-off)
-        auto at = [](int i, int j) { return i * M - i * (i - 1) / 2 + (j - i); };  // i <= j
 #pragma unroll
         for (int i = 0; i < M; ++i) {
 #pragma unroll
@@ -149,66 +211,130 @@ __global__ void dct_fit_generic_kernel(const T *__restrict__ raw, const T *__res
     for (int i = 0; i < M; ++i) coef[(size_t)i * S + s] = c[i];
 }
 
-// cont[z][s] = sum_i d0[z][i] coef[i][s].  One thread per spaxel, walking lambda.
+// cont[z][s] = sum_i d0[z][i] coef[i][s].  One thread per (spaxel, wavelength segment = blockIdx.y).
 //   cont_out (f64 or f32, may be NULL), data_out = raw - cont (f32, NaN->excluded by mask),
 //   lambda_sum / lambda_cnt: per-wavelength sums over the unmasked voxels of this launch.
-template <typename T, typename TO>
+//   MT > 0: compile-time order + 1 (coefficients in registers), MT = 0: any order
+template <typename T, typename TO, int MT>
 __global__ void __launch_bounds__(128)
-dct_synth_kernel(const T *__restrict__ raw, const uint8_t *__restrict__ mask, const double *__restrict__ d0, int M,
-                 int nz, size_t S, const double *__restrict__ coef, TO *__restrict__ cont_out,
+dct_synth_kernel(const T *__restrict__ raw, const uint8_t *__restrict__ mask, const double *__restrict__ d0, int Mrt,
+                 int nz, size_t S, int zseg, const double *__restrict__ coef, TO *__restrict__ cont_out,
                  double *__restrict__ cont64, float *__restrict__ data_out, double *__restrict__ lambda_sum,
                  double *__restrict__ lambda_cnt, int nx, int wy0, int wy1, int wx0, int wx1) {
+    extern __shared__ double seg_acc[];   // [2][zseg] when lambda_sum is requested
+    double *seg_sum = seg_acc, *seg_cnt = seg_acc + zseg;
+    const int M = MT > 0 ? MT : Mrt;
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = s < S;
+    const int z0 = blockIdx.y * zseg, z1 = min(nz, z0 + zseg);
+    if (lambda_sum) {
+        for (int i = threadIdx.x; i < 2 * zseg; i += blockDim.x) seg_acc[i] = 0.0;
+        __syncthreads();
+    }
     // only spaxels inside the owned window contribute to the per-wavelength sums (multi-GPU tiles)
     const int sy = (int)(s / nx), sx = (int)(s - (size_t)sy * nx);
     const bool counted = live && sy >= wy0 && sy < wy1 && sx >= wx0 && sx < wx1;
-    double c[DCT_MAXM];
-    for (int i = 0; i < M; ++i) c[i] = live ? coef[(size_t)i * S + s] : 0.0;
-    for (int z = 0; z < nz; ++z) {
+    double c[MT > 0 ? MT : DCT_MAXM];
+#pragma unroll
+    for (int i = 0; i < (MT > 0 ? MT : DCT_MAXM); ++i) c[i] = (live && i < M) ? coef[(size_t)i * S + s] : 0.0;
+    T nr = T(0);
+    uint8_t nm = 0;
+    const bool need_raw = data_out != nullptr || lambda_sum != nullptr;
+    if (live && need_raw && z0 < z1) {
+        nr = raw[(size_t)z0 * S + s];
+        if (counted) nm = mask[(size_t)z0 * S + s];
+    }
+    for (int z = z0; z < z1; ++z) {
         const double *d = d0 + (size_t)z * M;
+        const double rv = (double)nr;
+        const bool masked = nm != 0;
+        if (live && need_raw && z + 1 < z1) {
+            nr = raw[(size_t)(z + 1) * S + s];
+            if (counted) nm = mask[(size_t)(z + 1) * S + s];
+        }
         double cont = 0.0;
-        for (int i = 0; i < M; ++i) cont = fma(d[i], c[i], cont);
+        if (MT > 0) {
+#pragma unroll
+            for (int i = 0; i < MT; ++i) cont = fma(__ldg(d + i), c[i], cont);
+        } else {
+            for (int i = 0; i < M; ++i) cont = fma(d[i], c[i], cont);
+        }
         double v = 0.0, n = 0.0;
         if (live) {
             const size_t o = (size_t)z * S + s;
             if (cont_out) cont_out[o] = (TO)cont;
             if (cont64) cont64[o] = cont;
-            if (data_out) {
-                const double r = ld_as_f64(raw, o) - cont;
-                data_out[o] = (float)r;
-                if (counted && !mask[o]) { v = r; n = 1.0; }
+            if (need_raw) {
+                const double r = rv - cont;
+                if (data_out) data_out[o] = (float)r;
+                if (counted && !masked) { v = r; n = 1.0; }
             }
         }
         if (lambda_sum) {
-            for (int o = 16; o; o >>= 1) {
-                v += __shfl_xor_sync(0xffffffffu, v, o);
-                n += __shfl_xor_sync(0xffffffffu, n, o);
-            }
-            if ((threadIdx.x & 31) == 0 && n > 0.0) {
-                atomicAdd(lambda_sum + z, v);
-                atomicAdd(lambda_cnt + z, n);
+            // warp: shuffle sum of the data, ballot count; block: shared-memory accumulators of its
+            // wavelength segment; one global atomic per wavelength and block at the end
+            const unsigned cnt = __popc(__ballot_sync(0xffffffffu, n > 0.0));
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0 && cnt) {
+                atomicAdd(&seg_sum[z - z0], v);
+                atomicAdd(&seg_cnt[z - z0], (double)cnt);
             }
         }
     }
+    if (lambda_sum) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < z1 - z0; i += blockDim.x)
+            if (seg_cnt[i] > 0.0) {
+                atomicAdd(lambda_sum + z0 + i, seg_sum[i]);
+                atomicAdd(lambda_cnt + z0 + i, seg_cnt[i]);
+            }
+    }
 }
 
-// steps.py:439-450, :463-465, :472, :480 for one spaxel per thread.
-template <typename T>
+// steps.py:439-450, :463-465, :472, :480 for one (spaxel, wavelength segment) per thread.  The continuum is
+// re-synthesised from the spaxel's coefficients (order + 1 DFMAs per voxel) instead of being stored as a
+// float64 cube between the two phases; the four per-spaxel reductions are written as per-segment
+// partial sums part4[seg][4][S].
+template <typename T, int MT>
 __global__ void __launch_bounds__(128)
-standardise_kernel(const float *__restrict__ data, const double *__restrict__ cont, const T *__restrict__ var,
-                   const uint8_t *__restrict__ mask, const double *__restrict__ mean, int nz, size_t S,
-                   float *__restrict__ cube_std, float *__restrict__ cont_dct, double *__restrict__ ima_std,
-                   double *__restrict__ ima_dct, double *__restrict__ cont_sumsq, double *__restrict__ o2map) {
+standardise_kernel(const T *__restrict__ raw, const T *__restrict__ var, const uint8_t *__restrict__ mask,
+                   const double *__restrict__ d0, int Mrt, const double *__restrict__ coef,
+                   const double *__restrict__ mean, int nz, size_t S, int zseg,
+                   float *__restrict__ cube_std, float *__restrict__ cont_dct, double *__restrict__ part4) {
+    const int M = MT > 0 ? MT : Mrt;
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
+    const int z0 = blockIdx.y * zseg, z1 = min(nz, z0 + zseg);
+    double c[MT > 0 ? MT : DCT_MAXM];
+#pragma unroll
+    for (int i = 0; i < (MT > 0 ? MT : DCT_MAXM); ++i) c[i] = i < M ? coef[(size_t)i * S + s] : 0.0;
     double a_std = 0, a_dct = 0, a_c2 = 0, a_o2 = 0;
-    for (int z = 0; z < nz; ++z) {
+    T nr = T(0), nv = T(1);
+    uint8_t nm = 0;
+    if (z0 < z1) {
+        const size_t o = (size_t)z0 * S + s;
+        nr = raw[o]; nv = var[o]; nm = mask[o];
+    }
+    for (int z = z0; z < z1; ++z) {
         const size_t o = (size_t)z * S + s;
-        const double sd = sqrt(ld_as_f64(var, o));
+        const double rv = (double)nr, vr = (double)nv;
+        const bool masked = nm != 0;
+        if (z + 1 < z1) {
+            const size_t on = o + S;
+            nr = raw[on]; nv = var[on]; nm = mask[on];
+        }
+        const double *d = d0 + (size_t)z * M;
+        double cont = 0.0;
+        if (MT > 0) {
+#pragma unroll
+            for (int i = 0; i < MT; ++i) cont = fma(__ldg(d + i), c[i], cont);
+        } else {
+            for (int i = 0; i < M; ++i) cont = fma(d[i], c[i], cont);
+        }
+        const double sd = sqrt(vr);
         double v = 0.0;
-        if (!mask[o]) v = ((double)data[o] - mean[z]) / sd;
-        const float cd = (float)(cont[o] / sd);
+        if (!masked) v = ((rv - cont) - mean[z]) / sd;
+        const float cd = (float)(cont / sd);
         if (cube_std) cube_std[o] = (float)v;
         if (cont_dct) cont_dct[o] = cd;
         a_std += v;
@@ -216,10 +342,27 @@ standardise_kernel(const float *__restrict__ data, const double *__restrict__ co
         a_dct += (double)cd;
         a_c2 += (double)cd * (double)cd;
     }
-    if (ima_std) ima_std[s] = a_std / nz;
-    if (o2map) o2map[s] = a_o2 / nz;
-    if (ima_dct) ima_dct[s] = a_dct / nz;
-    if (cont_sumsq) cont_sumsq[s] = a_c2;
+    double *dst = part4 + (size_t)blockIdx.y * 4 * S + s;
+    dst[0] = a_std;
+    dst[S] = a_o2;
+    dst[2 * S] = a_dct;
+    dst[3 * S] = a_c2;
+}
+
+// ima_std = mean_z cube_std, o2map = mean_z cube_std^2, ima_dct = mean_z cont_dct, cont_sumsq = sum_z cont_dct^2
+__global__ void reduce_maps_kernel(const double *__restrict__ part4, int nseg, size_t S, int nz,
+                                   double *__restrict__ ima_std, double *__restrict__ ima_dct,
+                                   double *__restrict__ cont_sumsq, double *__restrict__ o2map) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double a[4] = {0, 0, 0, 0};
+    for (int seg = 0; seg < nseg; ++seg)   // fixed order
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] += part4[((size_t)seg * 4 + q) * S + s];
+    if (ima_std) ima_std[s] = a[0] / nz;
+    if (o2map) o2map[s] = a[1] / nz;
+    if (ima_dct) ima_dct[s] = a[2] / nz;
+    if (cont_sumsq) cont_sumsq[s] = a[3];
 }
 
 // -------------------------------------------------------------------------------------------
@@ -242,19 +385,70 @@ static int upload_dctmat(ogn_ctx *ctx, int nz, int M, const double **d0_dev) {
     return OGN_OK;
 }
 
+// cos(m theta_z), m = 0 .. 2M-2 (the products of two DCT atoms are sums of two of these)
+static int upload_costab(ogn_ctx *ctx, int nz, int M, const double **tab_dev) {
+    const int NC = 2 * M - 1;
+    std::vector<double> t((size_t)nz * NC);
+    const double step = M_PI / nz;
+    for (int z = 0; z < nz; ++z)
+        for (int m = 0; m < NC; ++m) t[(size_t)z * NC + m] = cos((z + 0.5) * step * m);
+    double *d = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, "dct_costab", t.size(), &d));
+    OGN_CUDA(cudaMemcpyAsync(d, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+    *tab_dev = d;
+    return OGN_OK;
+}
+
+static inline int dct_segments(int nz) { return std::max(1, std::min(DCT_NSEG, nz / 32)); }
+
 template <typename T>
 static int run_fit(ogn_ctx *ctx, const T *raw, const T *var, const uint8_t *mask, const double *d0, int M, int nz,
                    size_t S, int approx, double *coef) {
     const int blocks = ogn_div_up((int64_t)S, 128);
     if (M == 11) {
-        dct_fit_kernel<11, T><<<blocks, 128, 0, ctx->stream>>>(raw, var, mask, d0, nz, S, approx, coef);
-        OGN_LAUNCH_CHECK("dct_fit_kernel");
+        constexpr int NQ = 4 * 11 - 1;
+        const int nseg = dct_segments(nz), zseg = ogn_div_up(nz, nseg);
+        const double *ctab = nullptr;
+        OGN_TRY(upload_costab(ctx, nz, M, &ctab));
+        double *part = nullptr;
+        uint8_t *anym = nullptr;
+        OGN_TRY(ogn_scratch_t(ctx, "dct_part", (size_t)nseg * NQ * S, &part));
+        OGN_TRY(ogn_scratch_t(ctx, "dct_anym", (size_t)nseg * S, &anym));
+        {
+            ogn_timer t_(ctx, "k5a_dct_accum");
+            dct_accum_kernel<11, T><<<dim3(blocks, nseg), 128, 0, ctx->stream>>>(raw, var, mask, ctab, nz, S, approx, zseg,
+                                                                                part, anym);
+            OGN_LAUNCH_CHECK("dct_accum_kernel");
+        }
+        ogn_timer t_(ctx, "k5a_dct_solve");
+        dct_solve_kernel<11><<<blocks, 128, 0, ctx->stream>>>(part, anym, nseg, S, nz, approx, coef);
+        OGN_LAUNCH_CHECK("dct_solve_kernel");
     } else {
         double *ws = nullptr;
         OGN_TRY(ogn_scratch_t(ctx, "dct_gram_ws", S * (size_t)M * M, &ws));
         dct_fit_generic_kernel<T><<<blocks, 128, 0, ctx->stream>>>(raw, var, mask, d0, M, nz, S, approx, coef, ws);
         OGN_LAUNCH_CHECK("dct_fit_generic_kernel");
     }
+    return OGN_OK;
+}
+
+// cont = D0 coef on (spaxel, wavelength-segment) threads; order 10 (M = 11) keeps the coefficients in registers
+template <typename T, typename TO>
+static int launch_synth(ogn_ctx *ctx, const T *raw, const uint8_t *mask, const double *d0, int M, int nz, size_t S,
+                        const double *coef, TO *cont_out, double *cont64, float *data_out, double *lambda_sum,
+                        double *lambda_cnt, int nx, int wy0, int wy1, int wx0, int wx1) {
+    ogn_timer t_(ctx, "k5b_dct_synth");
+    const int nseg = dct_segments(nz), zseg = ogn_div_up(nz, nseg);
+    const dim3 grid(ogn_div_up((int64_t)S, 128), nseg);
+    const size_t sm = lambda_sum ? (size_t)2 * zseg * sizeof(double) : 0;
+    if (M == 11)
+        dct_synth_kernel<T, TO, 11><<<grid, 128, sm, ctx->stream>>>(raw, mask, d0, M, nz, S, zseg, coef, cont_out, cont64,
+                                                                  data_out, lambda_sum, lambda_cnt, nx, wy0, wy1, wx0, wx1);
+    else
+        dct_synth_kernel<T, TO, 0><<<grid, 128, sm, ctx->stream>>>(raw, mask, d0, M, nz, S, zseg, coef, cont_out, cont64,
+                                                                 data_out, lambda_sum, lambda_cnt, nx, wy0, wy1, wx0, wx1);
+    OGN_LAUNCH_CHECK("dct_synth_kernel");
     return OGN_OK;
 }
 
@@ -312,14 +506,11 @@ extern "C" int ogn_dct_residual(ogn_ctx *ctx, const void *raw, const void *var, 
         OGN_TRY(run_fit<float>(ctx, (const float *)in.raw, (const float *)in.var, in.mask, d0, M, nz, S, approx, coef));
     }
     if (out_dtype == OGN_F64)
-        dct_synth_kernel<float, double><<<blocks, 128, 0, ctx->stream>>>(nullptr, nullptr, d0, M, nz, S, coef,
-                                                                        (double *)d_cont, nullptr, nullptr, nullptr, nullptr,
-                                                                        nx, 0, ny, 0, nx);
+        OGN_TRY((launch_synth<float, double>(ctx, nullptr, nullptr, d0, M, nz, S, coef, (double *)d_cont, nullptr, nullptr,
+                                             nullptr, nullptr, nx, 0, ny, 0, nx)));
     else
-        dct_synth_kernel<float, float><<<blocks, 128, 0, ctx->stream>>>(nullptr, nullptr, d0, M, nz, S, coef,
-                                                                       (float *)d_cont, nullptr, nullptr, nullptr, nullptr,
-                                                                       nx, 0, ny, 0, nx);
-    OGN_LAUNCH_CHECK("dct_synth_kernel");
+        OGN_TRY((launch_synth<float, float>(ctx, nullptr, nullptr, d0, M, nz, S, coef, (float *)d_cont, nullptr, nullptr,
+                                            nullptr, nullptr, nx, 0, ny, 0, nx)));
     OGN_TRY(ogn_output_commit(ctx, cont, d_cont, vol * (out_dtype == OGN_F64 ? 8 : 4)));
     return ogn_finish_call(ctx);
 }
@@ -341,11 +532,8 @@ extern "C" int ogn_preprocess_begin(ogn_ctx *ctx, const void *raw, const void *v
     OGN_TRY(stage_dct_inputs(ctx, raw, var, in_dtype, mask, vol, approx, &in));
     const double *d0 = nullptr;
     OGN_TRY(upload_dctmat(ctx, nz, M, &d0));
-    double *coef = nullptr, *cont64 = nullptr;
-    float *data = nullptr;
+    double *coef = nullptr;
     OGN_TRY(ogn_scratch_t(ctx, "dct_coef", S * M, &coef));
-    OGN_TRY(ogn_scratch_t(ctx, "prep_cont64", vol, &cont64));
-    OGN_TRY(ogn_scratch_t(ctx, "prep_data", vol, &data));
     void *d_sum = nullptr, *d_cnt = nullptr;
     OGN_TRY(ogn_output(ctx, "prep_lsum", lambda_sum, (size_t)nz * 8, &d_sum));
     OGN_TRY(ogn_output(ctx, "prep_lcnt", lambda_cnt, (size_t)nz * 8, &d_cnt));
@@ -354,19 +542,17 @@ extern "C" int ogn_preprocess_begin(ogn_ctx *ctx, const void *raw, const void *v
     const int blocks = ogn_div_up((int64_t)S, 128);
     if (in_dtype == OGN_F64) {
         OGN_TRY(run_fit<double>(ctx, (const double *)in.raw, (const double *)in.var, in.mask, d0, M, nz, S, approx, coef));
-        dct_synth_kernel<double, double><<<blocks, 128, 0, ctx->stream>>>((const double *)in.raw, in.mask, d0, M, nz, S,
-                                                                         coef, nullptr, cont64, data, (double *)d_sum,
-                                                                         (double *)d_cnt, nx, wy0, wy1, wx0, wx1);
+        OGN_TRY((launch_synth<double, double>(ctx, (const double *)in.raw, in.mask, d0, M, nz, S, coef, nullptr, nullptr, nullptr,
+                                              (double *)d_sum, (double *)d_cnt, nx, wy0, wy1, wx0, wx1)));
     } else {
         OGN_TRY(run_fit<float>(ctx, (const float *)in.raw, (const float *)in.var, in.mask, d0, M, nz, S, approx, coef));
-        dct_synth_kernel<float, double><<<blocks, 128, 0, ctx->stream>>>((const float *)in.raw, in.mask, d0, M, nz, S,
-                                                                        coef, nullptr, cont64, data, (double *)d_sum,
-                                                                        (double *)d_cnt, nx, wy0, wy1, wx0, wx1);
+        OGN_TRY((launch_synth<float, double>(ctx, (const float *)in.raw, in.mask, d0, M, nz, S, coef, nullptr, nullptr, nullptr,
+                                             (double *)d_sum, (double *)d_cnt, nx, wy0, wy1, wx0, wx1)));
     }
-    OGN_LAUNCH_CHECK("dct_synth_kernel");
     ctx->prep.active = true;
     ctx->prep.nz = nz; ctx->prep.ny = ny; ctx->prep.nx = nx; ctx->prep.in_dtype = in_dtype;
-    ctx->prep.var = in.var; ctx->prep.mask = in.mask; ctx->prep.data = data; ctx->prep.cont = cont64;
+    ctx->prep.raw = in.raw; ctx->prep.var = in.var; ctx->prep.mask = in.mask;
+    ctx->prep.coef = coef; ctx->prep.d0 = d0; ctx->prep.M = M;
     OGN_TRY(ogn_output_commit(ctx, lambda_sum, d_sum, (size_t)nz * 8));
     OGN_TRY(ogn_output_commit(ctx, lambda_cnt, d_cnt, (size_t)nz * 8));
     return ogn_finish_call(ctx);
@@ -391,17 +577,24 @@ extern "C" int ogn_preprocess_finish(ogn_ctx *ctx, const double *lambda_mean, fl
     if (cont_sumsq) OGN_TRY(ogn_output(ctx, "prep_c2", cont_sumsq, S * 8, &d_c2));
     if (o2map) OGN_TRY(ogn_output(ctx, "prep_o2", o2map, S * 8, &d_o2));
     const int blocks = ogn_div_up((int64_t)S, 128);
-    if (st.in_dtype == OGN_F64)
-        standardise_kernel<double><<<blocks, 128, 0, ctx->stream>>>(st.data, st.cont, (const double *)st.var, st.mask,
-                                                                   (const double *)d_mean, nz, S, (float *)d_std,
-                                                                   (float *)d_cd, (double *)d_is, (double *)d_id,
-                                                                   (double *)d_c2, (double *)d_o2);
-    else
-        standardise_kernel<float><<<blocks, 128, 0, ctx->stream>>>(st.data, st.cont, (const float *)st.var, st.mask,
-                                                                  (const double *)d_mean, nz, S, (float *)d_std,
-                                                                  (float *)d_cd, (double *)d_is, (double *)d_id,
-                                                                  (double *)d_c2, (double *)d_o2);
-    OGN_LAUNCH_CHECK("standardise_kernel");
+    const int nseg = dct_segments(nz), zseg = ogn_div_up(nz, nseg);
+    double *part4 = nullptr;
+    OGN_TRY(ogn_scratch_t(ctx, "prep_part4", (size_t)nseg * 4 * S, &part4));
+    {
+        ogn_timer t_(ctx, "k5c_standardise");
+        const dim3 grid(blocks, nseg);
+#define OGN_STD(T_, MT_)                                                                                             \
+    standardise_kernel<T_, MT_><<<grid, 128, 0, ctx->stream>>>((const T_ *)st.raw, (const T_ *)st.var, st.mask, st.d0, st.M, \
+                                                               st.coef, (const double *)d_mean, nz, S, zseg, (float *)d_std,  \
+                                                               (float *)d_cd, part4)
+        if (st.in_dtype == OGN_F64) { if (st.M == 11) OGN_STD(double, 11); else OGN_STD(double, 0); }
+        else { if (st.M == 11) OGN_STD(float, 11); else OGN_STD(float, 0); }
+#undef OGN_STD
+        OGN_LAUNCH_CHECK("standardise_kernel");
+        reduce_maps_kernel<<<blocks, 128, 0, ctx->stream>>>(part4, nseg, S, nz, (double *)d_is, (double *)d_id, (double *)d_c2,
+                                                           (double *)d_o2);
+        OGN_LAUNCH_CHECK("reduce_maps_kernel");
+    }
     OGN_TRY(ogn_output_commit(ctx, cube_std, d_std, vol * 4));
     OGN_TRY(ogn_output_commit(ctx, cont_dct, d_cd, vol * 4));
     OGN_TRY(ogn_output_commit(ctx, ima_std, d_is, S * 8));
