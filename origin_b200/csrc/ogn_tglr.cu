@@ -653,11 +653,8 @@ static int launch_fsf_correlate(ogn_ctx *ctx, cudaStream_t stream, const float *
         CUtensorMap map;
         OGN_TRY(ogn_make_tile_map(ctx, &map, in, in_z_invariant ? 1 : nz, iny, inx, ipitch, G::PITCH, G::ROWS));
         auto kern = k1::fsf_correlate_kernel<25>;
-        static bool attr_set = false;
-        if (!attr_set) {
-            OGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
-            attr_set = true;
-        }
+        // per device, and cheap: set on every launch rather than cached in a process-wide flag
+        OGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
         const int tx = ogn_div_up(wnx, k1::TILE), ty = ogn_div_up(wny, k1::TILE);
         // several waves of resident blocks (4 per SM), every block walking nz/zsplit >= 8 planes: tiles of a
         // ragged window differ in live warps (32 x 32 patches outside the window are skipped), so the block
