@@ -41,9 +41,12 @@ dct_accum_kernel(const T *__restrict__ raw, const T *__restrict__ var, const uin
                  const double *__restrict__ ctab,  // [nz][2M-1]: cos(m theta_z)
                  int nz, size_t S, int approx, int zseg, double *__restrict__ part, uint8_t *__restrict__ anym) {
     constexpr int NC = 2 * M - 1, NQ = NC + 2 * M;
+    extern __shared__ double tab_sm[];   // this block's wavelength segment of the cosine table (broadcast LDS)
+    const int z0 = blockIdx.y * zseg, z1 = min(nz, z0 + zseg);
+    for (int i = threadIdx.x; i < (z1 - z0) * NC; i += blockDim.x) tab_sm[i] = ctab[(size_t)z0 * NC + i];
+    __syncthreads();
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    const int z0 = blockIdx.y * zseg, z1 = min(nz, z0 + zseg);
     double C[NC], R[M], B[M];
 #pragma unroll
     for (int i = 0; i < NC; ++i) C[i] = 0.0;
@@ -66,15 +69,15 @@ dct_accum_kernel(const T *__restrict__ raw, const T *__restrict__ var, const uin
             nv = raw[o];
             if (!approx) { nw = var[o]; nm = mask[o]; }
         }
-        const double *t = ctab + (size_t)z * NC;
+        const double *t = tab_sm + (size_t)(z - z0) * NC;
         if (approx) {
 #pragma unroll
-            for (int i = 0; i < M; ++i) B[i] = fma(__ldg(t + i), v, B[i]);
+            for (int i = 0; i < M; ++i) B[i] = fma(t[i], v, B[i]);
         } else {
             const double w = 1.0 / vr, vw = v * w;
 #pragma unroll
             for (int m = 0; m < NC; ++m) {
-                const double c = __ldg(t + m);
+                const double c = t[m];
                 C[m] = fma(c, w, C[m]);
                 if (m < M) {
                     R[m] = fma(c, vw, R[m]);
@@ -221,16 +224,15 @@ dct_synth_kernel(const T *__restrict__ raw, const uint8_t *__restrict__ mask, co
                  int nz, size_t S, int zseg, const double *__restrict__ coef, TO *__restrict__ cont_out,
                  double *__restrict__ cont64, float *__restrict__ data_out, double *__restrict__ lambda_sum,
                  double *__restrict__ lambda_cnt, int nx, int wy0, int wy1, int wx0, int wx1) {
-    extern __shared__ double seg_acc[];   // [2][zseg] when lambda_sum is requested
-    double *seg_sum = seg_acc, *seg_cnt = seg_acc + zseg;
+    extern __shared__ double seg_acc[];   // [2][zseg] per-wavelength accumulators, then [zseg][M] DCTMAT segment
+    double *seg_sum = seg_acc, *seg_cnt = seg_acc + zseg, *d0_sm = seg_acc + 2 * zseg;
     const int M = MT > 0 ? MT : Mrt;
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = s < S;
     const int z0 = blockIdx.y * zseg, z1 = min(nz, z0 + zseg);
-    if (lambda_sum) {
-        for (int i = threadIdx.x; i < 2 * zseg; i += blockDim.x) seg_acc[i] = 0.0;
-        __syncthreads();
-    }
+    for (int i = threadIdx.x; i < 2 * zseg; i += blockDim.x) seg_acc[i] = 0.0;
+    for (int i = threadIdx.x; i < (z1 - z0) * M; i += blockDim.x) d0_sm[i] = d0[(size_t)z0 * M + i];
+    __syncthreads();
     // only spaxels inside the owned window contribute to the per-wavelength sums (multi-GPU tiles)
     const int sy = (int)(s / nx), sx = (int)(s - (size_t)sy * nx);
     const bool counted = live && sy >= wy0 && sy < wy1 && sx >= wx0 && sx < wx1;
@@ -245,7 +247,7 @@ dct_synth_kernel(const T *__restrict__ raw, const uint8_t *__restrict__ mask, co
         if (counted) nm = mask[(size_t)z0 * S + s];
     }
     for (int z = z0; z < z1; ++z) {
-        const double *d = d0 + (size_t)z * M;
+        const double *d = d0_sm + (size_t)(z - z0) * M;
         const double rv = (double)nr;
         const bool masked = nm != 0;
         if (live && need_raw && z + 1 < z1) {
@@ -255,7 +257,7 @@ dct_synth_kernel(const T *__restrict__ raw, const uint8_t *__restrict__ mask, co
         double cont = 0.0;
         if (MT > 0) {
 #pragma unroll
-            for (int i = 0; i < MT; ++i) cont = fma(__ldg(d + i), c[i], cont);
+            for (int i = 0; i < MT; ++i) cont = fma(d[i], c[i], cont);
         } else {
             for (int i = 0; i < M; ++i) cont = fma(d[i], c[i], cont);
         }
@@ -301,10 +303,13 @@ standardise_kernel(const T *__restrict__ raw, const T *__restrict__ var, const u
                    const double *__restrict__ d0, int Mrt, const double *__restrict__ coef,
                    const double *__restrict__ mean, int nz, size_t S, int zseg,
                    float *__restrict__ cube_std, float *__restrict__ cont_dct, double *__restrict__ part4) {
+    extern __shared__ double d0_seg[];   // [zseg][M] DCTMAT segment
     const int M = MT > 0 ? MT : Mrt;
+    const int z0 = blockIdx.y * zseg, z1 = min(nz, z0 + zseg);
+    for (int i = threadIdx.x; i < (z1 - z0) * M; i += blockDim.x) d0_seg[i] = d0[(size_t)z0 * M + i];
+    __syncthreads();
     const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    const int z0 = blockIdx.y * zseg, z1 = min(nz, z0 + zseg);
     double c[MT > 0 ? MT : DCT_MAXM];
 #pragma unroll
     for (int i = 0; i < (MT > 0 ? MT : DCT_MAXM); ++i) c[i] = i < M ? coef[(size_t)i * S + s] : 0.0;
@@ -323,11 +328,11 @@ standardise_kernel(const T *__restrict__ raw, const T *__restrict__ var, const u
             const size_t on = o + S;
             nr = raw[on]; nv = var[on]; nm = mask[on];
         }
-        const double *d = d0 + (size_t)z * M;
+        const double *d = d0_seg + (size_t)(z - z0) * M;
         double cont = 0.0;
         if (MT > 0) {
 #pragma unroll
-            for (int i = 0; i < MT; ++i) cont = fma(__ldg(d + i), c[i], cont);
+            for (int i = 0; i < MT; ++i) cont = fma(d[i], c[i], cont);
         } else {
             for (int i = 0; i < M; ++i) cont = fma(d[i], c[i], cont);
         }
@@ -401,6 +406,12 @@ static int upload_costab(ogn_ctx *ctx, int nz, int M, const double **tab_dev) {
 }
 
 static inline int dct_segments(int nz) { return std::max(1, std::min(DCT_NSEG, nz / 32)); }
+// segments for the kernels that stage `rows` doubles per wavelength in shared memory (<= 40 KB per block)
+static inline int dct_segments_smem(int nz, int rows) {
+    int nseg = dct_segments(nz);
+    while ((size_t)ogn_div_up(nz, nseg) * rows * sizeof(double) > 40 * 1024) ++nseg;
+    return nseg;
+}
 
 template <typename T>
 static int run_fit(ogn_ctx *ctx, const T *raw, const T *var, const uint8_t *mask, const double *d0, int M, int nz,
@@ -408,7 +419,7 @@ static int run_fit(ogn_ctx *ctx, const T *raw, const T *var, const uint8_t *mask
     const int blocks = ogn_div_up((int64_t)S, 128);
     if (M == 11) {
         constexpr int NQ = 4 * 11 - 1;
-        const int nseg = dct_segments(nz), zseg = ogn_div_up(nz, nseg);
+        const int nseg = dct_segments_smem(nz, 21), zseg = ogn_div_up(nz, nseg);
         const double *ctab = nullptr;
         OGN_TRY(upload_costab(ctx, nz, M, &ctab));
         double *part = nullptr;
@@ -417,8 +428,9 @@ static int run_fit(ogn_ctx *ctx, const T *raw, const T *var, const uint8_t *mask
         OGN_TRY(ogn_scratch_t(ctx, "dct_anym", (size_t)nseg * S, &anym));
         {
             ogn_timer t_(ctx, "k5a_dct_accum");
-            dct_accum_kernel<11, T><<<dim3(blocks, nseg), 128, 0, ctx->stream>>>(raw, var, mask, ctab, nz, S, approx, zseg,
-                                                                                part, anym);
+            const size_t sm = (size_t)zseg * 21 * sizeof(double);
+            auto kern = dct_accum_kernel<11, T>;
+            kern<<<dim3(blocks, nseg), 128, sm, ctx->stream>>>(raw, var, mask, ctab, nz, S, approx, zseg, part, anym);
             OGN_LAUNCH_CHECK("dct_accum_kernel");
         }
         ogn_timer t_(ctx, "k5a_dct_solve");
@@ -439,9 +451,9 @@ static int launch_synth(ogn_ctx *ctx, const T *raw, const uint8_t *mask, const d
                         const double *coef, TO *cont_out, double *cont64, float *data_out, double *lambda_sum,
                         double *lambda_cnt, int nx, int wy0, int wy1, int wx0, int wx1) {
     ogn_timer t_(ctx, "k5b_dct_synth");
-    const int nseg = dct_segments(nz), zseg = ogn_div_up(nz, nseg);
+    const int nseg = dct_segments_smem(nz, 2 + M), zseg = ogn_div_up(nz, nseg);
     const dim3 grid(ogn_div_up((int64_t)S, 128), nseg);
-    const size_t sm = lambda_sum ? (size_t)2 * zseg * sizeof(double) : 0;
+    const size_t sm = (size_t)(2 + M) * zseg * sizeof(double);
     if (M == 11)
         dct_synth_kernel<T, TO, 11><<<grid, 128, sm, ctx->stream>>>(raw, mask, d0, M, nz, S, zseg, coef, cont_out, cont64,
                                                                   data_out, lambda_sum, lambda_cnt, nx, wy0, wy1, wx0, wx1);
@@ -577,14 +589,15 @@ extern "C" int ogn_preprocess_finish(ogn_ctx *ctx, const double *lambda_mean, fl
     if (cont_sumsq) OGN_TRY(ogn_output(ctx, "prep_c2", cont_sumsq, S * 8, &d_c2));
     if (o2map) OGN_TRY(ogn_output(ctx, "prep_o2", o2map, S * 8, &d_o2));
     const int blocks = ogn_div_up((int64_t)S, 128);
-    const int nseg = dct_segments(nz), zseg = ogn_div_up(nz, nseg);
+    const int nseg = dct_segments_smem(nz, st.M), zseg = ogn_div_up(nz, nseg);
     double *part4 = nullptr;
     OGN_TRY(ogn_scratch_t(ctx, "prep_part4", (size_t)nseg * 4 * S, &part4));
     {
         ogn_timer t_(ctx, "k5c_standardise");
         const dim3 grid(blocks, nseg);
+        const size_t sm = (size_t)st.M * zseg * sizeof(double);
 #define OGN_STD(T_, MT_)                                                                                             \
-    standardise_kernel<T_, MT_><<<grid, 128, 0, ctx->stream>>>((const T_ *)st.raw, (const T_ *)st.var, st.mask, st.d0, st.M, \
+    standardise_kernel<T_, MT_><<<grid, 128, sm, ctx->stream>>>((const T_ *)st.raw, (const T_ *)st.var, st.mask, st.d0, st.M, \
                                                                st.coef, (const double *)d_mean, nz, S, zseg, (float *)d_std,  \
                                                                (float *)d_cd, part4)
         if (st.in_dtype == OGN_F64) { if (st.M == 11) OGN_STD(double, 11); else OGN_STD(double, 0); }
