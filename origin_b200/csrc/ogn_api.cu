@@ -215,15 +215,26 @@ static int stage_reserve(ogn_ctx *ctx, size_t bytes) {
 
 int ogn_uploader::add(void *dst, const void *src, size_t bytes) {
     if (bytes == 0) return OGN_OK;
-    if (bytes % 4 || tab.n >= OGN_UPLOAD_MAX) return ogn_fail(ctx, OGN_ERR_ARG, "ogn_uploader: bad item");
+    if (bytes % 4) return ogn_fail(ctx, OGN_ERR_ARG, "ogn_uploader: item size must be a multiple of 4");
     if (used == 0 && ctx->stage_pending) {  // the previous batch may still be read by its kernel
         OGN_CUDA(cudaEventSynchronize(ctx->stage_ev));
         ctx->stage_pending = false;
     }
-    const size_t off = (used + 15) / 16 * 16;
+    size_t off = (used + 15) / 16 * 16;
     if (off + bytes > ctx->stage_cap) {
-        if (tab.n) return ogn_fail(ctx, OGN_ERR_NOMEM, "ogn_uploader: staging buffer too small");
-        OGN_TRY(stage_reserve(ctx, off + bytes));
+        if (tab.n) {   // send what is staged, wait until it has been read, start over at offset 0
+            OGN_TRY(flush(ctx->stream));
+            OGN_CUDA(cudaEventSynchronize(ctx->stage_ev));
+            ctx->stage_pending = false;
+            off = 0;
+        }
+        if (bytes > ctx->stage_cap) OGN_TRY(stage_reserve(ctx, bytes));
+    }
+    if (tab.n >= OGN_UPLOAD_MAX) {   // table full: same
+        OGN_TRY(flush(ctx->stream));
+        OGN_CUDA(cudaEventSynchronize(ctx->stage_ev));
+        ctx->stage_pending = false;
+        off = 0;
     }
     memcpy(ctx->stage_h + off, src, bytes);
     tab.item[tab.n++] = ogn_upload_item{dst, (unsigned)off, (unsigned)bytes};
