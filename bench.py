@@ -443,6 +443,9 @@ def main_gpu(args):
                       note='FP32-pipe issue slots actually used (FFMA and FADD both count 2): the figure to read as '
                            'pipe utilisation; "achieved" counts the direct-form 2*P^2 flops of SURVEY.md 8d, which the '
                            'folded kernel does not execute, so it can exceed the peak'),
+        frac_above_one=('K1 folds the mirror-symmetric FSF rows: it executes %.0f of the %d algorithmic flop slots per '
+                        'voxel, so achieved/peak can exceed 1; executed.frac is the FP32 pipe utilisation'
+                        % (k1_slots, 2 * PSF_SIZE ** 2)) if folded else None,
         traffic=summ.get('k1_dram_bytes_per_launch'),
         peak_source='FP32 FFMA peak measured on this device in this run by tools/fma_peak '
                     '(MEASURED_PEAKS.json has no FP32 figure; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)',
