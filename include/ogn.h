@@ -258,7 +258,10 @@ OGN_API int ogn_purity_counts(ogn_ctx *ctx,
  * pointer; the lists are the capacity-sized buffers of an ogn_step05 / ogn_step05_tile / ogn_local_extrema
  * call whose `counts` output was a DEVICE array (such a call does not synchronise either), and
  * list_counts is that array: the kernels read the true list lengths from it.  n1 / n0 can be handed to
- * an NCCL allreduce without the host ever seeing them. */
+ * an NCCL allreduce without the host ever seeing them.  A list that overflowed `capacity` cannot be
+ * reported by a return code here: the kernel then adds -2^56 to every count of that list, so a NEGATIVE
+ * count (also after a SUM over ranks) means "extremum list overflow: repeat the step with a larger
+ * capacity". */
 OGN_API int ogn_purity_counts_dev(ogn_ctx *ctx,
                           const int64_t *max_index, const float *max_value,
                           const int64_t *min_index, const float *min_value, int64_t capacity,

@@ -452,3 +452,53 @@ def spot_tglr(cube, fsf, prof_cut, points):
                     den += dj * dj * den_z[zz - z0]
             out[n, k] = num / np.sqrt(den) if den > 0 else 0.0
     return out
+
+
+def spot_box(win, fsf, prof_cut, origin, gshape, centre):
+    """Direct-space float64 ``T_k`` on the 3x3x3 neighbourhood of ``centre = (z, y, x)`` of a single-field
+    ``gshape`` cube (SURVEY.md appendix A.2 evaluated pointwise), from a window ``win`` of that cube whose
+    first voxel is ``origin`` and which covers the neighbourhood grown by the FSF half-size and the
+    longest profile.  Returns ``dict(tk=[3][3][3][K] (NaN outside the cube), valid=[3][3][3] bool)``:
+    enough to check correl / correl_min / argmax at the centre AND whether the centre is a 3x3x3 local
+    extremum (lib_origin.py:1244-1253), on cubes far too large for the full oracle."""
+    nz, ny, nx = gshape
+    z, y, x = centre
+    z0, y0, x0 = origin
+    fsf = np.asarray(fsf, dtype=np.float64)
+    p = fsf.shape[-1]
+    c = p // 2
+    reach = max(len(d) for d in prof_cut)
+    za, zb = max(0, z - 1 - reach), min(nz, z + 2 + reach)
+    za, zb = max(za, z0), min(zb, z0 + win.shape[0])
+    ker_all = fsf[za:zb] - fsf[za:zb].mean(axis=(1, 2), keepdims=True)
+    nk = len(prof_cut)
+    tk = np.full((3, 3, 3, nk), np.nan)
+    valid = np.zeros((3, 3, 3), dtype=bool)
+    for dy in range(3):
+        for dx in range(3):
+            yy, xx = y - 1 + dy, x - 1 + dx
+            if not (0 <= yy < ny and 0 <= xx < nx):
+                continue
+            ya, yb = max(0, yy - c), min(ny, yy + c + 1)
+            xa, xb = max(0, xx - c), min(nx, xx + c + 1)
+            if ya < y0 or xa < x0 or yb > y0 + win.shape[1] or xb > x0 + win.shape[2]:
+                raise ValueError('window does not cover the FSF footprint of (%d, %d)' % (yy, xx))
+            ker = ker_all[:, ya - yy + c:yb - yy + c, xa - xx + c:xb - xx + c]
+            patch = np.asarray(win[za - z0:zb - z0, ya - y0:yb - y0, xa - x0:xb - x0], dtype=np.float64)
+            num_z = (patch * ker).sum(axis=(1, 2))          # cube_fsf[za:zb, yy, xx]
+            den_z = (ker * ker).sum(axis=(1, 2))            # norm_fsf[za:zb, yy, xx]
+            for dz in range(3):
+                zz = z - 1 + dz
+                if not 0 <= zz < nz:
+                    continue
+                valid[dz, dy, dx] = True
+                for k, d in enumerate(prof_cut):
+                    ck = (len(d) - 1) // 2
+                    src = zz + ck - np.arange(len(d))
+                    ok = (src >= 0) & (src < nz)
+                    if np.any(ok & ((src < za) | (src >= zb))):
+                        raise ValueError('window does not cover the profile reach at z = %d' % zz)
+                    num = float(np.dot(d[ok], num_z[src[ok] - za]))
+                    den = float(np.dot(d[ok] ** 2, den_z[src[ok] - za]))
+                    tk[dz, dy, dx, k] = num / np.sqrt(den) if den > 0 else 0.0
+    return dict(tk=tk, valid=valid)

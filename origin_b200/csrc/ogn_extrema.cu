@@ -483,7 +483,14 @@ __global__ void list_counts_kernel(const int64_t *__restrict__ index, const floa
                                    const double *__restrict__ thresholds, int nthresh,
                                    unsigned long long *__restrict__ counts) {
     extern __shared__ unsigned int sm_counts[];
-    if (n_dev) n = min(n, *n_dev);
+    if (n_dev) {
+        // the list overflowed its capacity in the asynchronous call that filled it: the counts would be short.
+        // Nobody can raise from here, so block 0 poisons every count with -2^56 (it stays negative through an
+        // allreduce SUM over any realistic number of ranks); callers test for negative counts.
+        if (*n_dev > n && blockIdx.x == 0)
+            for (int t = threadIdx.x; t < nthresh; t += blockDim.x) atomicAdd(&counts[t], 0ull - (1ull << 56));
+        n = min(n, *n_dev);
+    }
     if ((int64_t)blockIdx.x * blockDim.x >= n) return;   // whole block past the end (uniform)
     for (int t = threadIdx.x; t < nthresh; t += blockDim.x) sm_counts[t] = 0;
     __syncthreads();

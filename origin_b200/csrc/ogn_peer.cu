@@ -166,6 +166,14 @@ extern "C" int ogn_scatter_tile(ogn_ctx *ctx, const float *src, int nz, int ny, 
     auto it = ctx->readers.find(src);
     if (it != ctx->readers.end()) done = it->second;
     else {
+        // callers that hand a fresh buffer every step would grow the map without bound: entries whose copy
+        // has completed protect nothing any more
+        if (ctx->readers.size() >= 16)
+            for (auto r = ctx->readers.begin(); r != ctx->readers.end();)
+                if (cudaEventQuery(r->second) == cudaSuccess) {
+                    cudaEventDestroy(r->second);
+                    r = ctx->readers.erase(r);
+                } else ++r;
         OGN_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
         ctx->readers[src] = done;
     }

@@ -212,6 +212,13 @@ class PeerGather:
         return self._torch.as_tensor(_DeviceBuffer(self.ptrs[slot], self.shape), device=dev)
 
     def close(self):
+        # remote copies into the destination's buffers may still be in flight: every rank first waits for its
+        # own copies, then all ranks meet, and only then are mappings closed and the owned buffers freed
+        if self._mapped or self._owned:
+            try:
+                self.wait()
+            except Exception:  # noqa: BLE001 - tearing down after a failure: free what we can
+                pass
         for p in self._mapped:
             self.ctx.lib.ogn_peer_close(self.ctx.handle, p)
         for p in self._owned:

@@ -21,7 +21,7 @@ from ._lib import OGN_F32, OGN_F64, OgnError, default_context, ptr
 
 __all__ = ['DCTMAT', 'dct_residual', 'O2test', 'Correlation_GLR_test', 'compute_local_max',
            'Compute_threshold_purity', 'prepare_profiles', 'tglr', 'local_extrema', 'LocalExtrema', 'DeviceExtrema',
-           'purity_counts', 'threshold_rows', 'preprocess', 'PurityTable', 'step05', 'fsf_stage']
+           'purity_counts', 'check_counts', 'threshold_rows', 'preprocess', 'PurityTable', 'step05', 'fsf_stage']
 
 
 # --------------------------------------------------------------------------
@@ -353,6 +353,15 @@ def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True,
                          dtype=np.int32)
         if (t.py1 - t.py0, t.px1 - t.px0) != (ny, nx):
             raise ValueError('cube does not have the shape of the padded tile')
+        psize = fsfs[0].shape[1]
+        need = (psize // 2 + size[1] // 2, psize // 2 + size[2] // 2)
+        for have, want_, at_edge, side in ((t.y0 - t.py0, need[0], t.py0 == 0, 'top'),
+                                           (t.py1 - t.y1, need[0], t.py1 == gny, 'bottom'),
+                                           (t.x0 - t.px0, need[1], t.px0 == 0, 'left'),
+                                           (t.px1 - t.x1, need[1], t.px1 == gnx, 'right')):
+            if have < want_ and not at_edge:
+                raise ValueError('tile halo on the %s side is %d pixels; the FSF (P = %d) and the %r extremum window '
+                                 'need %d where the field continues' % (side, have, psize, size, want_))
         ext_shape = (nz, gny, gnx)
     while True:
         lists = {}
@@ -383,18 +392,27 @@ def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True,
             break
         capacity = int(counts.max())
         out = {k: v for k, v in out.items() if k not in lists}
+        if tdesc is None and not dense and res.get('correl') is not None and res.get('correl_min') is not None:
+            # a list did not fit: every other product is complete, so only the extremum pass is repeated on the
+            # correl / correl_min just computed (not FSF + spectral stage + PCIe again)
+            ext, _, _ = local_extrema(res['correl'], res['correl_min'], m, size, capacity=capacity, ctx=ctx)
+            res['extrema'] = ext
+            return res
     n1, n0 = int(counts[0]), int(counts[1])
     res['extrema'] = LocalExtrema(ext_shape, lists['max_index'][:n1], lists['max_value'][:n1],
                                   lists['min_index'][:n0], lists['min_value'][:n0])
     return res
 
 
-def Correlation_GLR_test(cube, fsf, weights, profiles, nthreads=1, pcut=None, pmeansub=True, out_dtype=np.float32,
+def Correlation_GLR_test(cube, fsf, weights, profiles, nthreads=1, pcut=None, pmeansub=True, out_dtype=np.float64,
                          ctx=None):
     """GLR test cubes for the given FSF(s) and profile dictionary (reference
     lib_origin.py:1070-1217): returns ``(correl, profile, correl_min)``.
     ``nthreads`` is accepted for signature compatibility and ignored (the
-    reference only uses it to chunk its FFTs; results do not depend on it)."""
+    reference only uses it to chunk its FFTs; results do not depend on it).
+    ``correl`` / ``correl_min`` come back as float64 like the reference's (callers
+    mutate and keep them, steps.py:781); the kernels compute in FP32 — pass
+    ``out_dtype=np.float32`` to skip the widening."""
     res = tglr(cube, fsf, weights, profiles, None, pcut, pmeansub, want=('correl', 'profile', 'correl_min'), ctx=ctx)
     correl, correl_min = res['correl'], res['correl_min']
     if np.dtype(out_dtype) == np.float64:
@@ -512,7 +530,8 @@ def local_extrema(correl, correl_min, mask, size=3, dense=False, capacity=None, 
     dmax = _empty_like_kind(a, a.shape, np.float32) if dense else None
     dmin = _empty_like_kind(a, a.shape, np.float32) if dense else None
     if capacity is None:
-        capacity = max(4096, vol // 40)
+        # 3x3x3 maxima of white noise are 1/27 = 3.7 % of the voxels (the step01 call on cube_std, steps.py:453)
+        capacity = max(4096, vol // 20)
     counts = np.zeros(2, dtype=np.int64)
     while True:
         mi = _empty_like_kind(a, (capacity,), np.int64)
@@ -590,6 +609,28 @@ def purity_stats(ext, segmask, ctx=None):
     return float(stats[0]), float(stats[1]), spmax
 
 
+def _check_device_counts_args(thresholds, out):
+    torch = _torch()
+    if thresholds.dtype != torch.float64 or not thresholds.is_contiguous():
+        raise TypeError('device thresholds must be a contiguous float64 tensor')
+    nt = thresholds.numel()
+    if out is None:
+        out = torch.empty(2 * nt, dtype=torch.int64, device=thresholds.device)
+    if not (_is_torch(out) and out.is_cuda and out.dtype == torch.int64 and out.numel() == 2 * nt and out.is_contiguous()):
+        raise TypeError('out must be a contiguous int64 CUDA tensor of 2 * len(thresholds) entries')
+    return nt, out
+
+
+def check_counts(n1, n0):
+    """Raise OverflowError when per-threshold counts carry the overflow mark of the device-only counting
+    path (negative values: an extremum list of an asynchronous step did not fit its capacity)."""
+    for n in (n1, n0):
+        n = n.detach().cpu().numpy() if _is_torch(n) else np.asarray(n)
+        if n.size and n.min() < 0:
+            raise OverflowError('an extremum list overflowed its capacity in an asynchronous step05: the purity '
+                                'counts are invalid; repeat the step with a larger capacity')
+
+
 def purity_counts(ext, segmask, thresholds, ctx=None, out=None):
     """``n1[t] = #{maxima > t}``, ``n0[t] = #{background minima > t}`` (int64;
     the loop at reference lib_origin.py:1443-1449).
@@ -605,11 +646,11 @@ def purity_counts(ext, segmask, thresholds, ctx=None, out=None):
         torch = _torch()
         b = ext._bufs
         ctx = _ctx_for(b['max_value'], ctx)
-        nt = thresholds.numel()
-        if out is None:
-            out = torch.empty(2 * nt, dtype=torch.int64, device=thresholds.device)
+        nt, out = _check_device_counts_args(thresholds, out)
         if seg is not None and not _is_torch(seg):
             seg = torch.from_numpy(seg).to(thresholds.device)
+        # an overflowed list cannot raise here (nothing is synchronised): the kernel then makes every count
+        # of that list negative; check_counts() / Compute_threshold_purity test for it once they are read
         ctx.check(ctx.lib.ogn_purity_counts_dev(ctx.handle, ptr(b['max_index']), ptr(b['max_value']), ptr(b['min_index']),
                                                 ptr(b['min_value']), ext.capacity, ext.counts_dev.data_ptr(), ptr(seg), ny, nx,
                                                 ptr(thresholds), nt, out.data_ptr(), out.data_ptr() + 8 * nt))
@@ -618,13 +659,7 @@ def purity_counts(ext, segmask, thresholds, ctx=None, out=None):
     c1, c0 = ext.counts
     if _is_torch(thresholds) and thresholds.is_cuda:
         torch = _torch()
-        if thresholds.dtype != torch.float64 or not thresholds.is_contiguous():
-            raise TypeError('device thresholds must be a contiguous float64 tensor')
-        nt = thresholds.numel()
-        if out is None:
-            out = torch.empty(2 * nt, dtype=torch.int64, device=thresholds.device)
-        if out.dtype != torch.int64 or out.numel() != 2 * nt or not out.is_contiguous():
-            raise TypeError('out must be a contiguous int64 tensor of 2 * len(thresholds) entries')
+        nt, out = _check_device_counts_args(thresholds, out)
         if seg is not None and not _is_torch(seg):
             seg = torch.from_numpy(seg).to(thresholds.device)
         ctx.check(ctx.lib.ogn_purity_counts(ctx.handle, ptr(ext.max_index), ptr(ext.max_value), c1, ptr(ext.min_index),
@@ -698,12 +733,25 @@ def Compute_threshold_purity(purity, cube_local_max, cube_local_min, segmap=None
         threshlist = np.linspace(threshmin, threshmax, 50)  # :1439
     else:
         threshlist = np.asarray(threshlist, dtype=np.float64)
-    n1, n0 = backend.counts(ext, segmask, threshlist)
+        threshmin = float(np.min(threshlist)) if threshlist.size else 0.0   # :1441
+    # the reference prefilters both cubes with "> threshmin" (:1443-1444), so a threshold below threshmin
+    # (only possible for a decreasing default list, threshmax < threshmin) counts as threshmin
+    tcount = np.maximum(threshlist, threshmin)
+    neg = tcount < 0
+    if neg.any() and segmask is not None:
+        # background-only minima (cube_local_min * segmask zeroes the others, :1429): one extra threshold
+        tcount_ext = np.concatenate([tcount, [-np.inf]])
+    else:
+        tcount_ext = tcount
+    n1, n0 = backend.counts(ext, segmask, tcount_ext)
+    check_counts(n1, n0)
     if allreduce is not None:
         both = allreduce.sum(np.concatenate([n1, n0]).astype(np.int64))
         n1, n0 = both[:len(n1)], both[len(n1):]
+    if len(tcount_ext) != len(tcount):
+        n_min = int(n0[-1])                                # minima lying in the background
+        n1, n0 = n1[:-1], n0[:-1]
     # zeros of the dense cubes count for negative thresholds
-    neg = threshlist < 0
     if neg.any():
         n1 = n1 + neg * (vol - n_max)
         n0 = n0 + neg * (vol - n_min)

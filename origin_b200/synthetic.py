@@ -138,3 +138,144 @@ def field_weights(ny, nx, nfields=2):
     if nfields > 2:
         raise ValueError('synthetic generator supports 1 or 2 fields')
     return maps[:nfields]
+
+
+# --------------------------------------------------------------------------
+# Counter-based generator: any window of a large cube, on the host or on the device
+# --------------------------------------------------------------------------
+# The benchmark cube (3681 x 320 x 320, or the 3681 x 900 x 900 mosaic) is generated on the GPU by
+# every rank, while the CPU reference arm and the spot oracle need only a tile of the SAME cube on the
+# host.  Each voxel's value is therefore a pure function of (seed, global linear index): a 64-bit
+# integer mix (wrapping int64 arithmetic, identical in numpy and torch) feeding a float64 Box-Muller
+# transform.  The integer stage is bit-identical everywhere; the float64 log / cos may differ in the
+# last place between libm and CUDA, which survives the rounding to float32 for about one voxel in 1e9.
+
+_M1 = -7046029254386353131      # 0x9E3779B97F4A7C15 as a signed 64-bit integer
+_M2 = -4658895280553007687      # 0xBF58476D1CE4E5B9
+_M3 = -7723592293110705685      # 0x94D049BB133111EB
+
+
+def _mix64(h, xp):
+    """splitmix64 finaliser on int64 arrays / tensors with logical shifts emulated by masks."""
+    h = h ^ ((h >> 30) & ((1 << 34) - 1))
+    h = h * _M2
+    h = h ^ ((h >> 27) & ((1 << 37) - 1))
+    h = h * _M3
+    h = h ^ ((h >> 31) & ((1 << 33) - 1))
+    return h
+
+
+def _window_index(window, gshape, xp, device=None):
+    (z0, z1), (y0, y1), (x0, x1) = window
+    _, gny, gnx = gshape
+    if xp is np:
+        z = np.arange(z0, z1, dtype=np.int64)[:, None, None]
+        y = np.arange(y0, y1, dtype=np.int64)[None, :, None]
+        x = np.arange(x0, x1, dtype=np.int64)[None, None, :]
+    else:
+        z = xp.arange(z0, z1, dtype=xp.int64, device=device)[:, None, None]
+        y = xp.arange(y0, y1, dtype=xp.int64, device=device)[None, :, None]
+        x = xp.arange(x0, x1, dtype=xp.int64, device=device)[None, None, :]
+    return (z * gny + y) * gnx + x
+
+
+def hashed_uniform(seed, window, gshape, xp=np, device=None):
+    """float64 uniform(0, 1) per voxel of ``window = ((z0,z1),(y0,y1),(x0,x1))`` of a ``gshape`` cube."""
+    idx = _window_index(window, gshape, xp, device)
+    with np.errstate(over='ignore'):
+        h = _mix64(idx * _M1 + (int(seed) * 2 + 1) * 0x632BE5AB, xp)
+    u = ((h >> 11) & ((1 << 52) - 1))
+    u = u.astype(np.float64) if xp is np else u.to(xp.float64)
+    return (u + 0.5) * (1.0 / (1 << 52))
+
+
+def hashed_normal(seed, window, gshape, xp=np, device=None):
+    """float32 N(0, 1) per voxel of a window of a ``gshape`` cube (Box-Muller on two hashed uniforms)."""
+    u1 = hashed_uniform(2 * int(seed), window, gshape, xp, device)
+    u2 = hashed_uniform(2 * int(seed) + 1, window, gshape, xp, device)
+    if xp is np:
+        return (np.sqrt(-2.0 * np.log(u1)) * np.cos((2.0 * np.pi) * u2)).astype(np.float32)
+    return (xp.sqrt(-2.0 * xp.log(u1)) * xp.cos((2.0 * np.pi) * u2)).to(xp.float32)
+
+
+def emitter_catalogue(gshape, n_src=None, seed=0):
+    """Injected line emitters of the benchmark cube: rows ``(z0, y0, x0, sigma_z, amplitude)``."""
+    nz, ny, nx = gshape
+    if n_src is None:
+        n_src = max(1, int(round(200 * nz * ny * nx / (3681 * 320 * 320))))
+    rng = np.random.default_rng(seed)
+    cat = np.empty((n_src, 5))
+    cat[:, 0] = rng.integers(20, max(21, nz - 20), n_src)
+    cat[:, 1] = rng.integers(13, max(14, ny - 13), n_src)
+    cat[:, 2] = rng.integers(13, max(14, nx - 13), n_src)
+    cat[:, 3] = rng.uniform(2.0, 12.0, n_src) / 2.3548200450309493
+    cat[:, 4] = rng.uniform(5.0, 30.0, n_src)
+    return cat
+
+
+def _emitter_patches(cat, fsf, window, gshape):
+    """Yield ``(zslice, yslice, xslice, patch)`` (window coordinates, float32) of the emitters touching ``window``."""
+    nz = gshape[0]
+    (z0w, z1w), (y0w, y1w), (x0w, x1w) = window
+    c = fsf.shape[-1] // 2
+    for z0, y0, x0, sig, amp in cat:
+        z0, y0, x0 = int(z0), int(y0), int(x0)
+        hw = int(np.ceil(4 * sig))
+        za, zb = max(0, z0 - hw), min(nz, z0 + hw + 1)
+        if zb <= z0w or za >= z1w or y0 + c + 1 <= y0w or y0 - c >= y1w or x0 + c + 1 <= x0w or x0 - c >= x1w:
+            continue
+        zz = np.arange(za, zb)
+        line = np.exp(-0.5 * ((zz - z0) / sig) ** 2)
+        spat = np.asarray(fsf[z0], dtype=np.float64)
+        patch = (amp / np.sqrt((spat ** 2).sum() * (line ** 2).sum())) * line[:, None, None] * spat[None]
+        # clip the (zz, y0-c.., x0-c..) box to the window
+        a = [max(za, z0w), max(y0 - c, y0w), max(x0 - c, x0w)]
+        b = [min(zb, z1w), min(y0 + c + 1, y1w), min(x0 + c + 1, x1w)]
+        sub = patch[a[0] - za:b[0] - za, a[1] - (y0 - c):b[1] - (y0 - c), a[2] - (x0 - c):b[2] - (x0 - c)]
+        yield (slice(a[0] - z0w, b[0] - z0w), slice(a[1] - y0w, b[1] - y0w), slice(a[2] - x0w, b[2] - x0w),
+               sub.astype(np.float32))
+
+
+def _footprint(gshape, window):
+    _, ny, nx = gshape
+    (_, _), (y0, y1), (x0, x1) = window
+    yy, xx = np.mgrid[y0:y1, x0:x1]
+    cy, cx, th = (ny - 1) / 2, (nx - 1) / 2, np.deg2rad(3.0)
+    u = (xx - cx) * np.cos(th) + (yy - cy) * np.sin(th)
+    v = -(xx - cx) * np.sin(th) + (yy - cy) * np.cos(th)
+    return (np.abs(u) > 0.49 * nx) | (np.abs(v) > 0.49 * ny)
+
+
+def bench_window(gshape, window=None, fsf=None, seed=0, xp=np, device=None, zchunk=128, frac_random=1e-3):
+    """``(cube float32, mask uint8)`` of a window of the benchmark's step05 input: hashed N(0,1) noise
+    plus the emitters of :func:`emitter_catalogue`; mask = rotated-square footprint (~5 % of the spaxels)
+    plus ``frac_random`` hashed voxels.  ``xp=np`` builds it on the host, ``xp=torch`` on ``device``
+    (in chunks of ``zchunk`` planes); both give the same cube."""
+    nz, ny, nx = gshape
+    if window is None:
+        window = ((0, nz), (0, ny), (0, nx))
+    (z0, z1), (y0, y1), (x0, x1) = window
+    if fsf is None:
+        fsf = moffat_fsf(nz)
+    shape = (z1 - z0, y1 - y0, x1 - x0)
+    foot = _footprint(gshape, window)
+    if xp is np:
+        cube = np.empty(shape, dtype=np.float32)
+        mask = np.empty(shape, dtype=np.uint8)
+    else:
+        cube = xp.empty(shape, dtype=xp.float32, device=device)
+        mask = xp.empty(shape, dtype=xp.uint8, device=device)
+        foot = xp.from_numpy(foot).to(device)
+    for za in range(z0, z1, zchunk):
+        zb = min(z1, za + zchunk)
+        sub = ((za, zb), (y0, y1), (x0, x1))
+        cube[za - z0:zb - z0] = hashed_normal(seed, sub, gshape, xp, device)
+        rnd = hashed_uniform(1000003 + int(seed), sub, gshape, xp, device) < frac_random
+        m = rnd | foot[None]
+        mask[za - z0:zb - z0] = m.astype(np.uint8) if xp is np else m.to(xp.uint8)
+    for zs, ys, xs, patch in _emitter_patches(emitter_catalogue(gshape, None, seed), fsf, window, gshape):
+        if xp is np:
+            cube[zs, ys, xs] += patch
+        else:
+            cube[zs, ys, xs] += xp.from_numpy(patch).to(device)
+    return cube, mask

@@ -1,0 +1,148 @@
+// Microbenchmark: packed FP32 (fma.rn.f32x2 -> SASS FFMA2) on sm_100a against scalar FFMA, alone and
+// mixed with the instruction types that share K1/K2f's inner loops (LDS, FMNMX, FADD).  Development aid:
+// decides whether the sliding-window kernels should issue FFMA2.
+// Prints one JSON line with TFLOP/s (2 flop per FMA lane-op) for every variant.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(u64 v, float &a, float &b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+__constant__ float ct[256];
+
+// MODE 0: scalar FFMA, uniform tap operand          (acc[i] += t * s[i])
+// MODE 1: FFMA2, uniform scalar tap broadcast       (acc2[i] += t * s2[i])
+// MODE 2: MODE 1 + one LDS per 4 FFMA2
+// MODE 3: MODE 1 + one FMNMX per 2 FFMA2
+// MODE 4: MODE 0 + one LDS per 8 FFMA
+// MODE 5: MODE 0 + one FMNMX per 4 FFMA
+// MODE 6: FFMA2 with all-register operands (tap pair in registers)
+// MODE 7: MODE 1 + one FADD2 per 8 FFMA2  (the folded-sample adds)
+template <int MODE>
+__global__ void __launch_bounds__(128) probe(float *out, int iters, const float *in) {
+    __shared__ float sm[1024];
+    for (int i = threadIdx.x; i < 1024; i += 128) sm[i] = in[i];
+    __syncthreads();
+    constexpr int NS = 8, NG = 10;   // 8 samples (4 pairs), 10 taps: the shape of K2f's inner block
+    float s[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) s[i] = in[threadIdx.x + 32 * i];
+    float mx = -1e30f;
+    if (MODE == 0 || MODE == 4 || MODE == 5) {
+        float acc[NG][NS];
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int i = 0; i < NS; ++i) acc[g][i] = 0.f;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const float t = ct[(it * 4 + j) % 16 * NG + g];
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) acc[g][i] = fmaf(t, s[i], acc[g][i]);
+                    if (MODE == 4) s[g % NS] = sm[(it * 4 + j + g * 32 + threadIdx.x) & 1023];
+                    if (MODE == 5) { mx = fmaxf(mx, acc[g][0]); mx = fmaxf(mx, acc[g][1]); }
+                }
+            }
+        }
+        float r = mx;
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int i = 0; i < NS; ++i) r += acc[g][i];
+        if (r == 123.456f) out[0] = r;
+    } else {
+        u64 acc[NG][NS / 2];
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int i = 0; i < NS / 2; ++i) acc[g][i] = 0ull;
+        u64 s2[NS / 2];
+#pragma unroll
+        for (int i = 0; i < NS / 2; ++i) s2[i] = pk(s[2 * i], s[2 * i + 1]);
+        u64 treg[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) treg[g] = pk(in[g + threadIdx.x], in[g + 1 + threadIdx.x]);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const float t = ct[(it * 4 + j) % 16 * NG + g];
+                    const u64 tt = MODE == 6 ? treg[g] : pk(t, t);
+#pragma unroll
+                    for (int i = 0; i < NS / 2; ++i) acc[g][i] = fma2(tt, s2[i], acc[g][i]);
+                    if (MODE == 2) {
+                        float a, b;
+                        upk(s2[g % (NS / 2)], a, b);
+                        a = sm[(it * 4 + j + g * 32 + threadIdx.x) & 1023];
+                        s2[g % (NS / 2)] = pk(a, b);
+                    }
+                    if (MODE == 3) { float a, b; upk(acc[g][0], a, b); mx = fmaxf(mx, a); mx = fmaxf(mx, b); }
+                }
+                if (MODE == 7) {
+#pragma unroll
+                    for (int i = 0; i < NS / 2; ++i) s2[i] = add2(s2[i], s2[(i + 1) % (NS / 2)]);
+                }
+            }
+        }
+        float r = mx;
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int i = 0; i < NS / 2; ++i) { float a, b; upk(acc[g][i], a, b); r += a + b; }
+        if (r == 123.456f) out[0] = r;
+    }
+}
+
+template <int MODE>
+double run(float *out, const float *in, int sms, int bps) {
+    const int blocks = sms * bps, iters = 4096;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        probe<MODE><<<blocks, 128>>>(out, iters, in);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8 * 10 * 4 * (double)iters * 128 * blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep >= 2 && tf > best) best = tf;
+    }
+    return best;
+}
+
+int main() {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, 0) != cudaSuccess) { printf("{\"error\": \"no device\"}\n"); return 1; }
+    float *out, *in;
+    cudaMalloc(&out, 4);
+    cudaMalloc(&in, 8192);
+    cudaMemset(in, 0, 8192);
+    float h[256];
+    for (int i = 0; i < 256; ++i) h[i] = 1.f / (1 + i);
+    cudaMemcpyToSymbol(ct, h, sizeof(h));
+    const int sms = prop.multiProcessorCount;
+    printf("{");
+    for (int bps = 3; bps <= 12; bps *= 2) {
+        printf("\"blocks_per_sm_%d\": {", bps);
+        printf("\"ffma_uniform\": %.2f, ", run<0>(out, in, sms, bps));
+        printf("\"ffma2_uniform\": %.2f, ", run<1>(out, in, sms, bps));
+        printf("\"ffma2_uniform_lds_1_per_4\": %.2f, ", run<2>(out, in, sms, bps));
+        printf("\"ffma2_uniform_fmnmx_1_per_2\": %.2f, ", run<3>(out, in, sms, bps));
+        printf("\"ffma_uniform_lds_1_per_8\": %.2f, ", run<4>(out, in, sms, bps));
+        printf("\"ffma_uniform_fmnmx_1_per_4\": %.2f, ", run<5>(out, in, sms, bps));
+        printf("\"ffma2_reg\": %.2f, ", run<6>(out, in, sms, bps));
+        printf("\"ffma2_uniform_fadd2_1_per_10\": %.2f}%s", run<7>(out, in, sms, bps), bps < 12 ? ", " : "");
+    }
+    printf("}\n");
+    return 0;
+}
