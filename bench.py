@@ -783,8 +783,8 @@ def run_c3(env, hbm_peak, fp32_peak, steps, warmup):
         ext, _, _ = lo.local_extrema(out['cube_std'], out['cube_std'], job.mask, 3, capacity=max(4096, vol // 16), ctx=ctx)
         return out, ext
 
-    for _ in range(max(1, min(warmup, 2))):
-        step01()
+    for _ in range(3):          # same binding pattern as the timed loop: two product sets end up in the allocator's cache
+        out, ext = step01()
     torch.cuda.synchronize()
     ctx.timing(True)
     ctx.timing_report()
@@ -801,7 +801,7 @@ def run_c3(env, hbm_peak, fp32_peak, steps, warmup):
         st.setdefault(name, []).append(ms)
     ctx.timing(False)
     st = {k: float(np.mean(v)) for k, v in st.items()}
-    k5 = sum(v for k, v in st.items() if k.startswith('k5'))
+    k5 = sum(v for k, v in st.items() if k.startswith('k5'))          # DCT fit, per-lambda sums, standardisation
     step01_roof = dict(
         kernels_ms=st, dct_kernels_ms=k5, bound='hbm', bytes_per_voxel=17.0,
         achieved=17.0 * vol / (k5 * 1e-3) / 1e9 if k5 else None, peak=hbm_peak, unit='GB/s',
@@ -812,7 +812,7 @@ def run_c3(env, hbm_peak, fp32_peak, steps, warmup):
         workload='step01 (DCT order 10, weighted) + step05 TGLR + local extrema + step06 counts, %dx%dx%d, '
                  'Dico_FWHM_2_12 (%d profiles)' % (nz, ny, nx, job.nprof),
         ms_per_step=r['ms_per_step'], value=r['value'], unit='Gvoxel.profiles/s', steps=steps, warmup=warmup,
-        step01_ms=ms01, step01_wall_includes='ogn_preprocess_begin/finish (host reads the per-lambda sums in between) '
+        step01_ms=ms01, step01_wall_includes='ogn_preprocess (fit, per-lambda mean on the device, standardisation, image reductions) '
                                              '+ local extrema of cube_std',
         total_ms=r['ms_per_step'] + ms01, gpu_launches=r['launches'],
         roofline=dict(roofs[dominant], dominant_stage=dominant) if dominant else None,

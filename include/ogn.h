@@ -319,6 +319,18 @@ OGN_API int ogn_preprocess_finish(ogn_ctx *ctx, const double *lambda_mean,
                           double *ima_std, double *ima_dct,
                           double *cont_sumsq, double *o2map);
 
+/* Both phases in one call, for a whole field on one device (no cross-rank reduction in between): the
+ * per-wavelength mean (np.nanmean(data, axis=(1, 2)), steps.py:442; NaN for a plane without unmasked voxel)
+ * is formed on the device and, optionally, returned in lambda_mean[nz].  Outputs as in
+ * ogn_preprocess_finish; a call whose cubes are all device buffers does not synchronise. */
+OGN_API int ogn_preprocess(ogn_ctx *ctx,
+                   const void *raw, const void *var, int in_dtype,
+                   const uint8_t *mask, int nz, int ny, int nx,
+                   int order, int approx, double *lambda_mean,
+                   float *cube_std, float *cont_dct,
+                   double *ima_std, double *ima_dct,
+                   double *cont_sumsq, double *o2map);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,7 @@ extern "C" int ogn_trim(ogn_ctx *ctx) {
         if (kv.second.p) cudaFreeHost(kv.second.p);
     ctx->pins.clear();
     ctx->prep = ogn_prep_state();
+    ctx->dct_tab_nz = ctx->dct_tab_M = 0;
     for (auto e : ctx->events) cudaEventDestroy(e);
     ctx->events.clear();
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
@@ -411,8 +412,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                     CUtensorMapFloatOOBfill);
 
-int ogn_make_tile_map(ogn_ctx *ctx, CUtensorMap *map, const float *base, int nz, int ny, int nx, int pitch,
-                      int box_x, int box_y, int box_z, bool nan_fill) {
+static int get_encoder(ogn_ctx *ctx, PFN_encodeTiled *out) {
     static PFN_encodeTiled encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -422,6 +422,31 @@ int ogn_make_tile_map(ogn_ctx *ctx, CUtensorMap *map, const float *base, int nz,
             return ogn_fail(ctx, OGN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
         encode = reinterpret_cast<PFN_encodeTiled>(fn);
     }
+    *out = encode;
+    return OGN_OK;
+}
+
+// 2-D tiled map over a [rows][cols] array of 1- or 4-byte elements (row stride in bytes, a multiple of 16);
+// out-of-range elements are zero-filled.
+int ogn_make_map_2d(ogn_ctx *ctx, CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols,
+                    uint64_t row_stride_bytes, int box_cols, int box_rows) {
+    PFN_encodeTiled encode = nullptr;
+    OGN_TRY(get_encoder(ctx, &encode));
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_stride_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = encode(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ogn_fail(ctx, OGN_ERR_CUDA, "cuTensorMapEncodeTiled (2-D) failed with CUresult %d", (int)r);
+    return OGN_OK;
+}
+
+int ogn_make_tile_map(ogn_ctx *ctx, CUtensorMap *map, const float *base, int nz, int ny, int nx, int pitch,
+                      int box_x, int box_y, int box_z, bool nan_fill) {
+    PFN_encodeTiled encode = nullptr;
+    OGN_TRY(get_encoder(ctx, &encode));
     cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
     cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)ny * pitch * 4};
     cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, (cuuint32_t)box_z};

@@ -27,6 +27,7 @@ struct ogn_prep_state {
     const uint8_t *mask = nullptr;  // device
     const double *coef = nullptr;   // device: DCT coefficients [M][S]; the continuum is re-synthesised, never stored
     const double *d0 = nullptr;     // device: DCTMAT [nz][M]
+    double *d0p = nullptr;          // device: padded DCTMAT rows + mean column (streamed kernels), or nullptr
     int M = 0;
 };
 
@@ -47,6 +48,7 @@ struct ogn_ctx {
     std::map<std::string, ogn_buf> pins;  // named pinned host scratch, grow-only
     bool host_output_pending = false;     // a D2H copy to caller memory was enqueued
     ogn_prep_state prep;
+    int dct_tab_nz = 0, dct_tab_M = 0;    // (nz, order + 1) the cached DCT tables were built for (ogn_dct.cu)
     // side streams of the streamed host path (created on first use)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> events;

@@ -110,13 +110,42 @@ __global__ void fsf_prep_kernel(const double *const *__restrict__ fsf, int nz, i
 // the reference's "norm <= 0 -> inf", lib_origin.py:1057-1059).
 // Only the classes that occur in the sub-cube are tabulated (cls_list): all 25 x 25 for a whole field,
 // a single one for an interior tile of a multi-GPU run.
+//
+// The table depends only on (FSF, dictionary, geometry), not on the data, and costs 1.1 ms with the 20 profiles of
+// Dico_FWHM_2_12: it is kept across calls.  Whether the table in `rs` is still the right one is decided ON THE
+// DEVICE, without a host round trip: den_signature_kernel hashes the class table K0 just produced (it does
+// depend on the FSF values) into sig[0]; the host contributes a hash of everything else (taps, class list,
+// shapes, the address and size of `rs`); every block of den_table_kernel returns at once when both equal the
+// pair den_commit_kernel stored after the last rebuild (sig[2], sig[3]).
+__global__ void den_signature_kernel(const double *__restrict__ normcls, int nz, int nzp, int ncls_all,
+                                     unsigned long long *__restrict__ sig) {
+    const size_t n = (size_t)ncls_all * nzp;
+    unsigned long long h = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if ((int)(i % nzp) >= nz) continue;   // the pad planes are never written
+        unsigned long long v = (unsigned long long)__double_as_longlong(normcls[i]) + 0x9E3779B97F4A7C15ull * (i + 1);
+        v ^= v >> 30; v *= 0xBF58476D1CE4E5B9ull; v ^= v >> 27; v *= 0x94D049BB133111EBull; v ^= v >> 31;
+        h += v;                                // order-independent: any summation order gives the same hash
+    }
+    for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0 && h) atomicAdd(sig, h);
+}
+__global__ void den_commit_kernel(unsigned long long *__restrict__ sig, unsigned long long host_hash) {
+    sig[2] = sig[0];
+    sig[3] = host_hash;
+    sig[0] = 0;                                // den_signature_kernel of the next call accumulates from zero
+}
+
 __global__ void den_table_kernel(const double *__restrict__ normcls, int nz, int nzp, int ncls,
                                  const int *__restrict__ cls_list,
                                  const double *__restrict__ taps, const int *__restrict__ tap_off, int nprof,
-                                 float *__restrict__ rs) {
-    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+                                 float *__restrict__ rs, const unsigned long long *__restrict__ sig,
+                                 unsigned long long host_hash) {
+    if (sig[0] == sig[2] && sig[3] == host_hash) return;   // the cached table is current (block-uniform)
     const int cls = cls_list[blockIdx.y], k = blockIdx.z;
-    if (z >= nzp) return;
+    // a block walks a range of wavelengths: few enough blocks that a launch which finds the table current costs
+    // microseconds (one thread per (z, class, profile) meant 362 k empty blocks = 0.2 ms)
+    for (int z = blockIdx.x * blockDim.x + threadIdx.x; z < nzp; z += gridDim.x * blockDim.x) {
     float out = 0.f;
     if (z < nz) {
         const double *d = taps + tap_off[k];
@@ -131,6 +160,7 @@ __global__ void den_table_kernel(const double *__restrict__ normcls, int nz, int
         out = den > 0 ? (float)(1.0 / sqrt(den)) : 0.f;
     }
     rs[((size_t)k * ncls + cls) * nzp + z] = out;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -840,11 +870,39 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
     st->rs = nullptr;
     if (!st->pervoxel) {
         OGN_TRY(ogn_scratch_t(ctx, "rs", (size_t)nprof * st->ncy * st->ncx * st->nzp, &st->rs));
+        // signature words {current, -, cached, cached host hash}; zeroed when first allocated
+        unsigned long long *sig = nullptr;
+        const bool fresh = ctx->bufs.find("rs_sig") == ctx->bufs.end();
+        OGN_TRY(ogn_scratch_t(ctx, "rs_sig", (size_t)4, &sig));
+        if (fresh) OGN_TRY(ogn_fill_words(ctx, ctx->stream, sig, 0u, 4 * sizeof(unsigned long long)));
+        // host part of the key: everything the table depends on besides the FSF values
+        unsigned long long hh = 1469598103934665603ull;
+        auto mix = [&hh](const void *p, size_t n) {
+            const unsigned char *b = static_cast<const unsigned char *>(p);
+            for (size_t i = 0; i < n; ++i) { hh ^= b[i]; hh *= 1099511628211ull; }
+        };
+        const int geo[] = {nz, st->nzp, st->ncy, st->ncx, nprof, P, (int)cls_list.size()};
+        const void *rs_ptr = st->rs;
+        mix(geo, sizeof(geo));
+        mix(taps, (size_t)tap_offsets[nprof] * sizeof(double));
+        mix(tap_offsets, (size_t)(nprof + 1) * sizeof(int));
+        mix(cls_list.data(), cls_list.size() * sizeof(int));
+        mix(&rs_ptr, sizeof(rs_ptr));
+        static const bool no_cache = getenv("OGN_NO_DEN_CACHE") != nullptr;
+        if (no_cache) hh ^= (unsigned long long)ctx->launches;   // diagnostic: never matches the stored hash
+        if (hh == 0) hh = 1;
         ogn_timer t_(ctx, "den_table");
-        dim3 grid(ogn_div_up(st->nzp, 128), (unsigned)cls_list.size(), nprof);
+        den_signature_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(normcls, nz, st->nzp, st->ncy * st->ncx, sig);
+        OGN_LAUNCH_CHECK("den_signature_kernel");
+        // enough blocks to fill the device when the table is rebuilt, no more
+        const int zblocks = std::max(1, std::min(ogn_div_up(st->nzp, 128),
+                                                 ogn_div_up((int64_t)ctx->sm_count * 16, (int64_t)cls_list.size() * nprof)));
+        dim3 grid(zblocks, (unsigned)cls_list.size(), nprof);
         den_table_kernel<<<grid, 128, 0, ctx->stream>>>(normcls, nz, st->nzp, st->ncy * st->ncx, d_cls_list, d_taps64, d_tapoff,
-                                                        nprof, st->rs);
+                                                        nprof, st->rs, sig, hh);
         OGN_LAUNCH_CHECK("den_table_kernel");
+        den_commit_kernel<<<1, 1, 0, ctx->stream>>>(sig, hh);
+        OGN_LAUNCH_CHECK("den_commit_kernel");
     }
     return OGN_OK;
 }

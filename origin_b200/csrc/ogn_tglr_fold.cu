@@ -62,13 +62,49 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   c_ftaps[(toff + j * GP) / 4 + q] = taps of slots 4q .. 4q+3 at distance j (0 beyond a profile's h_k)
 __constant__ float4 c_ftaps[MAXT / 4];
 
+// Packed FP32 (sm_100a): fma.rn.f32x2 -> SASS FFMA2 Rd.F32x2, Ra.F32x2, URb.F32 (uniform tap broadcast to both
+// halves), Rc.F32x2.  Two FMAs of one lane per instruction: measured 72.5 TFLOP/s against 60 for scalar FFMAs
+// of the same shape (acc += uniform tap * sample; tools/ffma2_probe.cu), because the register file delivers
+// a 64-bit pair per operand read, and half the issue slots.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// accumulators of a group: scalar floats, or pairs of consecutive wavelengths for the packed variant
+template <int G, bool PK> struct Acc;
+template <int G> struct Acc<G, false> {
+    float v[G][ZB];
+    __device__ __forceinline__ float get(int g, int i) const { return v[g][i]; }
+};
+template <int G> struct Acc<G, true> {
+    f32x2 v[G][ZB / 2];
+    __device__ __forceinline__ float get(int g, int i) const {
+        float lo, hi;
+        unpack2(v[g][i >> 1], lo, hi);
+        return (i & 1) ? hi : lo;
+    }
+};
+
 // Eight consecutive tap distances (one turn of the register rings) for the NA widest slots of the
 // group.  Everything is static: ring indices, the slots touched, the tap offsets relative to t4.
 //   wj points at row (jb - 1) of the forward window of this lane, i.e. wj[(ZB + jj) * 32] is c[zb+ZB-1+j]
-template <int NA, int G>
+template <int NA, int G, bool PK>
 __device__ __forceinline__ void fold_block(const float *__restrict__ wf, const float *__restrict__ wb,
                                            const float4 *__restrict__ t4, float (&F)[ZB], float (&B)[ZB],
-                                           float &fn, float &bn, float (&acc)[G][ZB]) {
+                                           float &fn, float &bn, Acc<G, PK> &acc) {
     constexpr int GP = (G + 3) / 4 * 4;
     constexpr int Q0 = (G - NA) / 4;   // first float4 of the row that holds an active slot
 #pragma unroll
@@ -87,20 +123,35 @@ __device__ __forceinline__ void fold_block(const float *__restrict__ wf, const f
         float s[ZB];
 #pragma unroll
         for (int i = 0; i < ZB; ++i) s[i] = F[(i + 1 + jj) % ZB] + B[(i + ZB - 1 - jj) % ZB];
+        if constexpr (PK) {
+            f32x2 s2[ZB / 2];
 #pragma unroll
-        for (int g = G - NA; g < G; ++g)
+            for (int i = 0; i < ZB / 2; ++i) s2[i] = pack2(s[2 * i], s[2 * i + 1]);
 #pragma unroll
-            for (int i = 0; i < ZB; ++i) acc[g][i] = fmaf(t[g], s[i], acc[g][i]);
+            for (int g = G - NA; g < G; ++g) {
+                const f32x2 tt = pack2(t[g], t[g]);   // uniform: becomes the UR.F32 broadcast operand
+#pragma unroll
+                for (int i = 0; i < ZB / 2; ++i) acc.v[g][i] = fma2(tt, s2[i], acc.v[g][i]);
+            }
+        } else {
+#pragma unroll
+            for (int g = G - NA; g < G; ++g)
+#pragma unroll
+                for (int i = 0; i < ZB; ++i) acc.v[g][i] = fmaf(t[g], s[i], acc.v[g][i]);
+        }
     }
 }
 
 // acc[g][i] = num_{slot g}[zb + i] for the profiles of group `grp`; wrow points at c[zb] of this lane.
 // The half-lengths are padded to multiples of ZB with zero taps (host side), so the number of active
 // slots is constant over a block of ZB distances: one table lookup and one switch per block.
-template <int G>
+template <int G, bool PK>
 __device__ __forceinline__ void fold_group(const float *__restrict__ wrow, const FoldDict &d, int grp,
-                                           float (&acc)[G][ZB]) {
+                                           Acc<G, PK> &acc) {
     constexpr int GP = (G + 3) / 4 * 4;
+    // G = 10: one code path (all slots; taps past a profile's half-length are zero).  Measured with the packed
+    // kernel as well: per-NA variants {1,2,4,7,10} execute 14 % fewer FFMA2s and run 2 % SLOWER (9.82 vs 9.63 ms,
+    // Dico_FWHM_2_12) - the kernel is bound by latency at 3 warps per scheduler, not by the FMA pipe.
     constexpr bool FULL_ONLY = G > 3;
     const float4 *t4 = c_ftaps + (d.toff[grp] >> 2);
     float F[ZB], B[ZB];
@@ -117,10 +168,19 @@ __device__ __forceinline__ void fold_group(const float *__restrict__ wrow, const
             const float4 v = t4[q];
             t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
         }
+        if constexpr (PK) {
 #pragma unroll
-        for (int g = 0; g < G; ++g)
+            for (int g = 0; g < G; ++g) {
+                const f32x2 tt = pack2(t[g], t[g]);
 #pragma unroll
-            for (int i = 0; i < ZB; ++i) acc[g][i] = t[g] * F[i];  // centre tap (0 for empty slots)
+                for (int i = 0; i < ZB / 2; ++i) acc.v[g][i] = mul2(tt, pack2(F[2 * i], F[2 * i + 1]));
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int i = 0; i < ZB; ++i) acc.v[g][i] = t[g] * F[i];  // centre tap (0 for empty slots)
+        }
     }
     t4 += GP / 4;  // distance 1
     const float *wf = wrow + ZB * 32, *wb = wrow - 32;
@@ -130,12 +190,12 @@ __device__ __forceinline__ void fold_group(const float *__restrict__ wrow, const
         if (FULL_ONLY) {
             // one code path (all slots; taps past a profile's half-length are zero): the loop body stays
             // resident in the instruction cache, which matters more than the ~15 % extra FFMAs
-            fold_block<G, G>(wf, wb, t4, F, B, fn, bn, acc);
+            fold_block<G, G, PK>(wf, wb, t4, F, B, fn, bn, acc);
         } else {
             switch (d.nab[grp][blk]) {  // active slots in this block of distances (uniform)
-                case 1: fold_block<1, G>(wf, wb, t4, F, B, fn, bn, acc); break;
-                case 2: fold_block<(G >= 2 ? 2 : G), G>(wf, wb, t4, F, B, fn, bn, acc); break;
-                default: fold_block<G, G>(wf, wb, t4, F, B, fn, bn, acc); break;
+                case 1: fold_block<1, G, PK>(wf, wb, t4, F, B, fn, bn, acc); break;
+                case 2: fold_block<(G >= 2 ? 2 : G), G, PK>(wf, wb, t4, F, B, fn, bn, acc); break;
+                default: fold_block<G, G, PK>(wf, wb, t4, F, B, fn, bn, acc); break;
             }
         }
         wf += ZB * 32;
@@ -144,7 +204,7 @@ __device__ __forceinline__ void fold_group(const float *__restrict__ wrow, const
     }
 }
 
-template <int G, int NW, bool G2>
+template <int G, int NW, bool G2, bool PK>
 __global__ void __launch_bounds__(NW * 32, (G <= 3 ? 5 : 3))
 folded_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_constant__ FoldDict dict,
                   int nz, int wny, int wnx,                    // window (= K1 output) dims
@@ -251,8 +311,8 @@ folded_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_cons
 
 #pragma unroll 1
             for (int grp = 0; grp < dict.ngroups; ++grp) {
-                float acc[G][ZB];
-                fold_group<G>(wrow, dict, grp, acc);
+                Acc<G, PK> acc;
+                fold_group<G, PK>(wrow, dict, grp, acc);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     const int k = dict.k[grp][g];
@@ -275,7 +335,7 @@ folded_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_cons
                     }
 #pragma unroll
                     for (int i = 0; i < ZB; ++i) {
-                        const float t = acc[g][i] * r[i];
+                        const float t = acc.get(g, i) * r[i];
                         arg[i] = t > mx[i] ? k : arg[i];   // strict: the lowest k wins ties (lib_origin.py:1210)
                         mx[i] = fmaxf(mx[i], t);
                         mn[i] = fminf(mn[i], t);
@@ -397,14 +457,14 @@ int ogn_k2f_upload(ogn_ctx *ctx, ogn_uploader *up, const std::vector<float> &tab
     return up->add(sym, table.data(), table.size() * sizeof(float));
 }
 
-template <int G, int NW, bool G2 = false>
+template <int G, int NW, bool PK, bool G2 = false>
 static int launch_folded(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, ogn_window w,
                          const float *cube_fsf, int pitch, const uint8_t *mask, float *correl, float *correl_min,
                          uint8_t *profile, float *maxmap, float *minmap) {
     using namespace k2f;
     if (!G2 && st.gather2.dst)
-        return launch_folded<G, NW, true>(ctx, stream, st, w, cube_fsf, pitch, mask, correl, correl_min, profile, maxmap, minmap);
-    auto kern = folded_glr_kernel<G, NW, G2>;
+        return launch_folded<G, NW, PK, true>(ctx, stream, st, w, cube_fsf, pitch, mask, correl, correl_min, profile, maxmap, minmap);
+    auto kern = folded_glr_kernel<G, NW, G2, PK>;
     const FoldDict &d = *st.fold;
     const int wny = w.y1 - w.y0, wnx = w.x1 - w.x0;
     const size_t limit = 100 * 1024;
@@ -450,8 +510,12 @@ static int launch_folded(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup
 int ogn_k2f_launch(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, ogn_window w, const float *cube_fsf,
                    int pitch, const uint8_t *mask, float *correl, float *correl_min, uint8_t *profile, float *maxmap,
                    float *minmap) {
-    if (st.fold->G <= 3)
-        return launch_folded<3, 4>(ctx, stream, st, w, cube_fsf, pitch, mask, correl, correl_min, profile, maxmap, minmap);
-    return launch_folded<k2f::GMAX, 4>(ctx, stream, st, w, cube_fsf, pitch, mask, correl, correl_min, profile, maxmap,
-                                       minmap);
+    // OGN_K2F_SCALAR=1: scalar FFMAs instead of the packed FFMA2 form (diagnostic; both are parity-tested)
+    static const bool scalar = getenv("OGN_K2F_SCALAR") != nullptr;
+#define OGN_K2F(G_, PK_) launch_folded<G_, 4, PK_>(ctx, stream, st, w, cube_fsf, pitch, mask, correl, correl_min, profile, \
+                                                  maxmap, minmap)
+    if (st.fold->G <= 3) return scalar ? OGN_K2F(3, false) : OGN_K2F(3, true);
+    if (scalar) return OGN_K2F(k2f::GMAX, false);
+    return OGN_K2F(k2f::GMAX, true);
+#undef OGN_K2F
 }

@@ -31,6 +31,13 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
@@ -45,3 +52,6 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t b
 // NaN operands, which makes "ignore out-of-range neighbours" free for the extremum pass).
 int ogn_make_tile_map(ogn_ctx *ctx, CUtensorMap *map, const float *base, int nz, int ny, int nx, int pitch,
                       int box_x, int box_y, int box_z = 1, bool nan_fill = false);
+// 2-D tiled map over a [rows][cols] array of 1-byte or 4-byte elements; out-of-range elements read as zero.
+int ogn_make_map_2d(ogn_ctx *ctx, CUtensorMap *map, const void *base, int elem_bytes, uint64_t rows, uint64_t cols,
+                    uint64_t row_stride_bytes, int box_cols, int box_rows);

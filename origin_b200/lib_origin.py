@@ -186,6 +186,22 @@ def preprocess(cube_raw, var, mask, dct_order=10, dct_approx=False, allreduce=No
     m = _as_u8(mask)
     ctx = _ctx_for(raw, ctx)
     nz, ny, nx = raw.shape
+    out = dict(
+        cube_std=_empty_like_kind(raw, raw.shape, np.float32),
+        cont_dct=_empty_like_kind(raw, raw.shape, np.float32),
+        ima_std=_empty_like_kind(raw, (ny, nx), np.float64), ima_dct=_empty_like_kind(raw, (ny, nx), np.float64),
+        cont_sumsq=_empty_like_kind(raw, (ny, nx), np.float64), o2map=_empty_like_kind(raw, (ny, nx), np.float64),
+    )
+    if allreduce is None and owned is None:
+        # one device: both phases in one call, the per-wavelength mean stays on the device (device inputs:
+        # nothing synchronises, the images come back as device tensors too)
+        mean = _empty_like_kind(raw, (nz,), np.float64)
+        ctx.check(ctx.lib.ogn_preprocess(ctx.handle, ptr(raw), ptr(v), code, ptr(m), nz, ny, nx, int(dct_order),
+                                         int(bool(dct_approx)), ptr(mean), ptr(out['cube_std']), ptr(out['cont_dct']),
+                                         ptr(out['ima_std']), ptr(out['ima_dct']), ptr(out['cont_sumsq']),
+                                         ptr(out['o2map'])))
+        out['mean_lambda'] = mean
+        return out
     lsum = np.zeros(nz)
     lcnt = np.zeros(nz)
     win = None if owned is None else np.ascontiguousarray(owned, dtype=np.int32)
@@ -195,12 +211,6 @@ def preprocess(cube_raw, var, mask, dct_order=10, dct_approx=False, allreduce=No
         allreduce(lsum, lcnt)
     with np.errstate(invalid='ignore', divide='ignore'):
         mean = lsum / lcnt                      # NaN for fully masked planes, as np.nanmean
-    out = dict(
-        cube_std=_empty_like_kind(raw, raw.shape, np.float32),
-        cont_dct=_empty_like_kind(raw, raw.shape, np.float32),
-        ima_std=np.empty((ny, nx)), ima_dct=np.empty((ny, nx)),
-        cont_sumsq=np.empty((ny, nx)), o2map=np.empty((ny, nx)),
-    )
     ctx.check(ctx.lib.ogn_preprocess_finish(ctx.handle, ptr(mean), ptr(out['cube_std']), ptr(out['cont_dct']),
                                             ptr(out['ima_std']), ptr(out['ima_dct']), ptr(out['cont_sumsq']),
                                             ptr(out['o2map'])))

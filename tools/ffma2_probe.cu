@@ -21,6 +21,8 @@ __constant__ float ct[256];
 // MODE 5: MODE 0 + one FMNMX per 4 FFMA
 // MODE 6: FFMA2 with all-register operands (tap pair in registers)
 // MODE 7: MODE 1 + one FADD2 per 8 FFMA2  (the folded-sample adds)
+// MODE 8: FFMA2 with the tap in a VECTOR register, broadcast form (Rt.F32): K1's weights come from LDS
+// MODE 9: scalar FFMA with the tap in a vector register (what K1 issues today)
 template <int MODE>
 __global__ void __launch_bounds__(128) probe(float *out, int iters, const float *in) {
     __shared__ float sm[1024];
@@ -31,7 +33,10 @@ __global__ void __launch_bounds__(128) probe(float *out, int iters, const float 
 #pragma unroll
     for (int i = 0; i < NS; ++i) s[i] = in[threadIdx.x + 32 * i];
     float mx = -1e30f;
-    if (MODE == 0 || MODE == 4 || MODE == 5) {
+    if (MODE == 0 || MODE == 4 || MODE == 5 || MODE == 9) {
+        float tv[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) tv[g] = in[g * 3 + threadIdx.x];
         float acc[NG][NS];
 #pragma unroll
         for (int g = 0; g < NG; ++g)
@@ -42,7 +47,7 @@ __global__ void __launch_bounds__(128) probe(float *out, int iters, const float 
             for (int j = 0; j < 4; ++j) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    const float t = ct[(it * 4 + j) % 16 * NG + g];
+                    const float t = MODE == 9 ? tv[g] : ct[(it * 4 + j) % 16 * NG + g];
 #pragma unroll
                     for (int i = 0; i < NS; ++i) acc[g][i] = fmaf(t, s[i], acc[g][i]);
                     if (MODE == 4) s[g % NS] = sm[(it * 4 + j + g * 32 + threadIdx.x) & 1023];
@@ -66,6 +71,9 @@ __global__ void __launch_bounds__(128) probe(float *out, int iters, const float 
 #pragma unroll
         for (int i = 0; i < NS / 2; ++i) s2[i] = pk(s[2 * i], s[2 * i + 1]);
         u64 treg[NG];
+        float tv[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) tv[g] = in[g * 3 + threadIdx.x];
 #pragma unroll
         for (int g = 0; g < NG; ++g) treg[g] = pk(in[g + threadIdx.x], in[g + 1 + threadIdx.x]);
         for (int it = 0; it < iters; ++it) {
@@ -74,7 +82,7 @@ __global__ void __launch_bounds__(128) probe(float *out, int iters, const float 
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     const float t = ct[(it * 4 + j) % 16 * NG + g];
-                    const u64 tt = MODE == 6 ? treg[g] : pk(t, t);
+                    const u64 tt = MODE == 6 ? treg[g] : (MODE == 8 ? pk(tv[g], tv[g]) : pk(t, t));
 #pragma unroll
                     for (int i = 0; i < NS / 2; ++i) acc[g][i] = fma2(tt, s2[i], acc[g][i]);
                     if (MODE == 2) {
@@ -141,7 +149,9 @@ int main() {
         printf("\"ffma_uniform_lds_1_per_8\": %.2f, ", run<4>(out, in, sms, bps));
         printf("\"ffma_uniform_fmnmx_1_per_4\": %.2f, ", run<5>(out, in, sms, bps));
         printf("\"ffma2_reg\": %.2f, ", run<6>(out, in, sms, bps));
-        printf("\"ffma2_uniform_fadd2_1_per_10\": %.2f}%s", run<7>(out, in, sms, bps), bps < 12 ? ", " : "");
+        printf("\"ffma2_uniform_fadd2_1_per_10\": %.2f, ", run<7>(out, in, sms, bps));
+        printf("\"ffma2_vector_scalar_tap\": %.2f, ", run<8>(out, in, sms, bps));
+        printf("\"ffma_vector_tap\": %.2f}%s", run<9>(out, in, sms, bps), bps < 12 ? ", " : "");
     }
     printf("}\n");
     return 0;

@@ -12,9 +12,12 @@ mask = (torch.rand(shape, device='cuda', generator=g) < 0.002).to(torch.uint8)
 mask[:, :8, :] = 1
 ctx = lib_origin.default_context()
 ctx.timing(True)
-for rep in range(3):
+for rep in range(4):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     out = lib_origin.preprocess(raw, var, mask, 10, False)
-    torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    print('step01 %.2f ms  (%.1f Mspaxel/s)  %s' % (dt * 1e3, shape[1] * shape[2] / dt / 1e6,
+    t1 = time.perf_counter()
+    torch.cuda.synchronize(); t2 = time.perf_counter()
+    ext, _, _ = lib_origin.local_extrema(out['cube_std'], out['cube_std'], mask, 3, capacity=shape[0] * shape[1] * shape[2] // 16)
+    torch.cuda.synchronize(); t3 = time.perf_counter()
+    print('preprocess: host %.2f ms, done %.2f ms; extrema %.2f ms  %s' % ((t1 - t0) * 1e3, (t2 - t0) * 1e3, (t3 - t2) * 1e3,
           ' '.join('%s=%.3f' % kv for kv in ctx.timing_report())), flush=True)
