@@ -403,7 +403,16 @@ class Job:
         self.gather, self.gather_mode = None, None
         if self.world > 1:
             try:
-                self.gather = ogd.PeerGather(env.ctx, self.shape, dst=0, slots=2)
+                # the peer copies are enqueued after the allreduce, which aligns the ranks: they then take turns on rank
+                # 0's NVLink ingress (OGN_BENCH_GATHER_EARLY=1: copies start right behind K2, all at once;
+                # OGN_BENCH_STAGGER_US: length of a turn, 0 = off)
+                self.gather = ogd.PeerGather(env.ctx, self.shape, dst=0, slots=2,
+                                             dst_only=not os.environ.get('OGN_BENCH_GATHER_EARLY'))
+                if not os.environ.get('OGN_BENCH_GATHER_EARLY'):
+                    t_ = self.tile
+                    us = os.environ.get('OGN_BENCH_STAGGER_US')
+                    self.gather.stagger(nz * (t_.y1 - t_.y0) * (t_.x1 - t_.x0) * 4,
+                                        microseconds=float(us) if us is not None else None)
                 self.gather_mode = ('owned correl tiles stored into rank 0 over NVLink peer memory '
                                     '(ogn_scatter_tile, CUDA IPC)')
             except Exception as exc:  # noqa: BLE001
@@ -494,9 +503,20 @@ class Job:
         launches = env.ctx.launch_count - launches0
         folded = env.ctx.fsf_folded
         stages = {}
+        timeline = []
         for name, ms in env.ctx.timing_report():
+            if '@' in name:                      # OGN_TIMING_OFFSETS=1: "stage@start_ms" -> per-rank timeline on stderr
+                name, off = name.split('@')
+                timeline.append((float(off), name, ms))
             stages.setdefault(name, []).append(ms)
+        if timeline:
+            timeline.sort()
+            t_ref = [t for t in timeline if t[1] == 'step05_span'][2][0] if len([t for t in timeline if t[1] == 'step05_span']) > 6 else 0.0
+            sys.stderr.write('rank %d timeline (ms from the third timed step): %s\n' % (self.rank, ' '.join(
+                '%s[%.2f+%.2f]' % (n, o - t_ref, d) for o, n, d in timeline if 0 <= o - t_ref < 8.0
+                and n in ('step05_span', 'peer_scatter', 'k1_fsf_correlate'))))
         env.ctx.timing(False)
+        per_rank = None
         if self.world > 1:
             t = torch.tensor([ms_total], device=env.dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -504,11 +524,13 @@ class Job:
             lt = torch.tensor([launches], device=env.dev, dtype=torch.int64)
             dist.all_reduce(lt, op=dist.ReduceOp.SUM)
             launches = int(lt.item())
+            per_rank = [None] * self.world
+            dist.all_gather_object(per_rank, {k: round(float(np.mean(v)), 4) for k, v in stages.items()})
         nz, ny, nx = self.shape
         ms_step = ms_total / steps
         units = nz * ny * nx * self.nprof / 1e9
         return dict(ms_per_step=ms_step, value=units / (ms_step * 1e-3), units=units, launches=launches,
-                    stages=stages, folded=folded, clocks=clocks)
+                    stages=stages, folded=folded, clocks=clocks, per_rank_stages=per_rank)
 
     # ---- end to end through the host API with pinned host buffers ------------------------------
     def e2e(self, steps):
@@ -957,6 +979,7 @@ def main_gpu(args):
         step_fp32_tflops=total_flops / (ms_step * 1e-3) / 1e12,
         step_fp32_frac=(total_flops / (ms_step * 1e-3) / 1e12 / fp32_peak) if fp32_peak else None,
         fma_peak=fp32, parity_spot=spot, sharded_parity=sharded, configs=configs or None,
+        per_rank_stage_ms=r['per_rank_stages'],
     )
     if world == 1 and not args.no_cpu:
         # the reference arm in a child process (no fork of a CUDA process), one bounded step

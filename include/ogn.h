@@ -220,10 +220,16 @@ OGN_API int ogn_peer_free(ogn_ctx *ctx, void *dev_ptr);
 OGN_API int ogn_peer_open(ogn_ctx *ctx, const unsigned char *handle64, void **dev_ptr);
 OGN_API int ogn_peer_close(ogn_ctx *ctx, void *dev_ptr);
 OGN_API int ogn_scatter_tile(ogn_ctx *ctx, const float *src, int nz, int ny, int nx, const int *tile, float *dst);
-/* On the rank that owns the gathered cube: make the next ogn_step05_tile call store the window it owns
- * of correl into `dst` as well (fused into the spectral kernel), so that rank needs no ogn_scatter_tile of
- * its own tile.  One-shot. */
+/* Make the next ogn_step05_tile call deliver the window it owns of correl into `dst` by itself.  On the rank
+ * that owns the gathered cube (`dst` from ogn_peer_alloc) the spectral kernel stores the owned voxels there as
+ * well; on the other ranks (`dst` from ogn_peer_open) the copy of ogn_scatter_tile is enqueued right behind the
+ * spectral kernel, before the extremum pass, so it overlaps the rest of the step and the next one.  One-shot. */
 OGN_API int ogn_set_local_gather(ogn_ctx *ctx, float *dst);
+/* Stagger: every following ogn_scatter_tile of this context waits `microseconds` on the device (on the copy's
+ * stream, not the context's) before it starts.  The ranks share the destination GPU's NVLink ingress; taking
+ * turns (delay = turn x time of one tile on the link alone) keeps a source's memory system free of stalled
+ * remote stores except during its own turn.  0 switches it off. */
+OGN_API int ogn_peer_set_delay(ogn_ctx *ctx, int microseconds);
 OGN_API int ogn_peer_join(ogn_ctx *ctx);
 OGN_API int ogn_peer_sync(ogn_ctx *ctx);
 

@@ -34,6 +34,7 @@ SIGNATURES = {
     'ogn_peer_close': (c_int, [c_void_p, c_void_p]),
     'ogn_scatter_tile': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'ogn_set_local_gather': (c_int, [c_void_p, c_void_p]),
+    'ogn_peer_set_delay': (c_int, [c_void_p, c_int]),
     'ogn_peer_join': (c_int, [c_void_p]),
     'ogn_peer_sync': (c_int, [c_void_p]),
     'ogn_timing_enable': (c_int, [c_void_p, c_int]),
@@ -150,7 +151,7 @@ class Context:
 
     def timing_report(self):
         """``[(stage, ms), ...]`` for the stages timed since the last report."""
-        buf = ctypes.create_string_buffer(1 << 16)
+        buf = ctypes.create_string_buffer(1 << 20)
         self.check(self.lib.ogn_timing_report(self.handle, buf, len(buf)))
         out = []
         for item in buf.value.decode().split(';'):

@@ -131,12 +131,20 @@ extern "C" int ogn_timing_enable(ogn_ctx *ctx, int on) {
 extern "C" int ogn_timing_report(ogn_ctx *ctx, char *buf, size_t size) {
     if (!ctx || !buf || size == 0) return OGN_ERR_ARG;
     OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->peer_stream) OGN_CUDA(cudaStreamSynchronize(ctx->peer_stream));   // peer_scatter entries live there
     std::string out;
+    static const bool with_offsets = getenv("OGN_TIMING_OFFSETS") != nullptr;   // "name@start_ms:duration_ms" (timelines)
+    cudaEvent_t first = ctx->timings.empty() ? nullptr : ctx->timings.front().start;
     for (auto &e : ctx->timings) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, e.start, e.stop) == cudaSuccess) {
-            char tmp[160];
-            snprintf(tmp, sizeof(tmp), "%s:%.6f;", e.name.c_str(), ms);
+            char tmp[200];
+            float off = 0.f;
+            if (with_offsets && cudaEventElapsedTime(&off, first, e.start) == cudaSuccess)
+                snprintf(tmp, sizeof(tmp), "%s@%.4f:%.6f;", e.name.c_str(), off, ms);
+            else
+                snprintf(tmp, sizeof(tmp), "%s:%.6f;", e.name.c_str(), ms);
+            cudaGetLastError();
             out += tmp;
         } else {
             cudaGetLastError();

@@ -65,6 +65,8 @@ struct ogn_ctx {
     bool stage_pending = false;
     int64_t *res_h = nullptr, *res_d = nullptr;    // 32 mapped int64 result slots
     float *local_gather = nullptr;                 // ogn_set_local_gather: consumed by the next ogn_step05_tile
+    int peer_delay_us = 0;                         // ogn_peer_set_delay
+    bool local_gather_is_peer = false;             // ... it is another device's buffer (mapped with ogn_peer_open)
 };
 
 // Batches small host -> device copies into ONE kernel that reads a mapped pinned staging buffer over

@@ -53,6 +53,16 @@ scatter_tile_kernel(const float *__restrict__ src, int ny, int nx, int oy0, int 
     }
 }
 
+// device-side wait on the peer stream (one thread): staggers the ranks' copies into the shared destination
+__global__ void delay_kernel(unsigned long long ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(2000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < ns);
+}
+
 int peer_stream(ogn_ctx *ctx, cudaStream_t *out) {
     if (!ctx->peer_stream) OGN_CUDA(cudaStreamCreateWithFlags(&ctx->peer_stream, cudaStreamNonBlocking));
     *out = ctx->peer_stream;
@@ -135,6 +145,10 @@ extern "C" int ogn_scatter_tile(ogn_ctx *ctx, const float *src, int nz, int ny, 
     if (!ctx->peer_ev_begin) OGN_CUDA(cudaEventCreateWithFlags(&ctx->peer_ev_begin, cudaEventDisableTiming));
     OGN_CUDA(cudaEventRecord(ctx->peer_ev_begin, ctx->stream));
     OGN_CUDA(cudaStreamWaitEvent(ps, ctx->peer_ev_begin, 0));
+    if (ctx->peer_delay_us > 0) {
+        delay_kernel<<<1, 1, 0, ps>>>((unsigned long long)ctx->peer_delay_us * 1000ull);
+        OGN_LAUNCH_CHECK("delay_kernel");
+    }
     const int oh = oy1 - oy0, ow = ox1 - ox0;
     const long long nrow = (long long)nz * oh;
     const bool vec = ow % 4 == 0 && nx % 4 == 0 && gnx % 4 == 0 && ox0 % 4 == 0 && (gx0 + ox0) % 4 == 0 &&
@@ -147,6 +161,14 @@ extern "C" int ogn_scatter_tile(ogn_ctx *ctx, const float *src, int nz, int ny, 
     // from 7 peers, and no SM is taken from the main stream's kernels).  OGN_SCATTER_KERNEL=1 selects the
     // SM copy kernel instead (703 GB/s with 148 blocks, but it competes with K1 for registers).
     static const bool use_dma = getenv("OGN_SCATTER_KERNEL") == nullptr;
+    // stage timing (ogn_timing_enable): the copy's own duration on the peer stream
+    ogn_timing_entry t_copy;
+    if (ctx->timing) {
+        t_copy.name = "peer_scatter";
+        cudaEventCreate(&t_copy.start);
+        cudaEventCreate(&t_copy.stop);
+        cudaEventRecord(t_copy.start, ps);
+    }
     if (use_dma) {
         cudaMemcpy3DParms p3 = {};
         p3.srcPtr = make_cudaPitchedPtr(const_cast<float *>(src), (size_t)nx * 4, nx, ny);
@@ -156,11 +178,25 @@ extern "C" int ogn_scatter_tile(ogn_ctx *ctx, const float *src, int nz, int ny, 
         p3.extent = make_cudaExtent((size_t)ow * 4, oh, nz);
         p3.kind = cudaMemcpyDefault;
         OGN_CUDA(cudaMemcpy3DAsync(&p3, ps));
-    } else if (vec)
+    } else if (vec) {
+        // a copy block holds no shared memory; without a stated preference the driver configures an idle SM it
+        // lands on for maximum L1, and the TGLR kernels (38-48 KB of shared memory per block) then cannot place a
+        // block there until the copy block has left - measured as a full serialisation of the next step behind the
+        // copy.  Asking for the largest shared-memory carve-out keeps the SM usable for them.
+        static bool carve_set = false;
+        if (!carve_set) {
+            cudaFuncSetAttribute(scatter_tile_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(scatter_tile_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carve_set = true;
+        }
         scatter_tile_kernel<4><<<blocks, 256, 0, ps>>>(src, ny, nx, oy0, ox0, oh, ow, dst, gny, gnx, gy0 + oy0, gx0 + ox0, nrow);
-    else
+    } else
         scatter_tile_kernel<1><<<blocks, 256, 0, ps>>>(src, ny, nx, oy0, ox0, oh, ow, dst, gny, gnx, gy0 + oy0, gx0 + ox0, nrow);
     if (!use_dma) OGN_LAUNCH_CHECK("scatter_tile_kernel");
+    if (ctx->timing) {
+        cudaEventRecord(t_copy.stop, ps);
+        ctx->timings.push_back(t_copy);
+    }
     // ... and whoever overwrites src next on the main stream waits for it (ogn_wait_readers)
     cudaEvent_t done = nullptr;
     auto it = ctx->readers.find(src);
@@ -188,6 +224,9 @@ extern "C" int ogn_set_local_gather(ogn_ctx *ctx, float *dst) {
     if (!ctx) return OGN_ERR_ARG;
     if (dst && !ogn_is_device_ptr(dst)) return ogn_fail(ctx, OGN_ERR_ARG, "ogn_set_local_gather: dst must be device memory");
     ctx->local_gather = dst;
+    ctx->local_gather_is_peer = false;
+    // a buffer of ogn_peer_open lives on another GPU (cudaPointerGetAttributes reports IPC mappings as local)
+    if (dst) ctx->local_gather_is_peer = std::find(ctx->peer_mapped.begin(), ctx->peer_mapped.end(), (void *)dst) != ctx->peer_mapped.end();
     return OGN_OK;
 }
 
@@ -217,5 +256,16 @@ int ogn_wait_readers(ogn_ctx *ctx, cudaStream_t stream, const void *buf) {
     if (!buf || ctx->readers.empty()) return OGN_OK;
     auto it = ctx->readers.find(buf);
     if (it != ctx->readers.end()) OGN_CUDA(cudaStreamWaitEvent(stream, it->second, 0));
+    return OGN_OK;
+}
+
+// Every following ogn_scatter_tile of this context waits `microseconds` on the device (peer stream) before its copy.
+// All ranks push into ONE destination GPU, whose NVLink ingress they share: pushing at the same time, every source
+// keeps its memory system full of stalled remote stores for the whole gather, and its own latency-bound kernels
+// slow down several times (measured: a 0.02 ms kernel with atomics took 0.75 ms).  Staggered by rank - each source
+// alone on the link for its turn - the gather lasts as long but a source is congested only during its own turn.
+extern "C" int ogn_peer_set_delay(ogn_ctx *ctx, int microseconds) {
+    if (!ctx || microseconds < 0) return ctx ? ogn_fail(ctx, OGN_ERR_ARG, "ogn_peer_set_delay: negative delay") : OGN_ERR_ARG;
+    ctx->peer_delay_us = microseconds;
     return OGN_OK;
 }

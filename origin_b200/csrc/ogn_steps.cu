@@ -126,7 +126,12 @@ int step05_run(ogn_ctx *ctx, const Step05Args &a, const int *tile) {
     OGN_TRY(ogn_tglr_setup(ctx, nz, ny, nx, &place, a.nfields, a.fsf, a.psize, a.weights, a.taps, a.tap_offsets,
                            a.nprof, true, &st));
     OGN_HT("setup done");
-    if (tile && ctx->local_gather) {   // this rank owns the gathered cube: K2 stores its owned voxels there as well
+    float *peer_dst = nullptr;
+    if (tile && ctx->local_gather && ctx->local_gather_is_peer) {
+        // the gathered cube lives on another GPU: the owned window of correl is copied there as soon as the spectral
+        // kernel has produced it (before the extremum pass and whatever the caller enqueues next), on the peer stream
+        peer_dst = ctx->local_gather;
+    } else if (tile && ctx->local_gather) {   // this rank owns the gathered cube: K2 stores its owned voxels there as well
         st.gather2.dst = ctx->local_gather;
         st.gather2.ny = place.gny; st.gather2.nx = place.gnx; st.gather2.dy = place.gy0; st.gather2.dx = place.gx0;
         st.gather2.y0 = owned.y0; st.gather2.y1 = owned.y1; st.gather2.x0 = owned.x0; st.gather2.x1 = owned.x1;
@@ -162,6 +167,7 @@ int step05_run(ogn_ctx *ctx, const Step05Args &a, const int *tile) {
     OGN_TRY(ogn_tglr_window(ctx, ctx->stream, st, d_cube, (const uint8_t *)d_mask, w, (float *)d_correl,
                             (float *)d_cmin, (uint8_t *)d_prof, (float *)d_maxmap, (float *)d_minmap));
     OGN_HT("tglr enqueued");
+    if (peer_dst) OGN_TRY(ogn_scatter_tile(ctx, (const float *)d_correl, nz, ny, nx, tile, peer_dst));
     OGN_TRY(ogn_output_commit(ctx, a.correl, d_correl, vol * 4));
     OGN_TRY(ogn_output_commit(ctx, a.correl_min, d_cmin, vol * 4));
     OGN_TRY(ogn_output_commit(ctx, a.profile, d_prof, vol));

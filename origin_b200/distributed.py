@@ -132,11 +132,11 @@ class PeerGather:
     each other's memory; callers may then fall back to :func:`gather_owned`.
     """
 
-    def __init__(self, ctx, global_shape, dst=0, slots=1, group=None):
+    def __init__(self, ctx, global_shape, dst=0, slots=1, group=None, dst_only=False):
         import ctypes
         import torch
         import torch.distributed as dist
-        self.ctx, self.dst, self.group, self.dist = ctx, dst, group, dist
+        self.ctx, self.dst, self.group, self.dist, self.dst_only = ctx, dst, group, dist, dst_only
         self.rank = dist.get_rank(group)
         self.shape = tuple(int(s) for s in global_shape)
         self.nbytes = int(np.prod(self.shape)) * 4
@@ -171,13 +171,27 @@ class PeerGather:
             self.close()
             raise err if err is not None else RuntimeError('peer mapping failed on another rank')
         self._torch = torch
+        self.stagger_us = 0
+
+    def stagger(self, tile_bytes, link_gbs=650.0, microseconds=None):
+        """Let the source ranks take turns on the destination's NVLink ingress: rank r (counted among the sources)
+        starts its copy r turns after it was enqueued, a turn being the time one tile needs on the link alone
+        (``tile_bytes / link_gbs``, or ``microseconds``).  Call it on every rank; it relies on the copies being
+        enqueued at about the same time everywhere (e.g. right after a collective)."""
+        world = self.dist.get_world_size(self.group)
+        turn = microseconds if microseconds is not None else tile_bytes / (link_gbs * 1e3)
+        order = [r for r in range(world) if r != self.dst]
+        delay = int(round(order.index(self.rank) * turn)) if self.rank != self.dst else 0
+        self.stagger_us = delay
+        self.ctx.check(self.ctx.lib.ogn_peer_set_delay(self.ctx.handle, delay))
 
     def attach(self, slot=0):
-        """Call before ``step05(..., tile=...)``: on the destination rank the spectral kernel then stores the
-        voxels that rank owns straight into slot ``slot`` (``ogn_set_local_gather``) and :meth:`scatter` has
-        nothing left to do there; a no-op on the other ranks."""
+        """Call before ``step05(..., tile=...)``: the step then delivers the tile itself (``ogn_set_local_gather``)
+        and :meth:`scatter` has nothing left to do — on the destination rank the spectral kernel stores the voxels
+        that rank owns straight into slot ``slot``; on the other ranks the peer copy starts right behind the
+        spectral kernel (``dst_only=True`` in the constructor restricts this to the destination rank)."""
         self._attached = None
-        if self.rank == self.dst:
+        if self.rank == self.dst or not self.dst_only:
             self.ctx.check(self.ctx.lib.ogn_set_local_gather(self.ctx.handle, self.ptrs[slot]))
             self._attached = slot
 
@@ -185,8 +199,8 @@ class PeerGather:
         """Enqueue the copy of the owned window of ``cube_tile`` (``[nz][th][tw]`` float32 device tensor)
         into slot ``slot`` of the destination; returns immediately."""
         from ._lib import ptr
-        if getattr(self, '_attached', None) == slot and self.rank == self.dst:
-            self._attached = None      # already written by the fused stores of this step
+        if getattr(self, '_attached', None) == slot:
+            self._attached = None      # already delivered by the step itself (fused stores / copy behind K2)
             return
         nz, th, tw = cube_tile.shape
         gny, gnx = global_hw
@@ -212,6 +226,8 @@ class PeerGather:
         return self._torch.as_tensor(_DeviceBuffer(self.ptrs[slot], self.shape), device=dev)
 
     def close(self):
+        if self.stagger_us:
+            self.ctx.lib.ogn_peer_set_delay(self.ctx.handle, 0)
         # remote copies into the destination's buffers may still be in flight: every rank first waits for its
         # own copies, then all ranks meet, and only then are mappings closed and the owned buffers freed
         if self._mapped or self._owned:
