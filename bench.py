@@ -534,6 +534,10 @@ class Job:
 
     # ---- end to end through the host API with pinned host buffers ------------------------------
     def e2e(self, steps):
+        """step05 -> step06 counts -> step07 extraction through the host API, as the fused step mirror calls it
+        (origin_b200.steps._run_compute_tglr): float32 cube and bit-packed mask in pinned HOST memory in; correl,
+        the two maps, the extremum lists, the per-threshold counts and the detection rows back on the HOST;
+        correl_min and profile stay on the GPU behind lazy step products (fetched only if somebody reads them)."""
         import torch.distributed as dist
         from origin_b200 import _lib
         torch, env, lo = self.torch, self.env, self.lo
@@ -541,24 +545,39 @@ class Job:
         ty, tx = shape[1], shape[2]
         ny, nx = self.shape[1], self.shape[2]
         cube_h = _lib.pinned_empty(shape, np.float32)
-        mask_h = _lib.pinned_empty(shape, np.uint8)
         cube_h[...] = self.cube.cpu().numpy()
-        mask_h[...] = self.mask.cpu().numpy()
         cap = self.cap
-        out_h = dict(correl=_lib.pinned_empty(shape, np.float32), correl_min=_lib.pinned_empty(shape, np.float32),
-                     profile=_lib.pinned_empty(shape, np.uint8), maxmap=_lib.pinned_empty((ty, tx), np.float32),
+        single = self.world == 1
+        mask_np = self.mask.cpu().numpy()
+        if single:           # packed once per session (np.packbits), uploaded every step
+            packed = np.packbits(mask_np.reshape(-1))
+            mask_h = _lib.pinned_empty(packed.shape, np.uint8)
+            mask_h[...] = packed
+        else:                # tile mode takes the byte mask
+            mask_h = _lib.pinned_empty(shape, np.uint8)
+            mask_h[...] = mask_np
+        out_h = dict(correl=_lib.pinned_empty(shape, np.float32), maxmap=_lib.pinned_empty((ty, tx), np.float32),
                      minmap=_lib.pinned_empty((ty, tx), np.float32),
                      max_index=_lib.pinned_empty((cap,), np.int64), max_value=_lib.pinned_empty((cap,), np.float32),
                      min_index=_lib.pinned_empty((cap,), np.int64), min_value=_lib.pinned_empty((cap,), np.float32))
-        tile_arg = (self.tile, (ny, nx)) if self.world > 1 else None
+        dev = torch.device('cuda', env.ctx.device)
+        # device-resident products are allocated once, like the step mirror's (they are outputs, not traffic)
+        out_h['correl_min'] = torch.empty(shape, dtype=torch.float32, device=dev)
+        out_h['profile'] = torch.empty(shape, dtype=torch.uint8, device=dev)
+        tile_arg = (self.tile, (ny, nx)) if not single else None
 
         def step_e2e():
-            res = lo.step05(cube_h, self.fsf_host, None, self.profs, mask_h, 3, 1e-8, True, out=out_h, ctx=env.ctx,
-                            tile=tile_arg)
-            n1, n0 = lo.purity_counts(res['extrema'], None, THRESHOLDS, env.ctx)
-            if self.world > 1:
+            if single:
+                res = lo.step05(cube_h, self.fsf_host, None, self.profs, None, 3, 1e-8, True, out=out_h, ctx=env.ctx,
+                                mask_bits=mask_h)
+            else:
+                res = lo.step05(cube_h, self.fsf_host, None, self.profs, mask_h, 3, 1e-8, True, out=out_h, ctx=env.ctx,
+                                tile=tile_arg)
+            n1, n0 = lo.purity_counts(res['extrema'], None, THRESHOLDS, env.ctx)            # step06 counting loop
+            if not single:
                 self.reducer.sum(np.concatenate([n1, n0]))
-            return res
+            rows = lo.threshold_rows(res['extrema'], 8.0, res['profile'], 'max', env.ctx)   # step07 extraction
+            return res, rows
 
         step_e2e()
         self.sync_all()
@@ -567,7 +586,7 @@ class Job:
         t0 = time.perf_counter()
         e0.record()
         for _ in range(n_e2e):
-            res = step_e2e()
+            res, rows = step_e2e()
         e1.record()
         self.sync_all()
         wall = (time.perf_counter() - t0) * 1e3 / n_e2e
@@ -578,15 +597,21 @@ class Job:
             ms_e2e = float(t.item())
         n1c, n0c = res['extrema'].counts
         h2d = cube_h.nbytes + mask_h.nbytes + self.fsf_host.nbytes
-        d2h = (out_h['correl'].nbytes + out_h['correl_min'].nbytes + out_h['profile'].nbytes
-               + out_h['maxmap'].nbytes + out_h['minmap'].nbytes + 12 * (n1c + n0c) + 16)
+        d2h = (out_h['correl'].nbytes + out_h['maxmap'].nbytes + out_h['minmap'].nbytes + 12 * (n1c + n0c) + 16
+               + 13 * len(rows['z0']) + 8 * 2 * len(THRESHOLDS))
         nz, gny, gnx = self.shape
         units = nz * gny * gnx * self.nprof / 1e9
         return dict(value=units / (ms_e2e * 1e-3), unit='Gvoxel.profiles/s', ms_per_step=ms_e2e,
                     h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h), steps=n_e2e,
-                    api='origin_b200.lib_origin.step05 -> ogn_step05%s (pinned host numpy in/out) + purity_counts%s'
-                        % ('_tile' if self.world > 1 else '', ' + allreduce' if self.world > 1 else ''),
-                    bytes_note='per rank' if self.world > 1 else None)
+                    api='origin_b200.lib_origin.step05 -> %s (pinned host cube + %s mask in; correl, maps, lists out) + '
+                        'purity_counts%s + threshold_rows'
+                        % ('ogn_step05_bits' if single else 'ogn_step05_tile', 'bit-packed' if single else 'byte',
+                           '' if single else ' + allreduce'),
+                    lazy_on_device=['correl_min', 'profile', 'cube_local_max', 'cube_local_min'],
+                    lazy_note='these step products are fetched from the GPU only when read (origin_b200.steps.LazyProduct); '
+                              'fetching correl_min and profile as well adds %.2f GB of D2H per step'
+                              % ((self.cube.numel() * 5) / 1e9),
+                    n_detections=int(len(rows['z0'])), bytes_note='per rank' if self.world > 1 else None)
 
     # ---- parity on the benchmark cube itself -----------------------------------------------------
     def spot_points(self, ext_host, n_random=24, n_list=16):

@@ -179,6 +179,22 @@ OGN_API int ogn_step05(ogn_ctx *ctx,
                int64_t *min_index, float *min_value,
                int64_t capacity, int64_t *counts);
 
+/* ogn_step05 for a HOST cube with the mask given bit-packed: mask_bits = numpy.packbits of the flattened
+ * [nz][ny][nx] boolean mask (MSB first), 1/8 of the bytes on the PCIe link; it is unpacked on the device slab
+ * by slab.  nx must be a multiple of 8.  Every product may be a host buffer (copied back slab by slab while
+ * later slabs are computed) or a device buffer (written in place, e.g. products the caller fetches lazily). */
+OGN_API int ogn_step05_bits(ogn_ctx *ctx,
+                    const void *cube, int cube_dtype, int nz, int ny, int nx,
+                    int nfields, const double *const *fsf, int psize,
+                    const double *const *weights,
+                    const double *taps, const int *tap_offsets, int nprof,
+                    const uint8_t *mask_bits, int sz, int sy, int sx,
+                    float *correl, float *correl_min, uint8_t *profile,
+                    float *maxmap, float *minmap,
+                    int64_t *max_index, float *max_value,
+                    int64_t *min_index, float *min_value,
+                    int64_t capacity, int64_t *counts);
+
 /* ogn_step05 on one spatial tile of a larger field (multi-GPU runs).  `cube` is
  * the [nz][ny][nx] sub-cube cut from the field with its halo;
  *   tile = {gny, gnx, gy0, gx0, oy0, oy1, ox0, ox1}

@@ -15,6 +15,7 @@ struct Step05Args {
     const uint8_t *mask; int sz, sy, sx;
     float *correl, *correl_min; uint8_t *profile; float *maxmap, *minmap, *dense_max, *dense_min;
     int64_t *max_index; float *max_value; int64_t *min_index; float *min_value; int64_t capacity; int64_t *counts;
+    int mask_bits = 0;   // mask is bit-packed (numpy.packbits order, [nz][ny][nx] flattened), host memory
 };
 
 int get_event(ogn_ctx *ctx, size_t i, cudaEvent_t *ev) {
@@ -27,9 +28,29 @@ int get_event(ogn_ctx *ctx, size_t i, cudaEvent_t *ev) {
     return OGN_OK;
 }
 
-// Host cube in, host products out: the field is cut into slabs of image rows; the upload of slab
-// s+1, the K1/K2 pass on slab s and the download of the products of slab s-1 overlap on three streams.
-int step05_streamed(ogn_ctx *ctx, const Step05Args &a, const ogn_tglr_setup_t &st) {
+// out[i] = (bits[i >> 3] >> (7 - (i & 7))) & 1 for the voxels of `rows` image rows of every plane
+// (numpy.packbits order); one thread per output byte quad
+__global__ void unpack_mask_rows_kernel(const uint8_t *__restrict__ bits, uint8_t *__restrict__ out, int nz, size_t img,
+                                        size_t off, size_t count) {
+    const size_t per_plane = count / 4;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per_plane * nz) return;
+    const size_t z = i / per_plane, q = i - z * per_plane;
+    const size_t v = z * img + off + 4 * q;            // first voxel of the quad (a multiple of 4)
+    const unsigned byte = bits[v >> 3];
+    const unsigned sh = 4 - (unsigned)(v & 4);         // high nibble first
+    const unsigned nib = (byte >> sh) & 15u;
+    uchar4 o;
+    o.x = (nib >> 3) & 1u; o.y = (nib >> 2) & 1u; o.z = (nib >> 1) & 1u; o.w = nib & 1u;
+    *reinterpret_cast<uchar4 *>(out + v) = o;
+}
+
+// Host cube in, products to wherever the caller wants each of them (host: copied back slab by slab; device:
+// written in place by the kernels, e.g. the lazily fetched correl_min / profile of the step mirror): the field
+// is cut into slabs of image rows; the upload of slab s+1, the K1/K2 pass on slab s and the download of the
+// products of slab s-1 overlap on three streams.
+int step05_streamed(ogn_ctx *ctx, const Step05Args &a, const ogn_tglr_setup_t &st, ogn_window owned, ogn_place place,
+                    ogn_window w) {
     const int nz = a.nz, ny = a.ny, nx = a.nx;
     const size_t vol = (size_t)nz * ny * nx, img = (size_t)ny * nx, plane_b = img * 4;
     // Rows per slab.  The call is PCIe-bound (measured 57 GB/s one way, 46 GB/s each way when both directions
@@ -43,12 +64,15 @@ int step05_streamed(ogn_ctx *ctx, const Step05Args &a, const ogn_tglr_setup_t &s
     if (!ctx->h2d_stream) OGN_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
     if (!ctx->d2h_stream) OGN_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
     float *d_cube = nullptr, *d_correl = nullptr, *d_cmin = nullptr, *d_maxmap = nullptr, *d_minmap = nullptr;
-    uint8_t *d_mask = nullptr, *d_prof = nullptr;
+    uint8_t *d_mask = nullptr, *d_prof = nullptr, *d_bits = nullptr;
+    const bool correl_dev = a.correl && ogn_is_device_ptr(a.correl), cmin_dev = a.correl_min && ogn_is_device_ptr(a.correl_min);
+    const bool prof_dev = a.profile && ogn_is_device_ptr(a.profile);
     OGN_TRY(ogn_scratch_t(ctx, "cube", vol, &d_cube));
-    OGN_TRY(ogn_scratch_t(ctx, "s5_correl", vol, &d_correl));
-    OGN_TRY(ogn_scratch_t(ctx, "s5_correl_min", vol, &d_cmin));
-    if (a.profile) OGN_TRY(ogn_scratch_t(ctx, "s5_profile", vol, &d_prof));
+    if (correl_dev) d_correl = a.correl; else OGN_TRY(ogn_scratch_t(ctx, "s5_correl", vol, &d_correl));
+    if (cmin_dev) d_cmin = a.correl_min; else OGN_TRY(ogn_scratch_t(ctx, "s5_correl_min", vol, &d_cmin));
+    if (prof_dev) d_prof = a.profile; else if (a.profile) OGN_TRY(ogn_scratch_t(ctx, "s5_profile", vol, &d_prof));
     if (a.mask) OGN_TRY(ogn_scratch_t(ctx, "s5_mask", vol, &d_mask));
+    if (a.mask && a.mask_bits) OGN_TRY(ogn_scratch_t(ctx, "s5_mask_bits", (vol + 7) / 8 + 16, &d_bits));
     if (a.maxmap) OGN_TRY(ogn_scratch_t(ctx, "s5_maxmap", img, &d_maxmap));
     if (a.minmap) OGN_TRY(ogn_scratch_t(ctx, "s5_minmap", img, &d_minmap));
     OGN_TRY(ogn_tglr_init_maps(ctx, ctx->stream, d_maxmap, d_minmap, img));
@@ -64,9 +88,18 @@ int step05_streamed(ogn_ctx *ctx, const Step05Args &a, const ogn_tglr_setup_t &s
         const size_t off = (size_t)y0 * nx;
         OGN_CUDA(cudaMemcpy2DAsync(d_cube + off, plane_b, h_cube + off, plane_b, (size_t)rows * nx * 4, nz,
                                    cudaMemcpyHostToDevice, ctx->h2d_stream));
-        if (a.mask)
+        if (a.mask && a.mask_bits) {
+            // nx % 8 == 0 (checked by the caller): a slab of rows is a whole number of packed bytes per plane
+            OGN_CUDA(cudaMemcpy2DAsync(d_bits + off / 8, img / 8, a.mask + off / 8, img / 8, (size_t)rows * nx / 8, nz,
+                                       cudaMemcpyHostToDevice, ctx->h2d_stream));
+            const size_t count = (size_t)rows * nx;
+            unpack_mask_rows_kernel<<<ogn_div_up((int64_t)(count / 4) * nz, 256), 256, 0, ctx->h2d_stream>>>(d_bits, d_mask, nz, img,
+                                                                                                          off, count);
+            OGN_LAUNCH_CHECK("unpack_mask_rows_kernel");
+        } else if (a.mask) {
             OGN_CUDA(cudaMemcpy2DAsync(d_mask + off, img, a.mask + off, img, (size_t)rows * nx, nz,
                                        cudaMemcpyHostToDevice, ctx->h2d_stream));
+        }
         OGN_TRY(get_event(ctx, 1 + s, &ev));
         OGN_CUDA(cudaEventRecord(ev, ctx->h2d_stream));
     }
@@ -75,26 +108,30 @@ int step05_streamed(ogn_ctx *ctx, const Step05Args &a, const ogn_tglr_setup_t &s
         // slab s needs input rows up to y0 + rows + P/2: they arrive with slab s+1 (slab > P/2)
         OGN_TRY(get_event(ctx, 1 + std::min(s + 1, nslab - 1), &ev));
         OGN_CUDA(cudaStreamWaitEvent(ctx->stream, ev, 0));
-        OGN_TRY(ogn_tglr_window(ctx, ctx->stream, st, d_cube, d_mask, ogn_window{y0, y0 + rows, 0, nx}, d_correl,
+        // the rows of this slab inside the computed window (a tile computes its owned window grown by the extremum
+        // radius; a whole field everything)
+        const int cy0 = std::max(y0, w.y0), cy1 = std::min(y0 + rows, w.y1);
+        if (cy0 >= cy1) continue;
+        OGN_TRY(ogn_tglr_window(ctx, ctx->stream, st, d_cube, d_mask, ogn_window{cy0, cy1, w.x0, w.x1}, d_correl,
                                 d_cmin, d_prof, d_maxmap, d_minmap));
         OGN_TRY(get_event(ctx, 1 + nslab + s, &ev));
         OGN_CUDA(cudaEventRecord(ev, ctx->stream));
         OGN_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ev, 0));
-        const size_t off = (size_t)y0 * nx;
-        if (a.correl)
-            OGN_CUDA(cudaMemcpy2DAsync(a.correl + off, plane_b, d_correl + off, plane_b, (size_t)rows * nx * 4, nz,
+        const size_t off = (size_t)cy0 * nx;
+        const int crows = cy1 - cy0;
+        if (a.correl && !correl_dev)
+            OGN_CUDA(cudaMemcpy2DAsync(a.correl + off, plane_b, d_correl + off, plane_b, (size_t)crows * nx * 4, nz,
                                        cudaMemcpyDeviceToHost, ctx->d2h_stream));
-        if (a.correl_min)
-            OGN_CUDA(cudaMemcpy2DAsync(a.correl_min + off, plane_b, d_cmin + off, plane_b, (size_t)rows * nx * 4, nz,
+        if (a.correl_min && !cmin_dev)
+            OGN_CUDA(cudaMemcpy2DAsync(a.correl_min + off, plane_b, d_cmin + off, plane_b, (size_t)crows * nx * 4, nz,
                                        cudaMemcpyDeviceToHost, ctx->d2h_stream));
-        if (a.profile)
-            OGN_CUDA(cudaMemcpy2DAsync(a.profile + off, img, d_prof + off, img, (size_t)rows * nx, nz,
+        if (a.profile && !prof_dev)
+            OGN_CUDA(cudaMemcpy2DAsync(a.profile + off, img, d_prof + off, img, (size_t)crows * nx, nz,
                                        cudaMemcpyDeviceToHost, ctx->d2h_stream));
     }
     // extremum pass on the complete device cubes while the last products are still travelling
-    int rc = ogn_extrema_run(ctx, d_correl, d_cmin, d_mask, nz, ny, nx, ogn_window{0, ny, 0, nx},
-                             ogn_place{ny, nx, 0, 0}, a.sz, a.sy, a.sx, a.dense_max, a.dense_min, a.max_index,
-                             a.max_value, a.min_index, a.min_value, a.capacity, a.counts);
+    int rc = ogn_extrema_run(ctx, d_correl, d_cmin, d_mask, nz, ny, nx, owned, place, a.sz, a.sy, a.sx, a.dense_max,
+                             a.dense_min, a.max_index, a.max_value, a.min_index, a.min_value, a.capacity, a.counts);
     if (rc != OGN_OK && rc != OGN_ERR_OVERFLOW) return rc;
     OGN_TRY(ogn_output_commit(ctx, a.maxmap, d_maxmap, img * 4));
     OGN_TRY(ogn_output_commit(ctx, a.minmap, d_minmap, img * 4));
@@ -140,11 +177,20 @@ int step05_run(ogn_ctx *ctx, const Step05Args &a, const int *tile) {
     const size_t vol = (size_t)nz * ny * nx, img = (size_t)ny * nx;
 
     const bool host_in = !ogn_is_device_ptr(a.cube);
-    const bool host_out = (a.correl && !ogn_is_device_ptr(a.correl)) || (a.correl_min && !ogn_is_device_ptr(a.correl_min));
     static const bool no_stream = getenv("OGN_NO_STREAM") != nullptr;
-    if (!no_stream && !tile && host_in && host_out && a.cube_dtype == OGN_F32 && !st.pervoxel && ny >= 128 && nx % 4 == 0 &&
-        (!a.mask || !ogn_is_device_ptr(a.mask)) && (!a.profile || !ogn_is_device_ptr(a.profile)))
-        return step05_streamed(ctx, a, st);
+    if (a.mask_bits && (nx % 8 != 0 || ogn_is_device_ptr(a.mask)))
+        return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "a bit-packed mask must be host memory and nx a multiple of 8 (nx = %d)", nx);
+    // host cube: slab-pipelined path (every product goes to its own destination, host or device)
+    // TGLR on the owned window grown by the extremum radius (clipped to the sub-cube)
+    // ... and to the left down to a multiple of 4 columns: K1's TMA box starts P/2 = 12 columns left of the
+    // window and a TMA box must start on a 16-byte boundary (the few extra columns lie inside the sub-cube
+    // and belong to a neighbour; computing them is harmless)
+    const ogn_window w{std::max(0, owned.y0 - a.sy / 2), std::min(ny, owned.y1 + a.sy / 2),
+                       std::max(0, owned.x0 - a.sx / 2) / 4 * 4, std::min(nx, owned.x1 + a.sx / 2)};
+    const bool streamed = !no_stream && host_in && a.cube_dtype == OGN_F32 && !st.pervoxel && ny >= 64 && nx % 4 == 0 &&
+                          (!a.mask || !ogn_is_device_ptr(a.mask)) && !st.gather2.dst;
+    if (streamed) return step05_streamed(ctx, a, st, owned, place, w);
+    if (a.mask_bits) return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "a bit-packed mask is only taken on the streamed host path");
 
     void *d_correl = nullptr, *d_cmin = nullptr, *d_prof = nullptr, *d_maxmap = nullptr, *d_minmap = nullptr;
     // correl and correl_min are needed on the device even when the caller does not want them back
@@ -158,12 +204,6 @@ int step05_run(ogn_ctx *ctx, const Step05Args &a, const int *tile) {
     const float *d_cube = nullptr;
     OGN_TRY(ogn_input_cube_f32(ctx, "cube", a.cube, a.cube_dtype, vol, &d_cube));
     OGN_TRY(ogn_tglr_init_maps(ctx, ctx->stream, (float *)d_maxmap, (float *)d_minmap, img));
-    // TGLR on the owned window grown by the extremum radius (clipped to the sub-cube)
-    // ... and to the left down to a multiple of 4 columns: K1's TMA box starts P/2 = 12 columns left of the
-    // window and a TMA box must start on a 16-byte boundary (the few extra columns lie inside the sub-cube
-    // and belong to a neighbour; computing them is harmless)
-    const ogn_window w{std::max(0, owned.y0 - a.sy / 2), std::min(ny, owned.y1 + a.sy / 2),
-                       std::max(0, owned.x0 - a.sx / 2) / 4 * 4, std::min(nx, owned.x1 + a.sx / 2)};
     OGN_TRY(ogn_tglr_window(ctx, ctx->stream, st, d_cube, (const uint8_t *)d_mask, w, (float *)d_correl,
                             (float *)d_cmin, (uint8_t *)d_prof, (float *)d_maxmap, (float *)d_minmap));
     OGN_HT("tglr enqueued");
@@ -209,4 +249,19 @@ extern "C" int ogn_step05_tile(ogn_ctx *ctx, const void *cube, int cube_dtype, i
                        sz, sy, sx, correl, correl_min, profile, maxmap, minmap, nullptr, nullptr, max_index,
                        max_value, min_index, min_value, capacity, counts};
     return step05_run(ctx, a, tile);
+}
+
+// ogn_step05 with the mask given bit-packed (numpy.packbits of the flattened [nz][ny][nx] bool cube: 1/8 of the
+// bytes on the PCIe link; unpacked on the device slab by slab).  Host cube only, nx a multiple of 8.
+extern "C" int ogn_step05_bits(ogn_ctx *ctx, const void *cube, int cube_dtype, int nz, int ny, int nx, int nfields,
+                               const double *const *fsf, int psize, const double *const *weights, const double *taps,
+                               const int *tap_offsets, int nprof, const uint8_t *mask_bits, int sz, int sy, int sx,
+                               float *correl, float *correl_min, uint8_t *profile, float *maxmap, float *minmap,
+                               int64_t *max_index, float *max_value, int64_t *min_index, float *min_value,
+                               int64_t capacity, int64_t *counts) {
+    Step05Args a{cube, cube_dtype, nz, ny, nx, nfields, fsf, psize, weights, taps, tap_offsets, nprof, mask_bits,
+                 sz, sy, sx, correl, correl_min, profile, maxmap, minmap, nullptr, nullptr, max_index,
+                 max_value, min_index, min_value, capacity, counts};
+    a.mask_bits = mask_bits ? 1 : 0;
+    return step05_run(ctx, a, nullptr);
 }

@@ -305,7 +305,7 @@ def _tglr_args(cube, fsf, weights, profiles, mask, pcut, pmeansub):
 
 def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True, out=None, dense=False,
            capacity=None, want=('correl', 'profile', 'correl_min', 'maxmap', 'minmap'), tile=None, ctx=None,
-           sync=True):
+           sync=True, mask_bits=None, on_device=()):
     """The array part of ``ComputeTGLR.run`` (reference steps.py:768-802) in one
     device pass: TGLR, masking, maxmap / minmap and the local extrema.
 
@@ -321,6 +321,13 @@ def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True,
     sub-cube, only the owned window (grown by the extremum radius) is computed,
     the products are sub-cube shaped, and ``extrema`` holds the owned voxels with
     linear indices of the whole ``(nz, gny, gnx)`` field.
+
+    Host cubes (float32, C-contiguous; pinned memory is fastest): the field crosses PCIe in slabs of image
+    rows that overlap with the kernels and with the download of the products.  ``mask_bits`` — the mask as
+    ``np.packbits(mask)`` (flattened ``[nz][ny][nx]``), to be packed once per session — replaces ``mask``
+    on the link (1/8 of the bytes; ``nx`` a multiple of 8).  Products named in ``on_device`` (e.g.
+    ``('correl_min', 'profile')``) are left on the GPU as torch tensors instead of being copied back: the
+    step mirror hands them out lazily (:class:`origin_b200.steps.LazyProduct`).
 
     ``sync=False`` (CUDA tensors in and out only): the call returns with the kernels in flight and
     ``extrema`` is a :class:`DeviceExtrema` — the list lengths stay on the device until somebody reads
@@ -343,7 +350,12 @@ def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True,
         if key in want:
             res[key] = out.get(key)
             if res[key] is None:
-                res[key] = _empty_like_kind(cube, shape, dt)
+                if key in on_device and not _is_torch(cube):
+                    torch = _torch()
+                    res[key] = torch.empty(tuple(shape), dtype={np.float32: torch.float32, np.uint8: torch.uint8}[dt],
+                                           device=torch.device('cuda', ctx.device))
+                else:
+                    res[key] = _empty_like_kind(cube, shape, dt)
     if dense:
         res['cube_local_max'] = _empty_like_kind(cube, cube.shape, np.float32)
         res['cube_local_min'] = _empty_like_kind(cube, cube.shape, np.float32)
@@ -379,7 +391,19 @@ def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True,
                         ('min_value', np.float32)):
             buf = out.get(key)
             lists[key] = buf if buf is not None and len(buf) >= capacity else _empty_like_kind(cube, (capacity,), dt)
-        if tdesc is None:
+        if mask_bits is not None:
+            if tdesc is not None or dense or _is_torch(cube):
+                raise ValueError('mask_bits goes with a host cube, no tile and dense=False')
+            bits = np.ascontiguousarray(mask_bits, dtype=np.uint8)
+            if bits.size != (vol + 7) // 8:
+                raise ValueError('mask_bits must be np.packbits of the flattened (nz, ny, nx) mask')
+            rc = ctx.lib.ogn_step05_bits(
+                ctx.handle, ptr(cube), _dtype_code(cube), nz, ny, nx, len(fsfs), fsf_ptrs.address, fsfs[0].shape[1],
+                w_ptrs.address if w_ptrs else None, ptr(taps), ptr(offs), nprof, ptr(bits), size[0], size[1], size[2],
+                ptr(res.get('correl')), ptr(res.get('correl_min')), ptr(res.get('profile')), ptr(res.get('maxmap')),
+                ptr(res.get('minmap')), ptr(lists['max_index']), ptr(lists['max_value']), ptr(lists['min_index']),
+                ptr(lists['min_value']), capacity, ptr(counts))
+        elif tdesc is None:
             rc = ctx.lib.ogn_step05(
                 ctx.handle, ptr(cube), _dtype_code(cube), nz, ny, nx, len(fsfs), fsf_ptrs.address, fsfs[0].shape[1],
                 w_ptrs.address if w_ptrs else None, ptr(taps), ptr(offs), nprof, ptr(m), size[0], size[1], size[2],
@@ -402,7 +426,8 @@ def step05(cube, fsf, weights, profiles, mask, size=3, pcut=1e-8, pmeansub=True,
             break
         capacity = int(counts.max())
         out = {k: v for k, v in out.items() if k not in lists}
-        if tdesc is None and not dense and res.get('correl') is not None and res.get('correl_min') is not None:
+        if (tdesc is None and not dense and mask_bits is None and res.get('correl') is not None
+                and res.get('correl_min') is not None):
             # a list did not fit: every other product is complete, so only the extremum pass is repeated on the
             # correl / correl_min just computed (not FSF + spectral stage + PCIe again)
             ext, _, _ = local_extrema(res['correl'], res['correl_min'], m, size, capacity=capacity, ctx=ctx)

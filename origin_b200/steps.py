@@ -34,7 +34,7 @@ import numpy as np
 from . import lib_origin as lo
 
 __all__ = ['preprocessing', 'compute_tglr', 'compute_purity_threshold', 'detection_cat0', 'patch_steps',
-           'LazyDense']
+           'LazyProduct']
 
 
 # --------------------------------------------------------------------------
@@ -57,6 +57,7 @@ def preprocessing(cube_raw, var, mask, dct_order=10, dct_approx=False, local_max
 
 
 def compute_tglr(cube_faint, fsf, wfields, profiles, mask, size=3, pcut=1e-8, pmeansub=True, ctx=None, **kw):
+    # kw: out= (preallocated / pinned buffers), mask_bits=, on_device= ... see lib_origin.step05
     """Array part of ``ComputeTGLR.run`` (reference steps.py:768-802):
     ``cube_correl, cube_correl_min, cube_profile, maxmap, minmap`` and the
     local extrema as ``extrema``."""
@@ -99,22 +100,59 @@ def detection_cat0(extrema, cube_profile, threshold, extrema_std, threshold_std,
 # drop-in for the reference's step objects
 # --------------------------------------------------------------------------
 
-class LazyDense:
-    """Dense ``cube_local_max`` / ``cube_local_min`` materialised on first use.
+class LazyProduct:
+    """A step product that still lives on the GPU (or only as a compact extremum list), standing in for the
+    ``mpdaf`` object the step API promises until somebody looks at it.
 
-    ``mpdaf.obj.Cube(data=LazyDense(...))`` is not possible (mpdaf copies into a
-    masked array), so the fused steps store real dense arrays when the step API
-    is asked for them; this class is the container used by the array-level API
-    and by ``Detection`` when only the lists are needed."""
+    The reference keeps every product of a step as an attribute managed by the ``DataObj`` descriptor
+    (``steps.py:121-164``), which hands back whatever sits in the step's ``__dict__`` unless it is a file
+    path.  A ``LazyProduct`` sits there instead of the ``Cube`` / ``Image``; the first attribute access
+    (``.data``, ``._data``, ``.write(...)`` from ``Step.dump``, ``steps.py:301-337``, ...) fetches the array
+    from the device — float64 for floating-point cubes, as the reference stores and dumps them
+    (``convert_float32=False``, ``steps.py:318``) — builds the real object with the step's own
+    ``store_cube`` / ``store_image`` (which replaces this placeholder) and forwards the access.  Products
+    nobody reads (``cube_correl_min`` after a fused step06, the dense local-extremum cubes) never cross PCIe.
+    """
 
-    def __init__(self, extrema, which):
-        self.extrema, self.which, self._dense = extrema, which, None
-        self.shape = extrema.shape
+    def __init__(self, step, name, fetch, kind='cube', shape=None):
+        object.__setattr__(self, '_lazy', dict(step=step, name=name, fetch=fetch, kind=kind, shape=shape))
+
+    def materialise(self):
+        st = object.__getattribute__(self, '_lazy')
+        data = st['fetch']()
+        store = st['step'].store_cube if st['kind'] == 'cube' else st['step'].store_image
+        store(st['name'], data)
+        return getattr(st['step'], st['name'])
+
+    @property
+    def shape(self):
+        st = object.__getattribute__(self, '_lazy')
+        return st['shape'] if st['shape'] is not None else self.materialise().shape
+
+    def __getattr__(self, attr):
+        return getattr(self.materialise(), attr)
 
     def __array__(self, dtype=None, copy=None):
-        if self._dense is None:
-            self._dense = self.extrema.dense(self.which)
-        return self._dense if dtype is None else self._dense.astype(dtype)
+        return np.asarray(self.materialise().data, dtype=dtype)
+
+
+def _fetch_device(tensor, dtype):
+    def fetch():
+        arr = tensor.detach().cpu().numpy() if lo._is_torch(tensor) else np.asarray(tensor)
+        return arr.astype(dtype, copy=False)
+    return fetch
+
+
+def _packed_mask(orig):
+    """``np.packbits(orig.mask)``, made once per session and kept next to the mask."""
+    cached = getattr(orig, '_ogn_mask_bits', None)
+    if cached is None or cached[0] is not orig.mask:
+        cached = (orig.mask, np.packbits(np.asarray(orig.mask, dtype=bool).reshape(-1)))
+        try:
+            orig._ogn_mask_bits = cached
+        except AttributeError:
+            pass
+    return cached[1]
 
 
 def _run_preprocessing(self, orig, dct_order=10, dct_approx=False, pfasegcont=0.01, pfasegres=0.01,
@@ -128,8 +166,9 @@ def _run_preprocessing(self, orig, dct_order=10, dct_approx=False, pfasegcont=0.
     self.store_image('ima_std', out['ima_std'])
     ext = out['extrema_std']
     self._ogn_extrema_std = ext
-    self.store_cube('cube_std_local_max', ext.dense('max'))
-    self.store_cube('cube_std_local_min', ext.dense('min'))
+    shape = tuple(out['cube_std'].shape)
+    setattr(self, 'cube_std_local_max', LazyProduct(self, 'cube_std_local_max', lambda: ext.dense('max'), 'cube', shape))
+    setattr(self, 'cube_std_local_min', LazyProduct(self, 'cube_std_local_min', lambda: ext.dense('min'), 'cube', shape))
     self._loginfo('DCT continuum saved in self.cont_dct and self.ima_dct')
     self.store_cube('cont_dct', out['cont_dct'])
     self.store_image('ima_dct', out['ima_dct'])
@@ -147,18 +186,33 @@ def _run_preprocessing(self, orig, dct_order=10, dct_approx=False, pfasegcont=0.
 
 
 def _run_compute_tglr(self, orig, size=3, ncpu=1, pcut=1e-8, pmeansub=True):
-    """Fused ``ComputeTGLR.run`` (reference steps.py:756-802); ``ncpu`` is ignored."""
+    """Fused ``ComputeTGLR.run`` (reference steps.py:756-802); ``ncpu`` is ignored.
+
+    Only ``cube_correl``, the two maps and the compact extremum lists come back to the host.
+    ``cube_correl_min`` and ``cube_profile`` stay on the GPU and ``cube_local_max`` / ``cube_local_min`` stay
+    lists; all four are :class:`LazyProduct` attributes that turn into the reference's ``Cube`` objects when
+    somebody reads them (the fused step06 reads the lists, ``Detection`` the dense cubes, ``dump`` everything)."""
     self._loginfo('Correlation (B200)')
-    out = compute_tglr(orig.cube_faint._data, orig.PSF, orig.wfields, orig.profiles, orig.mask, size, pcut, pmeansub)
+    cube = orig.cube_faint._data
+    kw = {}
+    if (orig.wfields is None and isinstance(cube, np.ndarray) and cube.dtype == np.float32 and cube.shape[2] % 8 == 0
+            and cube.shape[1] >= 128):
+        kw = dict(mask_bits=_packed_mask(orig), on_device=('correl_min', 'profile'))
+    out = compute_tglr(cube, orig.PSF, orig.wfields, orig.profiles, None if kw else orig.mask, size, pcut, pmeansub, **kw)
     self.store_cube('cube_correl', out['cube_correl'])
-    self.store_cube('cube_correl_min', out['cube_correl_min'])
-    self.store_cube('cube_profile', out['cube_profile'])
+    shape = tuple(out['cube_correl'].shape)
+    for name, key, dt in (('cube_correl_min', 'cube_correl_min', np.float64), ('cube_profile', 'cube_profile', np.uint8)):
+        if lo._is_torch(out[key]):
+            setattr(self, name, LazyProduct(self, name, _fetch_device(out[key], dt), 'cube', shape))
+        else:
+            self.store_cube(name, out[key])
     self.store_image('maxmap', out['maxmap'])
     self.store_image('minmap', out['minmap'])
     ext = out['extrema']
     self._ogn_extrema = ext
-    self.store_cube('cube_local_max', ext.dense('max'))
-    self.store_cube('cube_local_min', ext.dense('min'))
+    self._ogn_profile = out['cube_profile']
+    setattr(self, 'cube_local_max', LazyProduct(self, 'cube_local_max', lambda: ext.dense('max'), 'cube', shape))
+    setattr(self, 'cube_local_min', LazyProduct(self, 'cube_local_min', lambda: ext.dense('min'), 'cube', shape))
 
 
 def _run_purity(self, orig, purity=0.9, purity_std=None, threshlist=None, pfasegfinal=1e-5, bins='fd'):

@@ -70,7 +70,10 @@ def test_tglr_single_field_golden(lo):
     mask = unpack_mask(g['mask'], g['shape'])
     profs = dictionaries.dico_3fwhm()[0]
     correl, profile, correl_min = lo.Correlation_GLR_test(g['cube'], g['fsf'], None, profs, pcut=1e-8)
-    assert correl.dtype == np.float32 and profile.dtype == np.uint8
+    # the reference's container types (lib_origin.py:1197-1217): float64 cubes, uint8 profile
+    assert correl.dtype == np.float64 and correl_min.dtype == np.float64 and profile.dtype == np.uint8
+    c32, _, _ = lo.Correlation_GLR_test(g['cube'], g['fsf'], None, profs, pcut=1e-8, out_dtype=np.float32)
+    assert c32.dtype == np.float32 and np.array_equal(c32.astype(np.float64), correl)
     assert_close(correl, g['correl_unmasked'], 'correl')
     assert_close(correl_min, g['cube_correl_min'], 'correl_min')
     tk = oracle_tk(g['cube'], g['fsf'], None, profs, 1e-8, True)

@@ -27,13 +27,27 @@ class FakeStep:
     def _loginfo(self, *a):
         self.log.append(a)
 
+    # like the reference's Step.store_cube / store_image (steps.py:284-299): the product becomes an attribute of
+    # the STEP; the ORIGIN object finds it there (origin.py:246-253)
     def store_cube(self, name, data, **kw):
         setattr(self, name, FakeData(data))
-        setattr(self.orig, name, FakeData(data))
 
     def store_image(self, name, data, **kw):
         setattr(self, name, FakeData(data))
-        setattr(self.orig, name, FakeData(data))
+
+
+class FakeOrigin:
+    """The part of ``ORIGIN`` the fused steps touch: inputs as attributes, products looked up on the steps."""
+
+    def __init__(self, **inputs):
+        self.__dict__.update(inputs)
+        self.param, self.steps = {}, {}
+
+    def __getattr__(self, name):
+        for step in self.__dict__.get('steps', {}).values():
+            if name in step.__dict__:
+                return getattr(step, name)
+        raise AttributeError(name)
 
 
 def fake_steps_module():
@@ -56,18 +70,22 @@ def test_patch_steps_runs_the_fused_steps():
     steps.patch_steps(mod, fused=True)
     try:
         assert mod.Correlation_GLR_test is lib_origin.Correlation_GLR_test
-        orig = types.SimpleNamespace(cube_raw=g['raw'].astype(np.float64), var=g['var'].astype(np.float64), mask=mask,
-                                     PSF=g['fsf'], wfields=None, profiles=dictionaries.dico_3fwhm()[0],
-                                     FWHM_PSF=[3.3], param={}, steps={})
+        orig = FakeOrigin(cube_raw=g['raw'].astype(np.float64), var=g['var'].astype(np.float64), mask=mask,
+                          PSF=g['fsf'], wfields=None, profiles=dictionaries.dico_3fwhm()[0], FWHM_PSF=[3.3])
         pre, tglr, pur = mod.Preprocessing(orig), mod.ComputeTGLR(orig), mod.ComputePurityThreshold(orig)
-        orig.steps = {'preprocessing': pre, 'compute_TGLR': tglr}
+        orig.steps = {'preprocessing': pre, 'compute_TGLR': tglr, 'purity': pur}
         pre.run(orig)
         np.testing.assert_allclose(orig.cube_std._data[100], g['cube_std_plane'], rtol=2e-4, atol=2e-4)
         orig.cube_faint = FakeData(orig.cube_std._data)          # steps 02-04 (PCA) are out of scope
         tglr.run(orig, pcut=1e-8)
         np.testing.assert_allclose(orig.cube_correl._data[100], g['correl_plane'], rtol=2e-4, atol=2e-4)
         np.testing.assert_allclose(orig.maxmap._data, g['maxmap'], rtol=2e-4, atol=2e-4)
+        # the dense extremum cubes are placeholders until somebody reads them, then real step products
+        assert isinstance(tglr.__dict__['cube_local_max'], steps.LazyProduct)
+        assert tglr.__dict__['cube_local_max'].shape == shape
         assert abs(np.count_nonzero(orig.cube_local_max._data) - int(g['n_local_max'])) <= 3
+        assert isinstance(tglr.__dict__['cube_local_max'], FakeData)
+        assert isinstance(tglr.__dict__['cube_local_min'], steps.LazyProduct)       # nobody asked for this one
         # step06 with the fixture's segmap instead of the gaussian-fit one
         orig.segmap_merged = FakeData(g['segmap'])
         mod.compute_segmap_gauss = lambda img, pfa, fwhm, bins='fd': (0.0, np.zeros_like(g['segmap']))
@@ -87,5 +105,38 @@ def test_patch_steps_runs_the_fused_steps():
         np.testing.assert_array_equal(cat0['profile'][:n], g['cat_profile'])
         np.testing.assert_array_equal(cat0['z0'][n:], g['std_z'])
         assert np.all(cat0['comp'][:n] == 0) and np.all(cat0['comp'][n:] == 1)
+    finally:
+        steps.unpatch_steps()
+
+
+def test_fused_tglr_keeps_unread_products_on_the_device():
+    """float32 host cube, width a multiple of 8: the fused step uploads the mask bit-packed, returns correl,
+    the maps and the lists, and leaves correl_min / profile on the GPU behind LazyProduct placeholders that
+    materialise (float64 / uint8, the reference's container types) on first access and equal the eager run."""
+    import torch
+    from origin_b200 import lib_origin, steps, synthetic
+    shape = (120, 128, 64)
+    fsf = synthetic.moffat_fsf(shape[0])
+    cube, _ = synthetic.faint_cube(shape, fsf, n_src=6, seed=5)
+    mask = synthetic.footprint_mask(shape, seed=5)
+    profs = dictionaries.dico_3fwhm()[0]
+    mod = fake_steps_module()
+    steps.patch_steps(mod, fused=True)
+    try:
+        orig = FakeOrigin(mask=mask, PSF=fsf, wfields=None, profiles=profs, cube_faint=FakeData(cube))
+        tglr = mod.ComputeTGLR(orig)
+        orig.steps = {'compute_TGLR': tglr}
+        tglr.run(orig, pcut=1e-8)
+        assert orig._ogn_mask_bits[1].size == (cube.size + 7) // 8
+        lazy = tglr.__dict__['cube_correl_min']
+        assert isinstance(lazy, steps.LazyProduct) and torch.is_tensor(tglr._ogn_profile) and tglr._ogn_profile.is_cuda
+        ref = lib_origin.step05(cube, fsf, None, profs, mask, 3, 1e-8, True)
+        np.testing.assert_array_equal(orig.cube_correl._data, ref['correl'])
+        got = orig.cube_correl_min._data                       # materialises
+        assert got.dtype == np.float64 and isinstance(tglr.__dict__['cube_correl_min'], FakeData)
+        np.testing.assert_array_equal(got.astype(np.float32), ref['correl_min'])
+        np.testing.assert_array_equal(orig.cube_profile._data, ref['profile'])
+        np.testing.assert_array_equal(tglr._ogn_extrema.max_index, ref['extrema'].max_index)
+        np.testing.assert_array_equal(orig.maxmap._data, ref['maxmap'])
     finally:
         steps.unpatch_steps()
