@@ -397,8 +397,9 @@ class Job:
                         min_index=torch.empty(self.cap, dtype=torch.int64, device=dev),
                         min_value=torch.empty(self.cap, device=dev))
 
-        # N > 1: two product sets, so that the peer copy of step i (side stream) overlaps the kernels of step i+1
-        self.out_sets = [alloc_out() for _ in range(2 if self.world > 1 else 1)]
+        # N > 1: three product sets, so that the peer copy of step i (side stream, staggered by rank) has until
+        # the spectral kernel of step i+3 to finish
+        self.out_sets = [alloc_out() for _ in range(3 if self.world > 1 else 1)]
         self.reducer = ogd.Reducer() if self.world > 1 else None
         self.gather, self.gather_mode = None, None
         if self.world > 1:
@@ -420,6 +421,7 @@ class Job:
         self.thr_dev = torch.from_numpy(THRESHOLDS).to(dev)
         self.counts_dev = torch.zeros(2 * len(THRESHOLDS), dtype=torch.int64, device=dev)
         self.i = 0
+        self.ar_events = []
         self.trace = {}
         self.last = {}
         self.lo = lib_origin
@@ -449,7 +451,14 @@ class Job:
         n1, n0 = lo.purity_counts(ext, None, self.thr_dev, env.ctx, out=self.counts_dev)   # step06 counting loop
         t0 = self._tick('purity_counts', t0)
         if self.world > 1:
-            self.reducer.sum_(self.counts_dev)                                    # NCCL allreduce of the histograms
+            if os.environ.get('OGN_TIMING_OFFSETS'):
+                ea, eb = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+                ea.record()
+                self.reducer.sum_(self.counts_dev)
+                eb.record()
+                self.ar_events.append((ea, eb))
+            else:
+                self.reducer.sum_(self.counts_dev)                                # NCCL allreduce of the histograms
             t0 = self._tick('allreduce', t0)
             # correl -> rank 0, enqueued last: the bulk stores would otherwise sit in front of the small
             # allreduce on the NVLink queues; this way they overlap the kernels of the next step instead
@@ -488,6 +497,7 @@ class Job:
             time.sleep(0.25)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.sync_all()
+        self.ar_events = []
         e0.record()
         for _ in range(steps):
             self.step()
@@ -509,12 +519,11 @@ class Job:
                 name, off = name.split('@')
                 timeline.append((float(off), name, ms))
             stages.setdefault(name, []).append(ms)
-        if timeline:
-            timeline.sort()
-            t_ref = [t for t in timeline if t[1] == 'step05_span'][2][0] if len([t for t in timeline if t[1] == 'step05_span']) > 6 else 0.0
-            sys.stderr.write('rank %d timeline (ms from the third timed step): %s\n' % (self.rank, ' '.join(
-                '%s[%.2f+%.2f]' % (n, o - t_ref, d) for o, n, d in timeline if 0 <= o - t_ref < 8.0
-                and n in ('step05_span', 'peer_scatter', 'k1_fsf_correlate'))))
+        if timeline:             # development aid: the raw per-rank timeline (stage, start, duration) as JSON
+            ar = [(e0.elapsed_time(a), a.elapsed_time(b)) for a, b in self.ar_events]
+            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+            with open(os.path.join(ROOT, 'gpurun_out', 'timeline_rank%d.json' % self.rank), 'w') as f:
+                json.dump(dict(stages=sorted(timeline), allreduce=ar), f)
         env.ctx.timing(False)
         per_rank = None
         if self.world > 1:
@@ -576,7 +585,8 @@ class Job:
             n1, n0 = lo.purity_counts(res['extrema'], None, THRESHOLDS, env.ctx)            # step06 counting loop
             if not single:
                 self.reducer.sum(np.concatenate([n1, n0]))
-            rows = lo.threshold_rows(res['extrema'], 8.0, res['profile'], 'max', env.ctx)   # step07 extraction
+            # step07 extraction (tile mode: the lists carry whole-field indices, the profile lookup belongs to rank 0)
+            rows = lo.threshold_rows(res['extrema'], 8.0, res['profile'] if single else None, 'max', env.ctx)
             return res, rows
 
         step_e2e()

@@ -86,16 +86,19 @@ extern "C" int ogn_trim(ogn_ctx *ctx) {
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     ctx->h2d_stream = ctx->d2h_stream = nullptr;
-    if (ctx->peer_stream) {
-        cudaStreamSynchronize(ctx->peer_stream);
-        cudaStreamDestroy(ctx->peer_stream);
-        ctx->peer_stream = nullptr;
-    }
+    for (auto &ps : ctx->peer_streams)
+        if (ps) {
+            cudaStreamSynchronize(ps);
+            cudaStreamDestroy(ps);
+            ps = nullptr;
+        }
+    ctx->peer_stream = nullptr;
     for (auto &kv : ctx->readers) cudaEventDestroy(kv.second);
     ctx->readers.clear();
     if (ctx->peer_ev_begin) cudaEventDestroy(ctx->peer_ev_begin);
     if (ctx->peer_ev_end) cudaEventDestroy(ctx->peer_ev_end);
-    ctx->peer_ev_begin = ctx->peer_ev_end = nullptr;
+    if (ctx->peer_ev_end2) cudaEventDestroy(ctx->peer_ev_end2);
+    ctx->peer_ev_begin = ctx->peer_ev_end = ctx->peer_ev_end2 = nullptr;
     return OGN_OK;
 }
 
@@ -131,7 +134,8 @@ extern "C" int ogn_timing_enable(ogn_ctx *ctx, int on) {
 extern "C" int ogn_timing_report(ogn_ctx *ctx, char *buf, size_t size) {
     if (!ctx || !buf || size == 0) return OGN_ERR_ARG;
     OGN_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->peer_stream) OGN_CUDA(cudaStreamSynchronize(ctx->peer_stream));   // peer_scatter entries live there
+    for (auto ps : ctx->peer_streams)
+        if (ps) OGN_CUDA(cudaStreamSynchronize(ps));   // peer_scatter entries live there
     std::string out;
     static const bool with_offsets = getenv("OGN_TIMING_OFFSETS") != nullptr;   // "name@start_ms:duration_ms" (timelines)
     cudaEvent_t first = ctx->timings.empty() ? nullptr : ctx->timings.front().start;
@@ -149,6 +153,8 @@ extern "C" int ogn_timing_report(ogn_ctx *ctx, char *buf, size_t size) {
         } else {
             cudaGetLastError();
         }
+    }
+    for (auto &e : ctx->timings) {   // after the loop: the first start event is the origin of the offsets
         cudaEventDestroy(e.start);
         cudaEventDestroy(e.stop);
     }

@@ -53,8 +53,10 @@ struct ogn_ctx {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> events;
     // peer gather (ogn_peer.cu)
-    cudaStream_t peer_stream = nullptr;
-    cudaEvent_t peer_ev_begin = nullptr, peer_ev_end = nullptr;
+    cudaStream_t peer_stream = nullptr;            // stream of the latest scatter (one of peer_streams)
+    cudaStream_t peer_streams[2] = {nullptr, nullptr};   // consecutive scatters alternate: a staggered copy's delay must not queue behind the previous copy
+    int peer_turn = 0;
+    cudaEvent_t peer_ev_begin = nullptr, peer_ev_end = nullptr, peer_ev_end2 = nullptr;
     std::vector<void *> peer_owned, peer_mapped;
     std::map<const void *, cudaEvent_t> readers;   // source buffer -> event of the last scatter reading it
     // zero-copy staging (ogn_api.cu): small host -> device tables and device -> host scalars travel through

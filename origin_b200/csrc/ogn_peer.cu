@@ -63,9 +63,19 @@ __global__ void delay_kernel(unsigned long long ns) {
     } while (t - t0 < ns);
 }
 
+// Consecutive scatters alternate between two streams: with a staggered start (ogn_peer_set_delay) the wait of
+// copy i+1 would otherwise queue behind copy i and every copy would start later than the one before.
 int peer_stream(ogn_ctx *ctx, cudaStream_t *out) {
-    if (!ctx->peer_stream) OGN_CUDA(cudaStreamCreateWithFlags(&ctx->peer_stream, cudaStreamNonBlocking));
-    *out = ctx->peer_stream;
+    cudaStream_t &ps = ctx->peer_streams[ctx->peer_turn & 1];
+    ctx->peer_turn++;
+    if (!ps) OGN_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    ctx->peer_stream = ps;
+    *out = ps;
+    return OGN_OK;
+}
+int sync_peer_streams(ogn_ctx *ctx) {
+    for (auto ps : ctx->peer_streams)
+        if (ps) OGN_CUDA(cudaStreamSynchronize(ps));
     return OGN_OK;
 }
 
@@ -123,7 +133,7 @@ extern "C" int ogn_peer_close(ogn_ctx *ctx, void *dev_ptr) {
     auto it = std::find(ctx->peer_mapped.begin(), ctx->peer_mapped.end(), dev_ptr);
     if (it == ctx->peer_mapped.end()) return ogn_fail(ctx, OGN_ERR_ARG, "ogn_peer_close: not a mapping of ogn_peer_open");
     OGN_CUDA(cudaSetDevice(ctx->device));
-    if (ctx->peer_stream) OGN_CUDA(cudaStreamSynchronize(ctx->peer_stream));
+    OGN_TRY(sync_peer_streams(ctx));
     OGN_CUDA(cudaIpcCloseMemHandle(dev_ptr));
     ctx->peer_mapped.erase(it);
     return OGN_OK;
@@ -236,8 +246,13 @@ extern "C" int ogn_peer_join(ogn_ctx *ctx) {
     if (!ctx->peer_stream) return OGN_OK;
     OGN_CUDA(cudaSetDevice(ctx->device));
     if (!ctx->peer_ev_end) OGN_CUDA(cudaEventCreateWithFlags(&ctx->peer_ev_end, cudaEventDisableTiming));
-    OGN_CUDA(cudaEventRecord(ctx->peer_ev_end, ctx->peer_stream));
-    OGN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->peer_ev_end, 0));
+    if (!ctx->peer_ev_end2) OGN_CUDA(cudaEventCreateWithFlags(&ctx->peer_ev_end2, cudaEventDisableTiming));
+    cudaEvent_t evs[2] = {ctx->peer_ev_end, ctx->peer_ev_end2};
+    for (int i = 0; i < 2; ++i)
+        if (ctx->peer_streams[i]) {
+            OGN_CUDA(cudaEventRecord(evs[i], ctx->peer_streams[i]));
+            OGN_CUDA(cudaStreamWaitEvent(ctx->stream, evs[i], 0));
+        }
     return OGN_OK;
 }
 
@@ -247,8 +262,7 @@ extern "C" int ogn_peer_sync(ogn_ctx *ctx) {
     if (!ctx) return OGN_ERR_ARG;
     if (!ctx->peer_stream) return OGN_OK;
     OGN_CUDA(cudaSetDevice(ctx->device));
-    OGN_CUDA(cudaStreamSynchronize(ctx->peer_stream));
-    return OGN_OK;
+    return sync_peer_streams(ctx);
 }
 
 // A kernel on `stream` is about to overwrite `buf`: wait for the scatter that may still read it.

@@ -1004,14 +1004,15 @@ int ogn_tglr_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &s
     if (w.y0 < 0 || w.x0 < 0 || w.y1 > st.ny || w.x1 > st.nx || w.y0 >= w.y1 || w.x0 >= w.x1)
         return ogn_fail(ctx, OGN_ERR_ARG, "window [%d,%d)x[%d,%d) outside the %dx%d sub-cube", w.y0, w.y1, w.x0, w.x1,
                         st.ny, st.nx);
-    // a peer scatter of the previous step may still be reading the buffer K2 is about to overwrite
-    OGN_TRY(ogn_wait_readers(ctx, stream, d_correl));
     float *cube_fsf = nullptr, *norm_fsf = nullptr;
     int pitch = 0;
     {
         ogn_timer t_(ctx, "k1_fsf_correlate");
         OGN_TRY(run_fsf_window(ctx, stream, st, dcube, w, &cube_fsf, &norm_fsf, &pitch));
     }
+    // a peer scatter of an earlier step may still be reading the buffer K2 is about to overwrite (K1 does not
+    // touch it: waiting here, not before K1, gives the copy the whole spatial stage to finish)
+    OGN_TRY(ogn_wait_readers(ctx, stream, d_correl));
     ogn_timer t_(ctx, "k2_spectral_glr");
     if (st.pervoxel)
         return launch_spectral<16, 4, true, false>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, dmask, d_correl,

@@ -810,6 +810,9 @@ def threshold_rows(ext, threshold, profile=None, which='max', ctx=None):
     idx = ext.max_index if which == 'max' else ext.min_index
     val = ext.max_value if which == 'max' else ext.min_value
     n = len(idx)
+    if profile is not None and tuple(profile.shape) != tuple(ext.shape):
+        # e.g. a tile's sub-cube profile with the whole-field indices of tile mode: the lookup would run off the end
+        raise ValueError('profile has shape %r but the extrema index a %r cube' % (tuple(profile.shape), tuple(ext.shape)))
     ctx = _ctx_for(val, ctx)
     dev_profile = profile if (profile is not None and _is_torch(profile) and profile.is_cuda) else None
     cap = max(1024, n // 64)

@@ -572,3 +572,35 @@ def test_tglr_folded_spectral_kernel_cases(lo, case):
     tk = oracle_tk(cube, fsf, None, profs, 1e-8, True)
     check_profile(np.where(mask, 0, out['profile']), np.where(mask, 0, ref['cube_profile']), tk, case + ' profile',
                   max_frac=3e-3)
+
+
+def test_threshold_rows_rejects_a_profile_of_another_shape(lo):
+    ext = lo.LocalExtrema((4, 6, 8), np.array([5, 100], dtype=np.int64), np.array([9.0, 7.0], dtype=np.float32),
+                          np.zeros(0, np.int64), np.zeros(0, np.float32))
+    with pytest.raises(ValueError):
+        lo.threshold_rows(ext, 1.0, np.zeros((4, 3, 8), np.uint8))
+
+
+def test_step05_host_tile_on_the_streamed_path(lo):
+    """A HOST sub-cube in tile mode takes the slab-pipelined path (upload / kernels / download overlapped): same
+    products on the owned window and same whole-field lists as the device-resident tile call."""
+    import torch
+    from origin_b200 import tiles
+    shape = (96, 160, 192)
+    nz, ny, nx = shape
+    fsf = synthetic.moffat_fsf(nz)
+    cube, _ = synthetic.faint_cube(shape, fsf, n_src=8, seed=13)
+    mask = synthetic.footprint_mask(shape, seed=13)
+    profs = dictionaries.dico_3fwhm()[0]
+    for t in tiles.plan_tiles(ny, nx, 2, 13):
+        sl = (slice(None),) + t.padded
+        sub, msub = np.ascontiguousarray(cube[sl]), np.ascontiguousarray(mask[sl])
+        host = lo.step05(sub, fsf, None, profs, msub, 3, 1e-8, True, tile=(t, (ny, nx)))
+        dev = lo.step05(torch.from_numpy(sub).cuda(), fsf, None, profs, torch.from_numpy(msub.view(np.uint8)).cuda(), 3,
+                        1e-8, True, tile=(t, (ny, nx)))
+        ys, xs = t.owned
+        for key in ('correl', 'correl_min', 'profile'):
+            np.testing.assert_array_equal(host[key][:, ys, xs], dev[key].cpu().numpy()[:, ys, xs], err_msg=key)
+        np.testing.assert_array_equal(host['extrema'].max_index, dev['extrema'].max_index.cpu().numpy())
+        np.testing.assert_array_equal(host['extrema'].min_value, dev['extrema'].min_value.cpu().numpy())
+        np.testing.assert_array_equal(host['maxmap'][ys, xs], dev['maxmap'].cpu().numpy()[ys, xs])
