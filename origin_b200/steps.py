@@ -177,10 +177,10 @@ def _run_preprocessing(self, orig, dct_order=10, dct_approx=False, pfasegcont=0.
     mean_fwhm = int(np.ceil(np.mean(self.orig.FWHM_PSF)))
     self._loginfo('Segmentation based on the continuum')
     map1 = np.log10(out['cont_sumsq'])
-    thresh, map_cont = mod.compute_segmap_gauss(map1, pfasegcont, mean_fwhm, bins=bins)
+    thresh, map_cont = _segmap_gauss(mod)(map1, pfasegcont, mean_fwhm, bins=bins)
     self.store_image('segmap_cont', map_cont)
     self._loginfo('Segmentation based on the residual')
-    thresh, map_res = mod.compute_segmap_gauss(out['o2map'], pfasegres, mean_fwhm, bins=bins)
+    thresh, map_res = _segmap_gauss(mod)(out['o2map'], pfasegres, mean_fwhm, bins=bins)
     segmap, nlabels = mod.ndi.label((map_cont > 0) | (map_res > 0))
     self.store_image('segmap_merged', segmap)
 
@@ -221,7 +221,7 @@ def _run_purity(self, orig, purity=0.9, purity_std=None, threshlist=None, pfaseg
     if purity_std is None:
         purity_std = purity
     orig.param.update(dict(purity=purity, purity_std=purity_std))
-    thresh, map_res = mod.compute_segmap_gauss(self.orig.maxmap._data, pfasegfinal, 0, bins=bins)
+    thresh, map_res = _segmap_gauss(mod)(self.orig.maxmap._data, pfasegfinal, 0, bins=bins)
     segmap, nlabels = mod.ndi.label((map_res > 0) | (orig.segmap_merged._data > 0))
     self.store_image('segmap_purity', segmap)
     tglr_step = orig.steps['compute_TGLR']
@@ -243,6 +243,16 @@ def _run_purity(self, orig, purity=0.9, purity_std=None, threshlist=None, pfaseg
 
 _STEPS_MODULE = None
 _ORIGINALS = {}
+
+
+def _segmap_gauss(mod):
+    """The reference's ``compute_segmap_gauss`` when the patched module has it (it needs astropy), else the
+    numpy / scipy restatement of :mod:`origin_b200.segmap`."""
+    fn = getattr(mod, 'compute_segmap_gauss', None)
+    if fn is None:
+        from . import segmap
+        fn = segmap.compute_segmap_gauss
+    return fn
 
 
 def patch_steps(steps_module=None, fused=True):
