@@ -204,8 +204,8 @@ __device__ __forceinline__ void fold_group(const float *__restrict__ wrow, const
     }
 }
 
-template <int G, int NW, bool G2, bool PK>
-__global__ void __launch_bounds__(NW * 32, (G <= 3 ? 5 : 3))
+template <int G, int NW, bool G2, bool PK, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 folded_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_constant__ FoldDict dict,
                   int nz, int wny, int wnx,                    // window (= K1 output) dims
                   int oy_off, int ox_off, int ony, int onx,    // window origin inside the [nz][ony][onx] products
@@ -400,6 +400,8 @@ bool ogn_k2f_prepare(const double *taps, const int *tap_offsets, int nprof, k2f:
     static const bool disabled = getenv("OGN_K2_NOFOLD") != nullptr;
     static const bool forced = getenv("OGN_K2_FOLD") != nullptr;
     if (disabled || nprof < 1 || (nprof <= 3 && !forced)) return false;
+    // groups of 5 (104 registers, 4 blocks per SM) measured 9.52 ms against 9.61 ms for groups of 10 (146 registers,
+    // 3 blocks): occupancy is not what holds the kernel back; 128 registers forced on groups of 10 spill (12.2 ms)
     const int G = nprof <= 3 ? 3 : GMAX, GP = (G + 3) / 4 * 4;
     const int ngroups = (nprof + G - 1) / G;
     if (ngroups > MAXG) return false;
@@ -457,14 +459,14 @@ int ogn_k2f_upload(ogn_ctx *ctx, ogn_uploader *up, const std::vector<float> &tab
     return up->add(sym, table.data(), table.size() * sizeof(float));
 }
 
-template <int G, int NW, bool PK, bool G2 = false>
+template <int G, int NW, bool PK, int MINB, bool G2 = false>
 static int launch_folded(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, ogn_window w,
                          const float *cube_fsf, int pitch, const uint8_t *mask, float *correl, float *correl_min,
                          uint8_t *profile, float *maxmap, float *minmap) {
     using namespace k2f;
     if (!G2 && st.gather2.dst)
-        return launch_folded<G, NW, PK, true>(ctx, stream, st, w, cube_fsf, pitch, mask, correl, correl_min, profile, maxmap, minmap);
-    auto kern = folded_glr_kernel<G, NW, G2, PK>;
+        return launch_folded<G, NW, PK, MINB, true>(ctx, stream, st, w, cube_fsf, pitch, mask, correl, correl_min, profile, maxmap, minmap);
+    auto kern = folded_glr_kernel<G, NW, G2, PK, MINB>;
     const FoldDict &d = *st.fold;
     const int wny = w.y1 - w.y0, wnx = w.x1 - w.x0;
     const size_t limit = 100 * 1024;
@@ -495,7 +497,7 @@ static int launch_folded(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup
     const int nchunk = ogn_div_up(st.nz, cz);
     const int cols = (pitch / 32) * wny;
     // enough blocks for ~8 waves of resident blocks, at most one block per chunk
-    int zsplit = ogn_div_up((int64_t)ctx->sm_count * (G <= 3 ? 5 : 3) * 8, cols);
+    int zsplit = ogn_div_up((int64_t)ctx->sm_count * MINB * 8, cols);
     zsplit = std::max(1, std::min(zsplit, nchunk));
     dim3 grid(pitch / 32, wny, zsplit);
     if (grid.y > 65535) return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "cube too large for the K2 launch grid");
@@ -512,10 +514,10 @@ int ogn_k2f_launch(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st
                    float *minmap) {
     // OGN_K2F_SCALAR=1: scalar FFMAs instead of the packed FFMA2 form (diagnostic; both are parity-tested)
     static const bool scalar = getenv("OGN_K2F_SCALAR") != nullptr;
-#define OGN_K2F(G_, PK_) launch_folded<G_, 4, PK_>(ctx, stream, st, w, cube_fsf, pitch, mask, correl, correl_min, profile, \
-                                                  maxmap, minmap)
-    if (st.fold->G <= 3) return scalar ? OGN_K2F(3, false) : OGN_K2F(3, true);
-    if (scalar) return OGN_K2F(k2f::GMAX, false);
-    return OGN_K2F(k2f::GMAX, true);
+#define OGN_K2F(G_, PK_, MB_) launch_folded<G_, 4, PK_, MB_>(ctx, stream, st, w, cube_fsf, pitch, mask, correl, correl_min, \
+                                                           profile, maxmap, minmap)
+    if (st.fold->G <= 3) return scalar ? OGN_K2F(3, false, 5) : OGN_K2F(3, true, 5);
+    if (scalar) return OGN_K2F(k2f::GMAX, false, 3);
+    return OGN_K2F(k2f::GMAX, true, 3);
 #undef OGN_K2F
 }
