@@ -984,7 +984,11 @@ def main_gpu(args):
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
     models = kernel_models(prof_cut, r['folded'], nprof > 3)
-    traffic = {k: summ.get(k + '_dram_bytes_per_launch') for k in models}
+    traffic = {k: summ.get(k + '_dram_bytes_per_launch') for k in models}   # ncu dram__bytes_read+write per launch
+    if nprof > 3:
+        traffic['k2_spectral_glr'] = summ.get('k2f_folded_glr_dram_bytes_per_launch')
+    if tuple(args.shape) != SHAPE:
+        traffic = {}                                     # the captures are of the 3681x320x320 cube
     roofs, dominant = stage_rooflines(r['stages'], models, vol_tile, fp32_peak, hbm_peak, traffic if world == 1 else {})
     roofline = None
     if dominant:

@@ -20,10 +20,13 @@
  *    the message.  There is no CPU fallback: without a usable CUDA device
  *    ogn_create fails.
  *  - One context per (process, device, stream).  Calls on one context must be
- *    serialised by the caller, and so must TGLR calls (ogn_tglr, ogn_step05*)
- *    of different contexts on the same device: the profile taps of the call in
- *    flight live in __constant__ memory, which the device's contexts share
- *    (multi-GPU runs use one process per GPU and are not affected).  All work
+ *    serialised by the caller.  TGLR calls (ogn_tglr, ogn_step05*) of different
+ *    contexts on the same device are serialised by the library: the profile
+ *    taps of the call in flight live in __constant__ memory, which the device's
+ *    contexts share, so the enqueue sections hold a process-wide lock and a
+ *    context that follows another one makes its stream wait for the event the
+ *    other recorded behind its last TGLR kernel (processes sharing one GPU are
+ *    separate CUDA contexts with their own constants).  All work
  *    is enqueued on the context's stream and
  *    every entry point that returns data to host memory synchronises that
  *    stream before returning.  Calls whose outputs are all device pointers
@@ -352,6 +355,24 @@ OGN_API int ogn_preprocess(ogn_ctx *ctx,
                    float *cube_std, float *cont_dct,
                    double *ima_std, double *ima_dct,
                    double *cont_sumsq, double *o2map);
+
+/* ---- step04: greedy PCA -------------------------------------------------------- */
+
+/* Compute_GreedyPCA (lib_origin.py:858-954, with O2test :957-974 and orthogonal_projection :76-88) on the
+ * spaxels `cols[0..n)` (column indices; NULL = all, then n == ld) of a [nz][ld] cube: until no spaxel's
+ * second-order test mean_z x^2 exceeds `thres`, the first left singular vector of the nuisance spectra
+ * (orthogonalised to the mean spectrum of the quietest 1 / noise_population of the background spaxels) is
+ * projected out of every spectrum of the block.  FP64 on the device.
+ *   cube    float32 / float64 (`dtype`), host or device, read only
+ *   test0   NULL (the test of the block is computed: Compute_PCA_threshold, :836) or [n] float64, host
+ *   faint   [nz][ld] cube of `out_dtype`, host or device: only the columns `cols` are written, so the caller
+ *           starts from a copy of `cube` like the reference (Compute_GreedyPCA_area, :797) or passes cube itself
+ *   map_o2  [n] float64, host: number of iterations each spaxel spent above the threshold (:887)
+ *   info    {nstop (iteration limit hit, :888-891), iterations, operator applications of the SVD} */
+OGN_API int ogn_greedy_pca(ogn_ctx *ctx, const void *cube, int dtype, int nz, int64_t ld,
+                   const int64_t *cols, int64_t n, const double *test0, double thres,
+                   double noise_population, int itermax, void *faint, int out_dtype,
+                   double *map_o2, int *info);
 
 #ifdef __cplusplus
 }

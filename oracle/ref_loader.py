@@ -71,6 +71,27 @@ class TableShim:
         return 'TableShim(%s)' % ', '.join(self.names)
 
 
+class _ProgressBar:
+    """``mpdaf.tools.progressbar`` (a tqdm wrapper) reduced to what the hot path touches: iteration over an iterable
+    (``Correlation_GLR_test``, ``Compute_threshold_purity``) and the context-manager form with ``update`` / ``n``
+    (``Compute_GreedyPCA``, lib_origin.py:884-950)."""
+
+    def __init__(self, iterable=None, total=None, **kw):
+        self.iterable, self.total, self.n = iterable, total, 0
+
+    def __iter__(self):
+        return iter(self.iterable)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def update(self, k=1):
+        self.n += k
+
+
 STUBS = ['matplotlib', 'matplotlib.pyplot', 'astropy', 'astropy.modeling', 'astropy.modeling.fitting',
          'astropy.modeling.models', 'astropy.nddata', 'astropy.stats', 'astropy.table', 'astropy.utils',
          'astropy.utils.exceptions', 'astropy.io', 'astropy.io.fits', 'astropy.units', 'mpdaf', 'mpdaf.obj',
@@ -87,7 +108,7 @@ def _install_stubs():
             except ImportError:
                 pass
             sys.modules[name] = MagicMock()
-    sys.modules['mpdaf.tools'].progressbar = lambda it=None, **kw: it
+    sys.modules['mpdaf.tools'].progressbar = _ProgressBar
 
     class AstropyUserWarning(Warning):
         pass

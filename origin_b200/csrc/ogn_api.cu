@@ -104,6 +104,7 @@ extern "C" int ogn_trim(ogn_ctx *ctx) {
 
 extern "C" void ogn_destroy(ogn_ctx *ctx) {
     if (!ctx) return;
+    ogn_tglr_forget(ctx);
     ogn_trim(ctx);
     if (ctx->stage_h) cudaFreeHost(ctx->stage_h);
     if (ctx->res_h) cudaFreeHost(ctx->res_h);

@@ -68,6 +68,7 @@ struct ogn_ctx {
     int64_t *res_h = nullptr, *res_d = nullptr;    // 32 mapped int64 result slots
     float *local_gather = nullptr;                 // ogn_set_local_gather: consumed by the next ogn_step05_tile
     int peer_delay_us = 0;                         // ogn_peer_set_delay
+    cudaEvent_t tglr_done = nullptr;               // recorded behind the last TGLR kernel of a call (ogn_tglr_guard)
     bool local_gather_is_peer = false;             // ... it is another device's buffer (mapped with ogn_peer_open)
 };
 
@@ -213,6 +214,20 @@ struct ogn_tglr_setup_t {
     ogn_gather2 gather2;
     std::shared_ptr<k2f::FoldDict> fold;   // set when the dictionary qualifies for K2f (taps already in constant memory)
 };
+
+// The profile taps of a TGLR call in flight live in __constant__ memory, which all contexts of a device share.
+// Every entry point that runs the spectral stage holds this guard from before the setup (which rewrites the
+// constants) until its last kernel is enqueued: the enqueue sections of different contexts cannot interleave on the
+// host (process-wide mutex), and a context that follows another one on the same device first makes its stream
+// wait for the event the other recorded behind its last TGLR kernel.
+struct ogn_tglr_guard {
+    ogn_ctx *ctx;
+    explicit ogn_tglr_guard(ogn_ctx *c);
+    ~ogn_tglr_guard();
+    ogn_tglr_guard(const ogn_tglr_guard &) = delete;
+    ogn_tglr_guard &operator=(const ogn_tglr_guard &) = delete;
+};
+void ogn_tglr_forget(ogn_ctx *ctx);   // ogn_destroy: the context leaves the per-device bookkeeping
 
 int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place, int nfields,
                    const double *const *fsf, int psize, const double *const *weights, const double *taps,

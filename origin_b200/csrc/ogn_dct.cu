@@ -518,8 +518,11 @@ sums_stream_kernel(const __grid_constant__ CUtensorMap raw_map, const __grid_con
     using L = Stage<DTP, false>;
     extern __shared__ __align__(128) unsigned char smem[];
     Ring ring = ring_init(smem, L::BYTES);
-    double *wsum = reinterpret_cast<double *>(smem + NST * L::BYTES + 64);   // [2][SP/32][ZT]
-    int *wcnt = reinterpret_cast<int *>(wsum + 2 * (SP / 32) * ZT);          // [2][SP/32][ZT]
+    // the block's per-plane sums: every thread parks its 8 values in shared memory, then 16 threads per plane add
+    // them in a fixed order (8 sequential adds each + a 4-level shuffle tree) - 8 shuffles per thread and stage
+    // instead of the 80 of a per-plane warp reduction
+    double *vbuf = reinterpret_cast<double *>(smem + NST * L::BYTES + 64);   // [2][ZT][SP]
+    int *wcnt = reinterpret_cast<int *>(vbuf + 2 * ZT * SP);                 // [2][SP/32][ZT]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, s0 = blockIdx.x * SP;
     const size_t s = (size_t)s0 + tid;
     const bool live = s < S;
@@ -534,6 +537,7 @@ sums_stream_kernel(const __grid_constant__ CUtensorMap raw_map, const __grid_con
     double c[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) c[i] = live ? coef[(size_t)i * S + s] : 0.0;
+    const int rz = tid >> 4, rp = tid & 15;   // reduction role: plane rz of the stage, partial rp of 16
     for (int it = 0; it < nit; ++it) {
         const int slot = it % NST;
         mbar_wait(&ring.bars[slot], (it / NST) & 1);
@@ -542,7 +546,7 @@ sums_stream_kernel(const __grid_constant__ CUtensorMap raw_map, const __grid_con
         const unsigned char *mp = st + L::MASK + tid;
         const double *tabp = reinterpret_cast<const double *>(st + L::TAB);
         const int nrow = min(ZT, z1 - (z0 + it * ZT));
-        double *ws = wsum + ((it & 1) * (SP / 32) + warp) * ZT;
+        double *vb = vbuf + (size_t)(it & 1) * ZT * SP;
         int *wc = wcnt + ((it & 1) * (SP / 32) + warp) * ZT;
 #pragma unroll
         for (int zz = 0; zz < ZT; ++zz) {
@@ -556,25 +560,27 @@ sums_stream_kernel(const __grid_constant__ CUtensorMap raw_map, const __grid_con
                 v = (double)rawp[zz * SP] - cont;
                 hit = true;
             }
+            vb[zz * SP + tid] = v;
             const unsigned b = __ballot_sync(0xffffffffu, hit);
-            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // fixed tree
-            if (lane == 0) { ws[zz] = v; wc[zz] = __popc(b); }
+            if (lane == 0) wc[zz] = __popc(b);
         }
-        __syncthreads();
-        if (tid < nrow) {   // the four warps in order
-            double a = 0.0;
-            int n = 0;
-            for (int w = 0; w < SP / 32; ++w) {
-                a += wsum[((it & 1) * (SP / 32) + w) * ZT + tid];
-                n += wcnt[((it & 1) * (SP / 32) + w) * ZT + tid];
-            }
-            const size_t o = (size_t)blockIdx.x * nz + z0 + it * ZT + tid;
-            psum[o] = a;
-            pcnt[o] = n;
-        }
+        __syncthreads();   // the stage's samples are consumed and the partial values parked
         if (tid == 0 && it + NST < nit)
             issue_stage<DTP, false>(ring.base + slot * L::BYTES, &ring.bars[slot], &raw_map, nullptr, &mask_map, d0p, s0,
                                     z0 + (it + NST) * ZT);
+        {
+            double a = 0.0;
+#pragma unroll
+            for (int j = 0; j < SP / 16; ++j) a += vb[rz * SP + rp + 16 * j];      // fixed order
+            for (int o = 8; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);    // fixed tree over the 16 partials
+            if (rp == 0 && rz < nrow) {
+                int n = 0;
+                for (int w = 0; w < SP / 32; ++w) n += wcnt[((it & 1) * (SP / 32) + w) * ZT + rz];
+                const size_t o = (size_t)blockIdx.x * nz + z0 + it * ZT + rz;
+                psum[o] = a;
+                pcnt[o] = n;
+            }
+        }
     }
 }
 
@@ -902,7 +908,8 @@ static int preprocess_phase1(ogn_ctx *ctx, const void *raw, const void *var, int
         OGN_TRY(ogn_scratch_t(ctx, "prep_psum", (size_t)nblk * nz, &psum));
         OGN_TRY(ogn_scratch_t(ctx, "prep_pcnt", (size_t)nblk * nz, &pcnt));
         using L = k5s::Stage<k5s::DTP, false>;
-        const size_t sm = (size_t)k5s::NST * L::BYTES + 64 + 2 * (k5s::SP / 32) * k5s::ZT * (sizeof(double) + sizeof(int));
+        const size_t sm = (size_t)k5s::NST * L::BYTES + 64 + 2 * k5s::ZT * k5s::SP * sizeof(double) +
+                          2 * (k5s::SP / 32) * k5s::ZT * sizeof(int);
         k5s::sums_stream_kernel<11><<<dim3(nblk, nseg), k5s::SP, sm, ctx->stream>>>(maps.raw, maps.mask, tab.d0p, nz, S, zseg, coef,
                                                                                    psum, pcnt, nx, wy0, wy1, wx0, wx1);
         OGN_LAUNCH_CHECK("sums_stream_kernel");

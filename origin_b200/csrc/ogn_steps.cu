@@ -158,6 +158,7 @@ int step05_run(ogn_ctx *ctx, const Step05Args &a, const int *tile) {
     if (a.sz < 1 || a.sy < 1 || a.sx < 1 || !(a.sz & 1) || !(a.sy & 1) || !(a.sx & 1))
         return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "window (%d,%d,%d): only odd sizes are supported", a.sz, a.sy, a.sx);
     OGN_HT("step05 enter");
+    ogn_tglr_guard guard(ctx);              // constant-memory taps: see ogn_common.cuh
     ogn_timer t_span(ctx, "step05_span");   // first to last device operation of the call (gaps included)
     ogn_tglr_setup_t st;
     OGN_TRY(ogn_tglr_setup(ctx, nz, ny, nx, &place, a.nfields, a.fsf, a.psize, a.weights, a.taps, a.tap_offsets,

@@ -649,6 +649,41 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
 }  // namespace k2
 
 // ---------------------------------------------------------------------------
+// constant-memory hand-over between contexts of one device
+// ---------------------------------------------------------------------------
+#include <mutex>
+namespace {
+std::mutex g_tglr_mutex;
+std::map<int, ogn_ctx *> g_tglr_last;   // device -> context whose taps are in constant memory
+}  // namespace
+
+ogn_tglr_guard::ogn_tglr_guard(ogn_ctx *c) : ctx(c) {
+    g_tglr_mutex.lock();
+    if (!ctx) return;
+    auto it = g_tglr_last.find(ctx->device);
+    if (it != g_tglr_last.end() && it->second != ctx && it->second->tglr_done)
+        cudaStreamWaitEvent(ctx->stream, it->second->tglr_done, 0);   // the other context's kernels still read the constants
+}
+ogn_tglr_guard::~ogn_tglr_guard() {
+    if (ctx) {
+        if (!ctx->tglr_done) cudaEventCreateWithFlags(&ctx->tglr_done, cudaEventDisableTiming);
+        if (ctx->tglr_done) cudaEventRecord(ctx->tglr_done, ctx->stream);
+        g_tglr_last[ctx->device] = ctx;
+    }
+    g_tglr_mutex.unlock();
+}
+void ogn_tglr_forget(ogn_ctx *ctx) {
+    std::lock_guard<std::mutex> lock(g_tglr_mutex);
+    auto it = g_tglr_last.find(ctx->device);
+    if (it != g_tglr_last.end() && it->second == ctx) {
+        if (ctx->tglr_done) cudaEventSynchronize(ctx->tglr_done);
+        g_tglr_last.erase(it);
+    }
+    if (ctx->tglr_done) cudaEventDestroy(ctx->tglr_done);
+    ctx->tglr_done = nullptr;
+}
+
+// ---------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------
 // dst[z][y][dpitch] = src[z][y][nx] * (w ? w[y][x] : 1), zero in the pad columns
@@ -1089,6 +1124,7 @@ extern "C" int ogn_tglr(ogn_ctx *ctx, const void *cube, int cube_dtype, int nz, 
     OGN_CUDA(cudaSetDevice(ctx->device));
     const size_t vol = (size_t)nz * ny * nx;
     const size_t img = (size_t)ny * nx;
+    ogn_tglr_guard guard(ctx);   // constant-memory taps: one TGLR enqueue at a time per process, ordered per device
     ogn_tglr_setup_t st;
     OGN_TRY(ogn_tglr_setup(ctx, nz, ny, nx, nullptr, nfields, fsf, psize, weights, taps, tap_offsets, nprof, true, &st));
 

@@ -19,7 +19,8 @@ import numpy as np
 from . import _lib
 from ._lib import OGN_F32, OGN_F64, OgnError, default_context, ptr
 
-__all__ = ['DCTMAT', 'dct_residual', 'O2test', 'Correlation_GLR_test', 'compute_local_max',
+__all__ = ['DCTMAT', 'dct_residual', 'O2test', 'Compute_PCA_threshold', 'Compute_GreedyPCA', 'Compute_GreedyPCA_area',
+           'Correlation_GLR_test', 'compute_local_max',
            'Compute_threshold_purity', 'prepare_profiles', 'tglr', 'local_extrema', 'LocalExtrema', 'DeviceExtrema',
            'purity_counts', 'check_counts', 'threshold_rows', 'preprocess', 'PurityTable', 'step05', 'fsf_stage']
 
@@ -216,6 +217,75 @@ def preprocess(cube_raw, var, mask, dct_order=10, dct_approx=False, allreduce=No
                                             ptr(out['o2map'])))
     out['mean_lambda'] = mean
     return out
+
+
+# --------------------------------------------------------------------------
+# step03 / step04: PCA threshold and greedy PCA
+# --------------------------------------------------------------------------
+
+def Compute_PCA_threshold(faint, pfa):
+    """O2 test of a block of spectra and its threshold from a Gaussian fit of the test's distribution
+    (reference lib_origin.py:821-842): ``(test, histO2, frecO2, thresO2, mea, std)``.  The fit is the numpy
+    restatement of :mod:`origin_b200.segmap` (the reference's needs astropy)."""
+    from . import segmap
+    test = O2test(faint)
+    test_host = test.detach().cpu().numpy() if _is_torch(test) else test
+    hist, edges, thres, mea, std = segmap.compute_thresh_gaussfit(test_host, pfa)
+    return test_host, hist, edges, thres, mea, std
+
+
+def _greedy_pca_block(cube, cols, test, thres, noise_population, itermax, faint, ctx):
+    """One ``ogn_greedy_pca`` call: the spaxels ``cols`` of the ``(nz, ld)`` matrix view of ``cube``."""
+    nz = cube.shape[0]
+    ld = int(np.prod(cube.shape[1:]))
+    n = ld if cols is None else len(cols)
+    cols = None if cols is None else np.ascontiguousarray(cols, dtype=np.int64)
+    t0 = None if test is None else np.ascontiguousarray(test, dtype=np.float64)
+    if t0 is not None and t0.size != n:
+        raise ValueError('test must hold one value per spaxel of the block')
+    map_o2 = np.zeros(n, dtype=np.float64)
+    info = np.zeros(3, dtype=np.int32)
+    ctx.check(ctx.lib.ogn_greedy_pca(ctx.handle, ptr(cube), _dtype_code(cube), nz, ld, ptr(cols), n, ptr(t0), float(thres),
+                                     float(noise_population), int(itermax), ptr(faint), _dtype_code(faint), ptr(map_o2),
+                                     ptr(info)))
+    return map_o2, int(info[0]), int(info[1]), int(info[2])
+
+
+def Compute_GreedyPCA(cube_in, test, thresO2, Noise_population, itermax, ctx=None):
+    """Greedy PCA of a block of spectra ``(nz, npix)`` (reference lib_origin.py:858-954): returns
+    ``(faint, mapO2, nstop)``.  ``test`` is the block's O2 test (or None to compute it)."""
+    cube = _as_float_cube(cube_in)
+    if cube.ndim != 2:
+        raise ValueError('cube_in must be (nz, npix)')
+    ctx = _ctx_for(cube, ctx)
+    faint = cube.clone() if _is_torch(cube) else cube.copy()
+    map_o2, nstop, _, _ = _greedy_pca_block(cube, None, test, thresO2, Noise_population, itermax, faint, ctx)
+    return faint, map_o2, nstop
+
+
+def Compute_GreedyPCA_area(NbArea, cube_std, areamap, Noise_population, threshold_test, itermax, testO2, ctx=None):
+    """Greedy PCA on each area of the field (reference lib_origin.py:769-818): returns
+    ``(cube_faint, mapO2, nstop)``.  ``cube_std`` may be a numpy cube (the result is a numpy cube of the same
+    dtype) or a CUDA tensor (float32 from the fused step01: ``cube_faint`` then stays on the device for step05)."""
+    cube = _as_float_cube(cube_std)
+    if cube.ndim != 3:
+        raise ValueError('cube_std must be (nz, ny, nx)')
+    ctx = _ctx_for(cube, ctx)
+    areamap = areamap.detach().cpu().numpy() if _is_torch(areamap) else np.asarray(areamap)
+    cube_faint = cube.clone() if _is_torch(cube) else cube.copy()               # :797
+    map_o2 = np.zeros(cube.shape[1:], dtype=np.float64)
+    nstop = 0
+    for area_ind in range(1, NbArea + 1):
+        ksel = areamap == area_ind                                               # :806
+        cols = np.flatnonzero(ksel.reshape(-1))                                  # C order = boolean-mask order of cube[:, ksel]
+        if cols.size == 0:
+            continue
+        test = None if testO2 is None else testO2[area_ind - 1]
+        m, k, _, _ = _greedy_pca_block(cube, cols, test, threshold_test[area_ind - 1], Noise_population, itermax,
+                                       cube_faint, ctx)
+        map_o2[ksel] = m                                                         # :815
+        nstop += k
+    return cube_faint, map_o2, nstop
 
 
 # --------------------------------------------------------------------------

@@ -604,3 +604,32 @@ def test_step05_host_tile_on_the_streamed_path(lo):
         np.testing.assert_array_equal(host['extrema'].max_index, dev['extrema'].max_index.cpu().numpy())
         np.testing.assert_array_equal(host['extrema'].min_value, dev['extrema'].min_value.cpu().numpy())
         np.testing.assert_array_equal(host['maxmap'][ys, xs], dev['maxmap'].cpu().numpy()[ys, xs])
+
+
+def test_two_contexts_on_one_device_do_not_mix_their_dictionaries(lo):
+    """The taps of a TGLR call live in __constant__ memory shared by the contexts of a device: the library orders
+    the calls of different contexts (ogn_tglr_guard), so interleaved asynchronous calls with different
+    dictionaries on two streams still give each context its own result."""
+    import torch
+    from origin_b200 import _lib
+    shape = (200, 64, 64)
+    fsf = torch.from_numpy(synthetic.moffat_fsf(shape[0])).cuda()
+    cube = torch.from_numpy(synthetic.faint_cube(shape, None, n_src=4, seed=17)[0]).cuda()
+    mask = torch.zeros(shape, dtype=torch.uint8, device='cuda')
+    p3, p20 = dictionaries.dico_3fwhm()[0], dictionaries.dico_fwhm_2_12()[0]
+    ref3 = lo.step05(cube, fsf, None, p3, mask, 3, 1e-8, True)
+    ref20 = lo.step05(cube, fsf, None, p20, mask, 3, 1e-8, True)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    c1, c2 = _lib.Context(0, s1.cuda_stream), _lib.Context(0, s2.cuda_stream)
+    outs = []
+    for _ in range(6):        # nothing synchronises in between: the streams would overlap without the guard
+        a = lo.step05(cube, fsf, None, p3, mask, 3, 1e-8, True, ctx=c1, sync=False)
+        b = lo.step05(cube, fsf, None, p20, mask, 3, 1e-8, True, ctx=c2, sync=False)
+        outs.append((a, b))
+    torch.cuda.synchronize()
+    for a, b in outs:
+        assert torch.equal(a['correl'], ref3['correl']) and torch.equal(a['profile'], ref3['profile'])
+        assert torch.equal(b['correl'], ref20['correl']) and torch.equal(b['profile'], ref20['profile'])
+    c1.close()
+    c2.close()
