@@ -320,7 +320,7 @@ def kernel_models(prof_cut, folded_k1, uses_k2f):
         fma, add = k2f_layout(prof_cut)
         k2_slots = 2.0 * (fma + add + len(prof_cut))          # + the normalisation multiply per profile
     else:
-        k2_slots = 2.0 * (sum(-(-len(p) // 4) * 4 for p in prof_cut) + len(prof_cut))
+        k2_slots = 2.0 * (sum(-(-len(p) // 4) * 4 for p in prof_cut) + len(prof_cut))   # taps padded to 4, + normalisation
     return dict(
         k1_fsf_correlate=dict(bound='fp32', algorithmic=2.0 * PSF_SIZE ** 2, executed=k1_slots,
                               kernel='k1::fsf_correlate_kernel<25>' + (' (row-folded: mirror-symmetric FSF)'

@@ -18,21 +18,8 @@
 
 #include "ogn_common.cuh"
 #include "ogn_tma.cuh"
+#include "ogn_tglr_dev.cuh"
 
-// ---------------------------------------------------------------------------
-// Edge classes.  With a single FSF the denominator of the GLR does not depend
-// on the data: norm_fsf[z,y,x] = sum of K_z^2 over the part of the P x P
-// footprint that falls inside the image (lib_origin.py:1039-1041 with
-// weights=None).  Along an axis of length n there are min(n, P) distinct
-// clippings ("classes"); class P/2 is the interior.
-// ---------------------------------------------------------------------------
-__host__ __device__ static inline int cls_of(int y, int n, int P) {
-    int half = P / 2;
-    if (n < P) return y;
-    if (y < half) return y;
-    if (y >= n - half) return P - (n - y);
-    return half;
-}
 __host__ __device__ static inline void cls_range(int c, int n, int P, int *lo, int *hi) {
     int half = P / 2;
     int y;
@@ -392,17 +379,15 @@ constexpr int CONST_TAPS = 15360;
 __constant__ float4 c_taps4[CONST_TAPS / 4];
 __constant__ ProfDesc c_desc[256];
 
-__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
-    if (v >= 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
-    else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
-}
-__device__ __forceinline__ void atomic_min_float(float *addr, float v) {
-    if (v >= 0.f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
-    else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
-}
+using namespace ogn_dev;
 
 // acc[i] += sum_j taps[j] * window[i + j] for one profile, window rows 32 floats apart
-template <int ZB, bool CTAPS>
+// PK = 1: the taps at even window offsets are issued as packed FFMA2 on the accumulator pairs (2p, 2p+1) — the
+// ring slot of window sample t is t mod RING with RING even, so those pairs are even-aligned register pairs; the
+// taps at odd offsets stay scalar FFMAs on the same registers (48 issue slots per 4 taps x 16 outputs instead of 64).
+// PK = 2: the odd offsets are packed as well, on a second accumulator set holding the pairs (2p-1, 2p)
+// (34 slots; 17 more registers).
+template <int ZB, bool CTAPS, int PK = 0>
 __device__ __forceinline__ void ring_correlate(const float *__restrict__ wp, const float4 *__restrict__ tp,
                                                int tap4, int nchunks, float (&acc)[ZB]) {
     constexpr int RING = ZB + 2 * U;
@@ -413,7 +398,10 @@ __device__ __forceinline__ void ring_correlate(const float *__restrict__ wp, con
     for (int t = 0; t < ZB + U - 1; ++t) ring[t] = wp[t * 32];
 #pragma unroll
     for (int i = 0; i < ZB; ++i) acc[i] = 0.f;
-    static_assert(PERIOD % 2 == 0, "tap double buffer needs an even period");
+    float odd[PK == 2 ? ZB : 1], last = 0.f;
+#pragma unroll
+    for (int i = 0; i < (PK == 2 ? ZB : 1); ++i) odd[i] = 0.f;
+    static_assert(PERIOD % 2 == 0 && RING % 2 == 0 && ZB % 2 == 0, "tap double buffer / register pairs need even sizes");
     float4 e[2];
     e[0] = CTAPS ? c_taps4[tap4] : tp[0];
 #pragma unroll 1
@@ -428,25 +416,47 @@ __device__ __forceinline__ void ring_correlate(const float *__restrict__ wp, con
                     ring[(U * qq + ZB + U - 1 + ii) % RING] = wp[(U * qq + ZB + U - 1 + ii) * 32];
                 const float ev[U] = {e[qq & 1].x, e[qq & 1].y, e[qq & 1].z, e[qq & 1].w};
 #pragma unroll
-                for (int ii = 0; ii < U; ++ii)
+                for (int ii = 0; ii < U; ++ii) {
+                    if (PK >= 1 && (ii & 1) == 0) {
+                        const f32x2 tt = pack2(ev[ii], ev[ii]);
 #pragma unroll
-                    for (int i = 0; i < ZB; ++i) acc[i] = fmaf(ev[ii], ring[(U * qq + i + ii) % RING], acc[i]);
+                        for (int p = 0; p < ZB / 2; ++p) {
+                            const int a = (U * qq + 2 * p + ii) % RING;       // even
+                            float lo, hi;
+                            unpack2(fma2(tt, pack2(ring[a], ring[a + 1]), pack2(acc[2 * p], acc[2 * p + 1])), lo, hi);
+                            acc[2 * p] = lo; acc[2 * p + 1] = hi;
+                        }
+                    } else if (PK == 2) {
+                        const f32x2 tt = pack2(ev[ii], ev[ii]);
+#pragma unroll
+                        for (int p = 0; p < ZB / 2; ++p) {                     // pairs (2p-1, 2p)
+                            const int a = (U * qq + 2 * p + ii - 1) % RING;   // even
+                            float lo, hi;
+                            unpack2(fma2(tt, pack2(ring[a], ring[a + 1]), pack2(odd[2 * p], odd[2 * p + 1])), lo, hi);
+                            odd[2 * p] = lo; odd[2 * p + 1] = hi;
+                        }
+                        last = fmaf(ev[ii], ring[(U * qq + ZB - 1 + ii) % RING], last);   // output ZB-1
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < ZB; ++i) acc[i] = fmaf(ev[ii], ring[(U * qq + i + ii) % RING], acc[i]);
+                    }
+                }
             }
         }
         wp += PERIOD * U * 32;
         tp += PERIOD;
         tap4 += PERIOD;
     }
+    if (PK == 2) {   // odd[2p] = output 2p-1 (odd[0] is the unused output -1), odd[2p+1] = output 2p
+#pragma unroll
+        for (int p = 0; p < ZB / 2; ++p) {
+            acc[2 * p] += odd[2 * p + 1];
+            acc[2 * p + 1] += p + 1 < ZB / 2 ? odd[2 * p + 2] : last;
+        }
+    }
 }
 
-__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
-    const uint32_t d = smem_u32(dst);
-    const int bytes = valid ? 16 : 0;  // src-size 0: nothing is read, the 16 bytes are zero-filled
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-template <int ZB, int NW, bool PERVOXEL, bool CTAPS, bool G2>
+template <int ZB, int NW, bool PERVOXEL, bool CTAPS, bool G2, int PK>
 // no minBlocksPerSM here: with it ptxas (12.9) stops using uniform registers for the taps
 __global__ void __launch_bounds__(NW * 32)
 spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_constant__ CUtensorMap den_map,
@@ -572,7 +582,7 @@ spectral_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_co
             for (int k = 0; k < nprof; ++k) {
                 const ProfDesc d = CTAPS ? c_desc[k] : desc[k];
                 float acc[ZB];
-                ring_correlate<ZB, CTAPS>(win + (warp * ZB + d.row_off) * 32 + lane,
+                ring_correlate<ZB, CTAPS, PK>(win + (warp * ZB + d.row_off) * 32 + lane,
                                           reinterpret_cast<const float4 *>(tap_sm + d.tap_off), d.tap_off / 4,
                                           d.nchunks, acc);
                 if (PERVOXEL) {
@@ -985,14 +995,14 @@ static int run_fsf_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setu
     return OGN_OK;
 }
 
-template <int ZB, int NW, bool PV, bool CT, bool G2 = false>
+template <int ZB, int NW, bool PV, bool CT, int PK = 0, bool G2 = false>
 static int launch_spectral(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st, ogn_window w,
                            const float *cube_fsf, const float *norm_fsf, int pitch, const uint8_t *mask,
                            float *correl, float *correl_min, uint8_t *profile, float *maxmap, float *minmap) {
     if (!G2 && st.gather2.dst)   // second destination requested: the variant with the extra store
-        return launch_spectral<ZB, NW, PV, CT, true>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, mask, correl, correl_min,
+        return launch_spectral<ZB, NW, PV, CT, PK, true>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, mask, correl, correl_min,
                                                      profile, maxmap, minmap);
-    auto kern = k2::spectral_glr_kernel<ZB, NW, PV, CT, G2>;
+    auto kern = k2::spectral_glr_kernel<ZB, NW, PV, CT, G2, PK>;
     const int wny = w.y1 - w.y0, wnx = w.x1 - w.x0;
     // window rows per chunk: the chunk itself, the longest profile, and the ring's read-ahead
     const int need_rows = NW * ZB + st.reach + 2 * k2::U;
@@ -1057,16 +1067,22 @@ int ogn_tglr_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &s
     static const int variant = getenv("OGN_K2_VARIANT") ? atoi(getenv("OGN_K2_VARIANT")) : 0;
 #define OGN_K2(ZB_, NW_, CT_) launch_spectral<ZB_, NW_, false, CT_>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, dmask, \
                                                                   d_correl, d_cmin, d_prof, d_maxmap, d_minmap)
+#define OGN_K2P(PK_) launch_spectral<16, 4, false, true, PK_>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, dmask, \
+                                                            d_correl, d_cmin, d_prof, d_maxmap, d_minmap)
     const bool fits = st.ntaps_total + 4 <= k2::CONST_TAPS;
-    // default: 16 wavelengths per thread, 4 warps, taps through the uniform datapath (fastest measured)
+    // default: 16 wavelengths per thread, 4 warps, taps through the uniform datapath, packed FFMA2 on the even tap
+    // offsets (fastest measured at 3681x320x320 with Dico_3FWHM)
     switch (fits ? variant : 100) {
         case 1: return OGN_K2(32, 4, true);
         case 10: return OGN_K2(32, 4, false);
         case 11: return OGN_K2(16, 8, false);
         case 100: return OGN_K2(32, 4, false);
-        default: return OGN_K2(16, 4, true);
+        case 2: return OGN_K2(16, 4, true);   // scalar FFMAs, taps through the uniform datapath (round 1: 2.54 ms)
+        case 21: return OGN_K2P(2);           // FFMA2 on all tap offsets, second accumulator set (2.42 ms)
+        default: return OGN_K2P(1);           // FFMA2 on the even tap offsets, scalar on the odd ones (2.37 ms)
     }
 #undef OGN_K2
+#undef OGN_K2P
 }
 
 __global__ void init_maps_kernel(float *__restrict__ maxmap, float *__restrict__ minmap, size_t n) {

@@ -30,32 +30,12 @@
 
 #include "ogn_common.cuh"
 #include "ogn_tma.cuh"
+#include "ogn_tglr_dev.cuh"
 
 namespace k2f {
 using namespace tma;
 
-__host__ __device__ static inline int cls_of(int y, int n, int P) {
-    int half = P / 2;
-    if (n < P) return y;
-    if (y < half) return y;
-    if (y >= n - half) return P - (n - y);
-    return half;
-}
-
-__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
-    if (v >= 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
-    else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
-}
-__device__ __forceinline__ void atomic_min_float(float *addr, float v) {
-    if (v >= 0.f) atomicMin(reinterpret_cast<int *>(addr), __float_as_int(v));
-    else atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
-}
-__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
-    const uint32_t d = smem_u32(dst);
-    const int bytes = valid ? 16 : 0;  // src-size 0: nothing is read, the 16 bytes are zero-filled
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+using namespace ogn_dev;
 
 // Tap table in constant memory, read as float4 through the uniform datapath (LDCU.64 pairs): the taps
 // enter the FFMAs as uniform-register operands and cost no vector registers.
@@ -66,23 +46,6 @@ __constant__ float4 c_ftaps[MAXT / 4];
 // halves), Rc.F32x2.  Two FMAs of one lane per instruction: measured 72.5 TFLOP/s against 60 for scalar FFMAs
 // of the same shape (acc += uniform tap * sample; tools/ffma2_probe.cu), because the register file delivers
 // a 64-bit pair per operand read, and half the issue slots.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 // accumulators of a group: scalar floats, or pairs of consecutive wavelengths for the packed variant
 template <int G, bool PK> struct Acc;
 template <int G> struct Acc<G, false> {
