@@ -271,6 +271,13 @@ folded_glr_kernel(const __grid_constant__ CUtensorMap num_map, const __grid_cons
             for (int i = 0; i < ZB; ++i) { mx[i] = -INFINITY; mn[i] = INFINITY; arg[i] = 0; }
             const float *rs_col = rs + (size_t)cls_base * nzp + zb;
             const float *rs_warp = rs_sm + (size_t)(stage * NW + warp) * nprof * wz + pass * ZB;
+            if (!rs_staged) {
+                // blocks on the field's left / right edge: every lane has its own edge class, so the 1/sqrt(den) rows
+                // cannot be staged as one broadcast row per profile.  Their 32-byte sectors are requested into L1 now,
+                // a whole pass of arithmetic before the epilogues read them (no register is held meanwhile).
+                for (int k = 0; k < nprof; ++k)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(rs_col + (size_t)k * ncls * nzp));
+            }
 
 #pragma unroll 1
             for (int grp = 0; grp < dict.ngroups; ++grp) {
