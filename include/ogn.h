@@ -374,6 +374,23 @@ OGN_API int ogn_greedy_pca(ogn_ctx *ctx, const void *cube, int dtype, int nz, in
                    double noise_population, int itermax, void *faint, int out_dtype,
                    double *map_o2, int *info);
 
+/* ---- step08: line estimation ----------------------------------------------------- */
+
+/* method_PCA_wgt (lib_origin.py:1535-1617, with LS_deconv_wgt :1482-1510 and conv_wgt :1513-1532) for a batch of
+ * P x P x nz windows of the raw cube - what GridAnalysis (:1620-1790) computes at every offset of its grid for every
+ * detection before its scalar criteria (peak search, flux / mse), which stay host code.  FP64 on the device.
+ *   raw, var      [nz][ny][nx] float32 / float64 (`dtype`), host or device; var = +inf marks invalid voxels
+ *                 (origin.py:262-274); windows may stick out of the image (raw 0 / var +inf there, :1893-1897)
+ *   psf           [nz][P][P] float64, single field
+ *   centres       [npos][2] int32: (y, x) of the centre of each window
+ *   order_dct     order of the DCT that denoises the second eigenvector; < 0 = PCA LS only (order_dct=None)
+ *   line, linevar [npos][nz] float64, host or device: estimated line and its theoretical variance
+ *   info          NULL or {operator applications of the SVDs, problems per batch} */
+OGN_API int ogn_line_estimates(ogn_ctx *ctx, const void *raw, const void *var, int dtype,
+                       int nz, int ny, int nx, const double *psf, int P,
+                       const int *centres, int npos, int order_dct,
+                       double *line, double *linevar, int *info);
+
 #ifdef __cplusplus
 }
 #endif

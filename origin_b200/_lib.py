@@ -74,6 +74,8 @@ SIGNATURES = {
                                       c_void_p]),
     'ogn_greedy_pca': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_int64, c_void_p, c_double, c_double,
                                c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    'ogn_line_estimates': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                   c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'ogn_preprocess': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

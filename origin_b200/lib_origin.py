@@ -22,7 +22,8 @@ from ._lib import OGN_F32, OGN_F64, OgnError, default_context, ptr
 __all__ = ['DCTMAT', 'dct_residual', 'O2test', 'Compute_PCA_threshold', 'Compute_GreedyPCA', 'Compute_GreedyPCA_area',
            'Correlation_GLR_test', 'compute_local_max',
            'Compute_threshold_purity', 'prepare_profiles', 'tglr', 'local_extrema', 'LocalExtrema', 'DeviceExtrema',
-           'purity_counts', 'check_counts', 'threshold_rows', 'preprocess', 'PurityTable', 'step05', 'fsf_stage']
+           'purity_counts', 'check_counts', 'threshold_rows', 'preprocess', 'PurityTable', 'step05', 'fsf_stage',
+           'line_estimates', 'estimation_line', 'peakdet']
 
 
 # --------------------------------------------------------------------------
@@ -907,3 +908,157 @@ def threshold_rows(ext, threshold, profile=None, which='max', ctx=None):
         else:
             rows['profile'] = np.asarray(profile)[z, y, x]
     return rows
+
+
+# --------------------------------------------------------------------------
+# step08: line estimation
+# --------------------------------------------------------------------------
+
+def line_estimates(raw, var, psf, centres, order_dct=30, ctx=None):
+    """``method_PCA_wgt`` (reference lib_origin.py:1535-1617) on the ``P x P x nz`` windows of ``raw`` / ``var``
+    centred at ``centres`` (``(npos, 2)`` array of ``(y, x)``): returns ``(line, linevar)``, float64 arrays
+    ``(npos, nz)``.  One batched device call for all windows."""
+    raw = _as_float_cube(raw)
+    v = _as_float_cube(var)
+    if _dtype_code(v) != _dtype_code(raw):
+        v = v.to(raw.dtype) if _is_torch(v) else v.astype(raw.dtype)
+    nz, ny, nx = raw.shape
+    psf = _f64_any(psf)
+    if psf.ndim != 3 or psf.shape[0] != nz or psf.shape[1] != psf.shape[2]:
+        raise ValueError('psf must be (nz, P, P): one field (weighted mosaics are not supported here)')
+    cen = np.ascontiguousarray(centres, dtype=np.int32).reshape(-1, 2)
+    ctx = _ctx_for(raw, ctx)
+    line = np.empty((len(cen), nz), dtype=np.float64)
+    lvar = np.empty((len(cen), nz), dtype=np.float64)
+    info = np.zeros(2, dtype=np.int32)
+    ctx.check(ctx.lib.ogn_line_estimates(ctx.handle, ptr(raw), ptr(v), _dtype_code(raw), nz, ny, nx, ptr(psf), psf.shape[1],
+                                         ptr(cen), len(cen), -1 if order_dct is None else int(order_dct), ptr(line), ptr(lvar),
+                                         ptr(info)))
+    return line, lvar
+
+
+def peakdet(v):
+    """Local maximum closest to the centre of ``v`` (reference lib_origin.py:1793-1801)."""
+    ind = np.where((v[1:-1] > v[:-2]) & (v[1:-1] > v[2:]))[0] + 1
+    imax = v.size // 2
+    if len(ind) > 0:
+        imax = ind[np.argmin((ind - imax) ** 2)]
+    return imax
+
+
+def _grid_criteria(lines, lvars, offsets, cut, psf, y0, x0, z0, size_grid, horiz, horiz_psf, criteria):
+    """The scalar part of ``GridAnalysis`` (reference lib_origin.py:1680-1790) for one detection, given the line
+    estimates of its grid offsets.  ``cut(zsel, dy, dx)`` returns the ``(len(zsel), 2 horiz_psf + 1, 2 horiz_psf + 1)``
+    values of the raw cube around the centre of the window at offset ``(dy, dx)``."""
+    if criteria not in ('flux', 'mse'):
+        raise ValueError('Bad criteria: (flux) or (mse)')
+    shape = (1 + 2 * size_grid, 1 + 2 * size_grid)
+    nl = lines.shape[1] if len(lines) else psf.shape[0]
+    zest = np.zeros(shape)
+    fest_00 = np.zeros(shape)
+    mse = np.full(shape, np.inf)
+    fest_05 = np.zeros(shape)
+    mse_5 = np.full(shape, np.inf)
+    ind_max = slice(max(0, z0 - 5), min(nl, z0 + 6))
+    longxy = psf.shape[1] // 2
+    inds = slice(longxy - horiz_psf, longxy + 1 + horiz_psf)
+    kept = {}
+    zidx = np.arange(nl)
+    skip_col = set()
+    for k, (dy, dx) in enumerate(offsets):          # reference order: dx outer, dy inner (:1701-1702)
+        if dx in skip_col:
+            continue
+        deconv_met, varest_met = lines[k], lvars[k]
+        z_est = peakdet(deconv_met[ind_max])
+        if z_est == 0:                               # `break` leaves the dy loop of this dx (:1716-1717)
+            skip_col.add(dx)
+            continue
+        maxz = z0 - 5 + z_est
+        zest[dy, dx] = maxz
+        kept[(dy, dx)] = k
+        ind_hrz = zidx[slice(maxz - horiz, maxz + horiz + 1)]      # python slice semantics, as the reference
+        if criteria == 'mse':
+            lc = psf[ind_hrz][:, inds, inds] * deconv_met[ind_hrz][:, None, None]
+            r1 = cut(ind_hrz, dy, dx)
+            mse[dy, dx] = np.sum((r1 - lc) ** 2) / np.sum(r1 ** 2)
+        ind_z5 = np.arange(max(0, maxz - 5), min(maxz + 6, nl))
+        lc = psf[ind_z5][:, inds, inds] * deconv_met[ind_z5][:, None, None]
+        r1 = cut(ind_z5, dy, dx)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            mse_5[dy, dx] = np.sum((r1 - lc) ** 2) / np.sum(r1 ** 2)
+        if criteria == 'flux':
+            fest_00[dy, dx] = np.sum(deconv_met[ind_hrz])
+        fest_05[dy, dx] = np.sum(deconv_met[ind_z5])
+    if criteria == 'flux':
+        wy, wx = np.where(fest_00 == fest_00.max())
+    else:
+        wy, wx = np.where(mse == mse.min())
+    if len(wx) == 0 or len(wy) == 0:
+        return 0.0, 1.0e6, np.array([0]), np.array([0]), y0, x0, z0
+    wy, wx = int(wy[0]), int(wx[0])
+    k = kept.get((wy, wx))
+    est = lines[k] if k is not None else np.zeros(nl)
+    evar = lvars[k] if k is not None else np.zeros(nl)
+    return (float(fest_05[wy, wx]), float(mse_5[wy, wx]), est, evar, int(y0 - size_grid + wy), int(x0 - size_grid + wx),
+            int(zest[wy, wx]))
+
+
+def estimation_line(Cat1, raw, var, psf, wght=None, wcs=None, wave=None, size_grid=1, criteria='flux', order_dct=30,
+                    horiz_psf=1, horiz=5, ctx=None):
+    """Estimated emission line and re-estimated position of every detection (reference ``estimation_line``,
+    lib_origin.py:1805-1938, which calls ``GridAnalysis`` :1620-1790 per detection).  All the windows of all
+    detections go through ONE batched device call (:func:`line_estimates`); the scalar criteria run on the host.
+
+    ``Cat1`` needs columns ``x0, y0, z0`` (an astropy Table or a dict of arrays).  Returns ``(cat2, lin_est, var_est)``
+    where ``cat2`` is a dict with the reference's added columns ``x, y, z, residual, flux, num_line`` (plus
+    ``ra, dec, lbda`` when ``wcs`` / ``wave`` are given) next to the input columns."""
+    if wght is not None:
+        raise NotImplementedError('estimation_line on the device covers the single-field case (wght=None)')
+    nz, ny, nx = raw.shape
+    zs, ys, xs = (np.asarray(Cat1[k], dtype=int) for k in ('z0', 'y0', 'x0'))
+    psf_h = psf.detach().cpu().numpy() if _is_torch(psf) else np.asarray(psf, dtype=np.float64)
+    centres, owner = [], []
+    for d, (y0, x0) in enumerate(zip(ys, xs)):
+        dxl = [dx for dx in range(1 + 2 * size_grid) if 0 <= x0 + dx - size_grid < nx]      # :1696-1699
+        dyl = [dy for dy in range(1 + 2 * size_grid) if 0 <= y0 + dy - size_grid < ny]
+        offs = [(dy, dx) for dx in dxl for dy in dyl]
+        owner.append((len(centres), offs))
+        centres += [(y0 + dy - size_grid, x0 + dx - size_grid) for dy, dx in offs]
+    if centres:
+        lines, lvars = line_estimates(raw, var, psf_h, np.array(centres, dtype=np.int32), order_dct, ctx)
+    else:
+        lines = lvars = np.zeros((0, nz))
+    hp = horiz_psf
+
+    def make_cut(y0, x0):
+        def cut(zsel, dy, dx):
+            cy, cx = y0 + dy - size_grid, x0 + dx - size_grid
+            out = np.zeros((len(zsel), 2 * hp + 1, 2 * hp + 1))
+            ya, yb, xa, xb = max(0, cy - hp), min(ny, cy + hp + 1), max(0, cx - hp), min(nx, cx + hp + 1)
+            if ya < yb and xa < xb and len(zsel):
+                blk = raw[zsel[0]:zsel[-1] + 1, ya:yb, xa:xb] if np.all(np.diff(zsel) == 1) else raw[zsel][:, ya:yb, xa:xb]
+                blk = blk.detach().cpu().numpy() if _is_torch(blk) else np.asarray(blk)
+                out[:, ya - (cy - hp):yb - (cy - hp), xa - (cx - hp):xb - (cx - hp)] = blk
+            return out
+        return cut
+
+    res = []
+    for d, (first, offs) in enumerate(owner):
+        sl = slice(first, first + len(offs))
+        res.append(_grid_criteria(lines[sl], lvars[sl], offs, make_cut(int(ys[d]), int(xs[d])), psf_h, int(ys[d]), int(xs[d]),
+                                  int(zs[d]), size_grid, horiz, horiz_psf, criteria))
+    cat2 = {k: np.asarray(Cat1[k]) for k in (Cat1.colnames if hasattr(Cat1, 'colnames') else Cat1.keys())}
+    if res:
+        flux5, res5, lin_est, var_est, yg, xg, zg = zip(*res)
+    else:
+        flux5 = res5 = yg = xg = zg = ()
+        lin_est = var_est = []
+    cat2.update(x=np.array(xg, dtype=int), y=np.array(yg, dtype=int), z=np.array(zg, dtype=int),
+                residual=np.array(res5, dtype=float), flux=np.array(flux5, dtype=float),
+                num_line=np.arange(1, len(res) + 1))
+    if wcs is not None and len(res):
+        dec, ra = wcs.pix2sky(np.stack((yg, xg)).T).T
+        cat2['ra'], cat2['dec'] = ra, dec
+    if wave is not None and len(res):
+        cat2['lbda'] = wave.coord(np.array(zg))
+    return cat2, list(lin_est), list(var_est)
