@@ -30,7 +30,7 @@ namespace {
 using namespace ogn_lz;
 
 constexpr int LT = 256;
-constexpr int EL_M = 24;          // Krylov vectors per restart cycle
+constexpr int EL_M = 40;          // Krylov vectors per restart cycle
 constexpr int EL_CYCLES = 200;
 constexpr int EL_ZSEG = 128;      // wavelengths per partial sum of X^T q
 
