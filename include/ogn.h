@@ -87,6 +87,11 @@ OGN_API int ogn_timing_report(ogn_ctx *ctx, char *buf, size_t size);
  * footprint rows dy and P-1-dy before multiplying (half the FFMAs of _convolve_fsf's direct form,
  * lib_origin.py:1027-1043), 0 when the general kernel ran.  Synchronises the stream. */
 OGN_API int ogn_fsf_folded(ogn_ctx *ctx, int *folded);
+/* Which code path each stage took on its last launch on `ctx`, as "stage=path;..." (stages: k1, k2, k3,
+ * step01, step05).  The reference has one code path per function (lib_origin.py:150, 1027, 1070, 1220); this
+ * library picks between kernels by shape, alignment and OGN_* diagnostic switches, and the tests pin the
+ * defaults with this call.  No device work. */
+OGN_API int ogn_variants(ogn_ctx *ctx, char *buf, size_t size);
 /* Release the context's scratch memory (it is re-grown on demand). */
 OGN_API int ogn_trim(ogn_ctx *ctx);
 /* Pinned host memory for fast staging (optional; any host pointer works). */

@@ -39,6 +39,7 @@ SIGNATURES = {
     'ogn_peer_sync': (c_int, [c_void_p]),
     'ogn_timing_enable': (c_int, [c_void_p, c_int]),
     'ogn_timing_report': (c_int, [c_void_p, ctypes.c_char_p, ctypes.c_size_t]),
+    'ogn_variants': (c_int, [c_void_p, ctypes.c_char_p, ctypes.c_size_t]),
     'ogn_host_alloc': (c_int, [ctypes.c_size_t, ctypes.POINTER(c_void_p)]),
     'ogn_host_free': (c_int, [c_void_p]),
     'ogn_tglr': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
@@ -166,6 +167,12 @@ class Context:
                 name, ms = item.rsplit(':', 1)
                 out.append((name, float(ms)))
         return out
+
+    def variants(self):
+        """``{stage: code path}`` of the last launch of each stage on this context (``ogn_variants``)."""
+        buf = ctypes.create_string_buffer(4096)
+        self.check(self.lib.ogn_variants(self.handle, buf, len(buf)))
+        return dict(item.split('=', 1) for item in buf.value.decode().split(';') if item)
 
     def trim(self):
         self.check(self.lib.ogn_trim(self.handle))

@@ -164,6 +164,14 @@ extern "C" int ogn_timing_report(ogn_ctx *ctx, char *buf, size_t size) {
     return OGN_OK;
 }
 
+extern "C" int ogn_variants(ogn_ctx *ctx, char *buf, size_t size) {
+    if (!ctx || !buf || size == 0) return OGN_ERR_ARG;
+    std::string out;
+    for (auto &kv : ctx->variants) out += kv.first + "=" + kv.second + ";";
+    snprintf(buf, size, "%s", out.c_str());
+    return OGN_OK;
+}
+
 extern "C" int ogn_fsf_folded(ogn_ctx *ctx, int *folded) {
     if (!ctx || !folded) return OGN_ERR_ARG;
     auto it = ctx->bufs.find("fsf_asym");

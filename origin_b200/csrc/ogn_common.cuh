@@ -69,6 +69,7 @@ struct ogn_ctx {
     float *local_gather = nullptr;                 // ogn_set_local_gather: consumed by the next ogn_step05_tile
     int peer_delay_us = 0;                         // ogn_peer_set_delay
     cudaEvent_t tglr_done = nullptr;               // recorded behind the last TGLR kernel of a call (ogn_tglr_guard)
+    std::map<std::string, std::string> variants;   // stage -> code path of its last launch (ogn_variants)
     bool local_gather_is_peer = false;             // ... it is another device's buffer (mapped with ogn_peer_open)
 };
 

@@ -858,6 +858,7 @@ extern "C" int ogn_dct_residual(ogn_ctx *ctx, const void *raw, const void *var, 
     OGN_TRY(ogn_output(ctx, "dct_cont_out", cont, vol * (out_dtype == OGN_F64 ? 8 : 4), &d_cont));
     DctMaps maps;
     const bool stream = dct_streamable(in.raw, in.var, in.mask, in_dtype, M, S);
+    ctx->variants["step01"] = stream ? "tma-stream" : "column";
     if (stream) OGN_TRY(make_dct_maps(ctx, in.raw, in.var, in.mask, nz, S, &maps));
     if (in_dtype == OGN_F64) {
         OGN_TRY(run_fit<double>(ctx, (const double *)in.raw, (const double *)in.var, in.mask, tab, M, nz, S, approx, coef, nullptr));
@@ -892,6 +893,7 @@ static int preprocess_phase1(ogn_ctx *ctx, const void *raw, const void *var, int
     double *coef = nullptr;
     OGN_TRY(ogn_scratch_t(ctx, "dct_coef", S * M, &coef));
     const bool stream = dct_streamable(in.raw, in.var, in.mask, in_dtype, M, S);
+    ctx->variants["step01"] = stream ? "tma-stream" : "column";
     DctMaps maps;
     if (stream) OGN_TRY(make_dct_maps(ctx, in.raw, in.var, in.mask, nz, S, &maps));
     if (in_dtype == OGN_F64)

@@ -700,6 +700,7 @@ int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t 
                         (!d_dmax || (reinterpret_cast<uintptr_t>(d_dmax) & 15) == 0) &&
                         (!d_dmin || (reinterpret_cast<uintptr_t>(d_dmin) & 15) == 0);
     if (sz == 3 && sy == 3 && sx == 3 && vec_ok && !no_v4_kernel) {
+        ctx->variants["k3"] = "tma3x3x3";
         CUtensorMap a_map, b_map;
         OGN_TRY(ogn_make_tile_map(ctx, &a_map, (const float *)da, nz, ny, nx, nx, E4_BX, E4_ROWS, 1, true));
         OGN_TRY(ogn_make_tile_map(ctx, &b_map, (const float *)db, nz, ny, nx, nx, E4_BX, E4_ROWS, 1, true));
@@ -714,6 +715,7 @@ int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t 
         delete t_k3;
         OGN_LAUNCH_CHECK("local_extrema3_tma_kernel");
     } else if (sz == 3 && sy == 3 && sx == 3) {
+        ctx->variants["k3"] = "scalar3x3x3";
         dim3 block(32, EX_TY + 2);
         dim3 grid(nxw, ogn_div_up(ony, EX_TY), ogn_div_up(nz, EX_CZ));
         local_extrema3_kernel<<<grid, block, 0, ctx->stream>>>((const float *)da, (const float *)db,
@@ -723,6 +725,7 @@ int ogn_extrema_run(ogn_ctx *ctx, const float *a, const float *b, const uint8_t 
         delete t_k3;
         OGN_LAUNCH_CHECK("local_extrema3_kernel");
     } else {
+        ctx->variants["k3"] = "generic";
         dim3 block(32, 8);
         dim3 grid(nxw, ogn_div_up(ony, 8), nz);
         local_extrema_kernel<<<grid, block, 0, ctx->stream>>>((const float *)da, (const float *)db,

@@ -190,6 +190,7 @@ int step05_run(ogn_ctx *ctx, const Step05Args &a, const int *tile) {
                        std::max(0, owned.x0 - a.sx / 2) / 4 * 4, std::min(nx, owned.x1 + a.sx / 2)};
     const bool streamed = !no_stream && host_in && a.cube_dtype == OGN_F32 && !st.pervoxel && ny >= 64 && nx % 4 == 0 &&
                           (!a.mask || !ogn_is_device_ptr(a.mask)) && !st.gather2.dst;
+    ctx->variants["step05"] = streamed ? "slab-pipelined" : "resident";
     if (streamed) return step05_streamed(ctx, a, st, owned, place, w);
     if (a.mask_bits) return ogn_fail(ctx, OGN_ERR_UNSUPPORTED, "a bit-packed mask is only taken on the streamed host path");
 

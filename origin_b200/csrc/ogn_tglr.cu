@@ -737,11 +737,13 @@ static int launch_fsf_correlate(ogn_ctx *ctx, cudaStream_t stream, const float *
         static const int waves = getenv("OGN_K1_WAVES") ? std::max(1, atoi(getenv("OGN_K1_WAVES"))) : 4;
         int zsplit = std::max(1, (ctx->sm_count * 4 * waves) / (tx * ty));
         zsplit = std::min(zsplit, std::max(1, nz / 8));
+        ctx->variants["k1"] = "tma25";
         dim3 grid(tx, ty, zsplit);
         kern<<<grid, k1::THREADS, G::SMEM, stream>>>(map, in_z_invariant, weights, out, wy0, wx0, wny, wnx, opitch, nz,
                                                      zsplit, accumulate, asym);
         OGN_LAUNCH_CHECK("fsf_correlate_kernel");
     } else {
+        ctx->variants["k1"] = "naive";
         dim3 grid(ogn_div_up(wnx, 128), wny, nz);
         fsf_correlate_naive_kernel<<<grid, 128, 0, stream>>>(in, in_z_invariant, iny, inx, ipitch, weights, P, WP, out,
                                                             wy0, wx0, wny, wnx, opitch, nz, accumulate);
@@ -1059,6 +1061,7 @@ int ogn_tglr_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &s
     // touch it: waiting here, not before K1, gives the copy the whole spatial stage to finish)
     OGN_TRY(ogn_wait_readers(ctx, stream, d_correl));
     ogn_timer t_(ctx, "k2_spectral_glr");
+    ctx->variants["k2"] = st.pervoxel ? "pervoxel" : st.fold ? "folded" : "ring";
     if (st.pervoxel)
         return launch_spectral<16, 4, true, false>(ctx, stream, st, w, cube_fsf, norm_fsf, pitch, dmask, d_correl,
                                                    d_cmin, d_prof, d_maxmap, d_minmap);
@@ -1072,6 +1075,7 @@ int ogn_tglr_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &s
     const bool fits = st.ntaps_total + 4 <= k2::CONST_TAPS;
     // default: 16 wavelengths per thread, 4 warps, taps through the uniform datapath, packed FFMA2 on the even tap
     // offsets (fastest measured at 3681x320x320 with Dico_3FWHM)
+    ctx->variants["k2"] = fits ? "ring:" + std::to_string(variant) : "ring:global-taps";
     switch (fits ? variant : 100) {
         case 1: return OGN_K2(32, 4, true);
         case 10: return OGN_K2(32, 4, false);

@@ -486,6 +486,7 @@ int ogn_k2f_launch(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setup_t &st
     static const bool scalar = getenv("OGN_K2F_SCALAR") != nullptr;
 #define OGN_K2F(G_, PK_, MB_) launch_folded<G_, 4, PK_, MB_>(ctx, stream, st, w, cube_fsf, pitch, mask, correl, correl_min, \
                                                            profile, maxmap, minmap)
+    ctx->variants["k2"] = std::string("folded:g") + (st.fold->G <= 3 ? "3" : std::to_string(k2f::GMAX)) + (scalar ? ":ffma" : ":ffma2");
     if (st.fold->G <= 3) return scalar ? OGN_K2F(3, false, 5) : OGN_K2F(3, true, 5);
     if (scalar) return OGN_K2F(k2f::GMAX, false, 3);
     return OGN_K2F(k2f::GMAX, true, 3);

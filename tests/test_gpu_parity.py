@@ -633,3 +633,35 @@ def test_two_contexts_on_one_device_do_not_mix_their_dictionaries(lo):
         assert torch.equal(b['correl'], ref20['correl']) and torch.equal(b['profile'], ref20['profile'])
     c1.close()
     c2.close()
+
+
+def test_default_kernel_variants(lo):
+    """The code paths the library picks when no OGN_* diagnostic switch is set (``ogn_variants``): TMA spatial
+    kernel, constant-tap ring kernel for Dico_3FWHM / folded FFMA2 kernel for Dico_FWHM_2_12, TMA 3x3x3
+    extremum kernel, slab-pipelined step05 for host cubes, TMA-streamed step01 for float32 cubes."""
+    import os
+    import torch
+    from origin_b200._lib import default_context
+    switches = [k for k in os.environ if k.startswith('OGN_') and k not in ('OGN_BENCH_STAGGER_US',)]
+    if switches:
+        pytest.skip('diagnostic switches set: %s' % switches)
+    ctx = default_context()
+    shape = (160, 64, 96)
+    fsf = synthetic.moffat_fsf(shape[0])
+    cube, _ = synthetic.faint_cube(shape, fsf, n_src=3, seed=5)
+    mask = synthetic.footprint_mask(shape, seed=5)
+    lo.step05(cube, fsf, None, dictionaries.dico_3fwhm()[0], mask, 3, 1e-8, True)
+    v = ctx.variants()
+    assert v['k1'] == 'tma25' and v['k2'] == 'ring:0' and v['k3'] == 'tma3x3x3' and v['step05'] == 'slab-pipelined', v
+    assert ctx.fsf_folded                                   # the Moffat FSF is mirror-symmetric: row-folded K1
+    dcube = torch.from_numpy(cube).cuda()
+    dmask = torch.from_numpy(mask.view(np.uint8)).cuda()
+    lo.step05(dcube, fsf, None, dictionaries.dico_fwhm_2_12()[0], dmask, 3, 1e-8, True)
+    v = ctx.variants()
+    assert v['k2'] == 'folded:g10:ffma2' and v['step05'] == 'resident', v
+    raw = (cube * 2 + 1).astype(np.float32)
+    var = np.full(shape, 4.0, np.float32)
+    lo.preprocess(raw, var, mask, dct_order=10)
+    assert ctx.variants()['step01'] == 'tma-stream', ctx.variants()
+    lo.preprocess(raw.astype(np.float64), var.astype(np.float64), mask, dct_order=10)
+    assert ctx.variants()['step01'] == 'column', ctx.variants()
