@@ -212,6 +212,7 @@ struct ogn_tglr_setup_t {
     const void *d_desc = nullptr;
     int ntaps_total = 0, reach = 0, woff_min = 0;
     std::vector<const double *> w_dev;
+    std::vector<ogn_window> w_box;   // per field: bounding box of the support of its weight map (sub-cube coordinates)
     ogn_gather2 gather2;
     std::shared_ptr<k2f::FoldDict> fold;   // set when the dictionary qualifies for K2f (taps already in constant memory)
 };

@@ -221,12 +221,16 @@ __device__ __forceinline__ void strip_fma(float (&acc)[STRIP], const float (&in)
         for (int i = 0; i < STRIP; ++i) acc[i] = fmaf(w[dx], in[i + dx], acc[i]);
 }
 
-template <int P>
+// SUB: the output window is a sub-rectangle of a larger [nz][*][opitch] buffer (one field of a mosaic restricted
+// to its weight footprint): `out` points at the rectangle's first voxel, planes are `oplane` floats apart and
+// columns at or beyond `olimit` are never touched.
+template <int P, bool SUB = false>
 __global__ void __launch_bounds__(THREADS, 4)
 fsf_correlate_kernel(const __grid_constant__ CUtensorMap in_map, int in_z_invariant,
                      const float *__restrict__ weights,  // [nz][P][WP]
                      float *__restrict__ out, int oy0, int ox0, int ony, int onx, int opitch,
-                     int nz, int zsplit, int accumulate, const int *__restrict__ asym) {
+                     int nz, int zsplit, int accumulate, const int *__restrict__ asym, size_t oplane = 0,
+                     int olimit = 0) {
     using G = Geo<P>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *tile = reinterpret_cast<float *>(smem_raw);
@@ -250,7 +254,7 @@ fsf_correlate_kernel(const __grid_constant__ CUtensorMap in_map, int in_z_invari
 
     const int oy = ty0 + row;
     const int ox = tx0 + strip * STRIP;
-    const bool live = oy < ony && ox < opitch;
+    const bool live = oy < ony && ox < (SUB ? olimit : opitch);
     // a warp is 32 rows of one strip: warps whose whole patch lies outside the window skip the
     // arithmetic (they still take part in the barriers), so ragged windows cost 32x32 granularity
     const bool warp_live = (ty0 + (row & ~31)) < ony && ox < onx;
@@ -297,7 +301,7 @@ fsf_correlate_kernel(const __grid_constant__ CUtensorMap in_map, int in_z_invari
         }
 
         if (live && warp_live) {
-            float *op = out + ((size_t)z * ony + oy) * opitch + ox;
+            float *op = SUB ? out + (size_t)z * oplane + (size_t)oy * opitch + ox : out + ((size_t)z * ony + oy) * opitch + ox;
 #pragma unroll
             for (int i = 0; i < STRIP / 4; ++i) {
                 float4 v = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
@@ -710,6 +714,32 @@ __global__ void pitch_copy_kernel(const float *__restrict__ src, const double *_
     dst[((size_t)z * ny + y) * dpitch + x] = v;
 }
 
+// dst[z][y][x] = src[z][y][x] * w[y][x] on the rectangle [y0, y0 + gridDim.y) x [x0, x1) only
+__global__ void weighted_box_kernel(const float *__restrict__ src, const double *__restrict__ w, float *__restrict__ dst,
+                                    int ny, int nx, int dpitch, int y0, int x0, int x1) {
+    const int x = x0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = y0 + blockIdx.y, z = blockIdx.z;
+    if (x < x1) dst[((size_t)z * ny + y) * dpitch + x] = src[((size_t)z * ny + y) * nx + x] * (float)w[(size_t)y * nx + x];
+}
+
+// Bounding box of the support of one weight map (device memory), one thread per row:
+// box[0..3] = max(ny - y), max(y + 1), max(nx - x), max(x + 1) over the voxels with w != 0 (0 when there are none)
+__global__ void weight_box_kernel(const double *__restrict__ w, int ny, int nx, int *__restrict__ box) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= ny) return;
+    int first = -1, last = -1;
+    for (int x = 0; x < nx; ++x)
+        if (!(w[(size_t)y * nx + x] == 0.0)) {
+            if (first < 0) first = x;
+            last = x;
+        }
+    if (first < 0) return;
+    atomicMax(box + 0, ny - y);
+    atomicMax(box + 1, y + 1);
+    atomicMax(box + 2, nx - first);
+    atomicMax(box + 3, last + 1);
+}
+
 // out[z][y][nx] = in[z][y][pitch]
 __global__ void unpitch_kernel(const float *__restrict__ src, float *__restrict__ dst, int ny, int nx, int pitch) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -720,14 +750,17 @@ __global__ void unpitch_kernel(const float *__restrict__ src, float *__restrict_
 // Launch K1 (or the naive fallback) for one field: out (+)= corr(in, weights) on the output window
 // [wy0, wy0+wny) x [wx0, wx0+wnx) of the input; out is window-relative [nz][wny][opitch].
 //   in: device f32 [nz or 1][iny][ipitch], 16-byte aligned, ipitch % 4 == 0
+// oplane != 0 (P == 25 only): the window is a sub-rectangle of a wider buffer whose planes are `oplane` floats
+// apart; `out` points at its first voxel and only columns below `olimit` (a multiple of 32) may be written.
 static int launch_fsf_correlate(ogn_ctx *ctx, cudaStream_t stream, const float *in, int in_z_invariant, int nz,
                                 int iny, int inx, int ipitch, const float *weights, int P, int WP, float *out,
-                                int wy0, int wx0, int wny, int wnx, int opitch, int accumulate, const int *asym) {
+                                int wy0, int wx0, int wny, int wnx, int opitch, int accumulate, const int *asym,
+                                size_t oplane = 0, int olimit = 0) {
     if (P == 25) {
         using G = k1::Geo<25>;
         CUtensorMap map;
         OGN_TRY(ogn_make_tile_map(ctx, &map, in, in_z_invariant ? 1 : nz, iny, inx, ipitch, G::PITCH, G::ROWS));
-        auto kern = k1::fsf_correlate_kernel<25>;
+        auto kern = oplane ? k1::fsf_correlate_kernel<25, true> : k1::fsf_correlate_kernel<25, false>;
         // per device, and cheap: set on every launch rather than cached in a process-wide flag
         OGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
         const int tx = ogn_div_up(wnx, k1::TILE), ty = ogn_div_up(wny, k1::TILE);
@@ -737,12 +770,13 @@ static int launch_fsf_correlate(ogn_ctx *ctx, cudaStream_t stream, const float *
         static const int waves = getenv("OGN_K1_WAVES") ? std::max(1, atoi(getenv("OGN_K1_WAVES"))) : 4;
         int zsplit = std::max(1, (ctx->sm_count * 4 * waves) / (tx * ty));
         zsplit = std::min(zsplit, std::max(1, nz / 8));
-        ctx->variants["k1"] = "tma25";
+        ctx->variants["k1"] = oplane ? "tma25:footprint" : "tma25";
         dim3 grid(tx, ty, zsplit);
         kern<<<grid, k1::THREADS, G::SMEM, stream>>>(map, in_z_invariant, weights, out, wy0, wx0, wny, wnx, opitch, nz,
-                                                     zsplit, accumulate, asym);
+                                                     zsplit, accumulate, asym, oplane, olimit);
         OGN_LAUNCH_CHECK("fsf_correlate_kernel");
     } else {
+        if (oplane) return ogn_fail(ctx, OGN_ERR_ARG, "footprint windows need the 25 x 25 spatial kernel");
         ctx->variants["k1"] = "naive";
         dim3 grid(ogn_div_up(wnx, 128), wny, nz);
         fsf_correlate_naive_kernel<<<grid, 128, 0, stream>>>(in, in_z_invariant, iny, inx, ipitch, weights, P, WP, out,
@@ -867,6 +901,23 @@ int ogn_tglr_setup(ogn_ctx *ctx, int nz, int ny, int nx, const ogn_place *place,
             st->w_dev[f] = static_cast<const double *>(d);
         }
     }
+    // support of every weight map: the spatial stage of a field only runs where its weights can reach
+    st->w_box.assign(nf, ogn_window{0, ny, 0, nx});
+    if (weights) {
+        int *d_box = nullptr;
+        OGN_TRY(ogn_scratch_t(ctx, "wbox", (size_t)4 * nf, &d_box));
+        OGN_TRY(ogn_fill_words(ctx, ctx->stream, d_box, 0u, (size_t)4 * nf * sizeof(int)));
+        for (int f = 0; f < nf; ++f) {
+            weight_box_kernel<<<ogn_div_up(ny, 64), 64, 0, ctx->stream>>>(st->w_dev[f], ny, nx, d_box + 4 * f);
+            OGN_LAUNCH_CHECK("weight_box_kernel");
+        }
+        std::vector<int> box(4 * (size_t)nf);
+        OGN_CUDA(cudaMemcpyAsync(box.data(), d_box, box.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        OGN_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int f = 0; f < nf; ++f)
+            st->w_box[f] = box[4 * f + 1] == 0 ? ogn_window{0, 0, 0, 0}
+                                               : ogn_window{ny - box[4 * f], box[4 * f + 1], nx - box[4 * f + 2], box[4 * f + 3]};
+    }
     // edge classes present in this sub-cube: (row classes) x (column classes)
     std::vector<int> cls_list;
     int *d_cls_list = nullptr;
@@ -964,6 +1015,73 @@ static int run_fsf_window(ogn_ctx *ctx, cudaStream_t stream, const ogn_tglr_setu
     OGN_TRY(ogn_scratch_t(ctx, "cube_fsf", (size_t)nz * wny * pitch, &cube_fsf));
     if (st.pervoxel) OGN_TRY(ogn_scratch_t(ctx, "norm_fsf", (size_t)nz * wny * pitch, &norm_fsf));
     const bool aligned = (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(cube) & 15) == 0);
+    // Mosaics: a field contributes only within P/2 of the support of its weight map (the weighted data and the
+    // weights are zero elsewhere, lib_origin.py:1028-1041), so its two K1 passes run on that rectangle of the window
+    // and add into buffers cleared beforehand.  The rectangle starts on a multiple of 32 columns of the window
+    // (K1 writes whole 32-column strips) and spans a multiple of 32 columns unless the window ends first.
+    static const bool no_footprint = getenv("OGN_K1_NO_FOOTPRINT") != nullptr;
+    std::vector<ogn_window> sub(nf, w);
+    bool restricted = false;
+    if (st.pervoxel && P == 25 && !no_footprint) {
+        for (int f = 0; f < nf; ++f) {
+            if (!st.w_dev[f]) continue;
+            const ogn_window &b = st.w_box[f];
+            ogn_window s{std::max(w.y0, b.y0 - P / 2), std::min(w.y1, b.y1 + P / 2), std::max(w.x0, b.x0 - P / 2),
+                         std::min(w.x1, b.x1 + P / 2)};
+            if (s.y0 >= s.y1 || s.x0 >= s.x1) {
+                s = ogn_window{0, 0, 0, 0};   // the field does not reach this window
+            } else {
+                s.x0 = w.x0 + (s.x0 - w.x0) / 32 * 32;
+                s.x1 = std::min(w.x1, s.x0 + (int)ogn_round_up(s.x1 - s.x0, 32));
+            }
+            sub[f] = s;
+            restricted |= (s.y1 - s.y0) * (int64_t)(s.x1 - s.x0) < (int64_t)wny * wnx;
+        }
+    }
+    if (restricted) {
+        OGN_CUDA(cudaMemsetAsync(cube_fsf, 0, (size_t)nz * wny * pitch * sizeof(float), stream));
+        OGN_CUDA(cudaMemsetAsync(norm_fsf, 0, (size_t)nz * wny * pitch * sizeof(float), stream));
+        for (int f = 0; f < nf; ++f) {
+            const ogn_window &s = sub[f];
+            if (s.y0 >= s.y1) continue;
+            const int ipitch = (int)ogn_round_up(nx, 4), sny = s.y1 - s.y0, snx = s.x1 - s.x0;
+            const size_t off = (size_t)(s.y0 - w.y0) * pitch + (s.x0 - w.x0);
+            const int olimit = pitch - (s.x0 - w.x0);
+            const float *in = cube;
+            int ip = nx;
+            if (st.w_dev[f] || !aligned) {
+                // weighted copy of the inputs the rectangle reads (its rows and columns grown by P/2)
+                float *tmp = nullptr;
+                OGN_TRY(ogn_scratch_t(ctx, "cube_w", (size_t)nz * ny * ipitch, &tmp));
+                const int iy0 = std::max(0, s.y0 - P / 2), iy1 = std::min(ny, s.y1 + P / 2);
+                const int ix0 = std::max(0, s.x0 - P / 2), ix1 = std::min(nx, s.x1 + P / 2);
+                if (st.w_dev[f]) {
+                    dim3 grid(ogn_div_up(ix1 - ix0, 128), iy1 - iy0, nz);
+                    weighted_box_kernel<<<grid, 128, 0, stream>>>(cube, st.w_dev[f], tmp, ny, nx, ipitch, iy0, ix0, ix1);
+                    OGN_LAUNCH_CHECK("weighted_box_kernel");
+                } else {
+                    dim3 grid(ogn_div_up(ipitch, 128), ny, nz);
+                    pitch_copy_kernel<<<grid, 128, 0, stream>>>(cube, nullptr, tmp, nz, ny, nx, ipitch, 0);
+                    OGN_LAUNCH_CHECK("pitch_copy_kernel");
+                }
+                in = tmp;
+                ip = ipitch;
+            }
+            OGN_TRY(launch_fsf_correlate(ctx, stream, in, 0, nz, ny, nx, ip, st.w32 + (size_t)f * nz * P * WP, P, WP,
+                                         cube_fsf + off, s.y0, s.x0, sny, snx, pitch, 1, st.asym, (size_t)wny * pitch, olimit));
+            float *wplane = nullptr;
+            OGN_TRY(ogn_scratch_t(ctx, "wplane", (size_t)ny * ipitch, &wplane));
+            dim3 grid(ogn_div_up(ipitch, 128), ny, 1);
+            pitch_copy_kernel<<<grid, 128, 0, stream>>>(nullptr, st.w_dev[f], wplane, 1, ny, nx, ipitch, 1);
+            OGN_LAUNCH_CHECK("pitch_copy_kernel");
+            OGN_TRY(launch_fsf_correlate(ctx, stream, wplane, 1, nz, ny, nx, ipitch, st.w32sq + (size_t)f * nz * P * WP, P, WP,
+                                         norm_fsf + off, s.y0, s.x0, sny, snx, pitch, 1, st.asym, (size_t)wny * pitch, olimit));
+        }
+        *cube_fsf_out = cube_fsf;
+        *norm_fsf_out = norm_fsf;
+        *pitch_out = pitch;
+        return OGN_OK;
+    }
     for (int f = 0; f < nf; ++f) {
         const float *in = cube;
         int ipitch = nx;

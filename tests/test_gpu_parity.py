@@ -665,3 +665,35 @@ def test_default_kernel_variants(lo):
     assert ctx.variants()['step01'] == 'tma-stream', ctx.variants()
     lo.preprocess(raw.astype(np.float64), var.astype(np.float64), mask, dct_order=10)
     assert ctx.variants()['step01'] == 'column', ctx.variants()
+
+
+def test_mosaic_fields_restricted_to_their_footprints(lo):
+    """Two fields whose weight maps cover different parts of the image: each field's spatial passes run only on
+    the rectangle its weights can reach (``ogn_variants``: k1 = tma25:footprint) and the sum must still be what
+    ``_convolve_fsf`` gives over the whole image (lib_origin.py:1027-1043)."""
+    from origin_b200._lib import default_context
+    shape = (120, 96, 224)
+    nz, ny, nx = shape
+    fsf0 = synthetic.moffat_fsf(nz, fwhm0=3.6, fwhm1=2.9)
+    fsf1 = synthetic.moffat_fsf(nz, fwhm0=4.2, fwhm1=3.1)
+    cube, _ = synthetic.faint_cube(shape, fsf0, n_src=8, seed=41)
+    xx = np.arange(nx)[None, :] * np.ones((ny, 1))
+    w0 = np.clip((100 - xx) / 16.0, 0.0, 1.0)            # field 0: x < 100, full weight below 84
+    w1 = 1.0 - w0                                        # field 1: x > 84 ...
+    w1[:30] = 0.0                                        # ... and only rows >= 30
+    w0[:30, 100:] = 0.0
+    cf, nf = lo.fsf_stage(cube, [fsf0, fsf1], [w0, w1])
+    assert default_context().variants()['k1'] == 'tma25:footprint'
+    rcf, rnf = orc.fsf_correlate(cube, [fsf0, fsf1], [w0, w1])
+    assert_close(cf, rcf, 'mosaic cube_fsf')
+    assert_close(nf, rnf, 'mosaic norm_fsf')
+    # nothing reaches rows < 30 - 12 right of x = 100 + 12: exact zeros there, not stale scratch
+    assert not cf[:, :18, 112:].any() and not nf[:, :18, 112:].any()
+    profs = dictionaries.dico_3fwhm()[0]
+    ref = orc.correlation_glr_test(cube, [fsf0, fsf1], [w0, w1], profs, pcut=1e-8)
+    correl, profile, correl_min = lo.Correlation_GLR_test(cube, [fsf0, fsf1], [w0, w1], profs, pcut=1e-8)
+    sel = np.ones((ny, nx), dtype=bool)
+    sel[:30 + 12, 100 - 12:] = False                     # the footprint sees uncovered voxels there (note N1)
+    assert_close(correl[:, sel], ref[0][:, sel], 'mosaic correl')
+    assert_close(correl_min[:, sel], ref[2][:, sel], 'mosaic correl_min')
+    assert np.mean(profile[:, sel] == ref[1][:, sel]) > 0.999

@@ -15,6 +15,7 @@ g = torch.Generator(device='cuda').manual_seed(0)
 cube = torch.randn(shape, device='cuda', generator=g)
 ctx = lib_origin.default_context()
 ctx.timing(True)
+print('variants after the runs are printed last; OGN_K1_NO_FOOTPRINT=%s' % os.environ.get('OGN_K1_NO_FOOTPRINT'))
 for name, profs in (('3FWHM', dictionaries.dico_3fwhm()[0]), ('2_12', dictionaries.dico_fwhm_2_12()[0])):
     for rep in range(2):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -23,3 +24,4 @@ for name, profs in (('3FWHM', dictionaries.dico_3fwhm()[0]), ('2_12', dictionari
         e1.record(); torch.cuda.synchronize()
         print('%s, %d fields: tglr %.2f ms  %s' % (name, nf, e0.elapsed_time(e1),
               ' '.join('%s=%.3f' % kv for kv in ctx.timing_report())), flush=True)
+print(ctx.variants())
