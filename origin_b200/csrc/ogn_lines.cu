@@ -9,8 +9,11 @@
 //
 //   build_kernel        Xs = raw / sqrt(var), W = 1 / sqrt(var) (0 outside the image: raw 0 / var +inf there, as
 //                       estimation_line pads its minicube, :1893-1897), Xc = Xs - row mean                (:1574-1579)
-//   gemv_t_* / gemv_n   the two halves of the operator X X^T of the batched Lanczos iteration (first left singular
-//                       vector, as ogn_pca.cu: full reorthogonalisation, restarted, tridiagonal solve on the host)
+//   gram_kernel / symv  the first left singular vector comes from the Gram matrix G = X^T X (P*P x P*P, the small side,
+//                       as scipy's svds works on the smaller of X^H X / X X^H): G is formed once per SVD and the
+//                       batched Lanczos iteration (full reorthogonalisation, restarted, tridiagonal solve on the
+//                       host, as ogn_pca.cu) runs on it, 2 nz / (P*P) times cheaper per step than on X X^T;
+//                       u = X v / |X v|.  OGN_LINES_NO_GRAM=1 iterates on X X^T instead (gemv_t_* / gemv_n)
 //   project_deconv      residual = Xs - u (u^T X) and LS_deconv_wgt on it, fused per wavelength          (:1583-1587, :1482-1510)
 //   clean_kernel        data_clean = (data - psf * line) / sqrt(var), centred                            (:1589-1597)
 //   dct_denoise         U = D0 D0^T u with the first order_dct + 1 DCT atoms                              (:1600-1603)
@@ -30,7 +33,8 @@ namespace {
 using namespace ogn_lz;
 
 constexpr int LT = 256;
-constexpr int EL_M = 40;          // Krylov vectors per restart cycle
+constexpr int EL_M = 64;          // most Krylov vectors per restart cycle (layout of Q / scal / y)
+constexpr int EL_M_DEFAULT = 40;  // ... used unless OGN_LINES_KRYLOV says otherwise
 constexpr int EL_CYCLES = 200;
 constexpr int EL_ZSEG = 128;      // wavelengths per partial sum of X^T q
 
@@ -78,18 +82,87 @@ __global__ void gemv_t_finish_kernel(const double *__restrict__ part, int nseg, 
     c[(size_t)p * n + j] = a;
 }
 // y[p][z] = sum_j M[p][z][j] c[p][j]
-__global__ void gemv_n_kernel(const double *__restrict__ M, int nz, int n, const double *__restrict__ c, double *__restrict__ y,
-                              int ldy) {
+__global__ void gemv_n_kernel(const double *__restrict__ M, int nz, int n, const double *__restrict__ c, size_t ldc,
+                              double *__restrict__ y, int ldy) {
     const int z = blockIdx.x, p = blockIdx.y;
     const double *row = M + ((size_t)p * nz + z) * n;
-    const double *cp = c + (size_t)p * n;
+    const double *cp = c + (size_t)p * ldc;
     double a = 0.0;
     for (int j = threadIdx.x; j < n; j += blockDim.x) a = fma(row[j], cp[j], a);
     a = block_sum(a);
     if (threadIdx.x == 0) y[(size_t)p * ldy + z] = a;
 }
 
-// ---- batched Lanczos vector kernels: one block per problem; Q[p][EL_M + 1][nz], scal[p][2 EL_M] ---------------
+// G[p] = M[p]^T M[p] for the [nz][n] matrices M[p] (n x n, symmetric): one block per 64 x 64 tile of the upper
+// triangle, 8 x 4 outputs per thread, wavelengths staged through shared memory GK at a time and summed in
+// order (deterministic); off-diagonal tiles are mirrored on store.
+constexpr int GT = 64, GK = 16;
+__global__ void __launch_bounds__(128) gram_kernel(const double *__restrict__ M, int nz, int n, double *__restrict__ G, int ntile) {
+    __shared__ double sa[GK][GT], sb[GK][GT];
+    int t = blockIdx.x, ta = 0;
+    while (t >= ntile - ta) { t -= ntile - ta; ++ta; }
+    const int tb = ta + t, p = blockIdx.y;
+    const double *Mp = M + (size_t)p * nz * n;
+    double *Gp = G + (size_t)p * n * n;
+    const int a0 = ta * GT, b0 = tb * GT;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // rows a0 + ty + 8 i, columns b0 + tx + 16 j
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int z0 = 0; z0 < nz; z0 += GK) {
+        for (int i = threadIdx.x; i < GK * GT; i += 128) {
+            const int zz = i / GT, c = i % GT, z = z0 + zz;
+            sa[zz][c] = (z < nz && a0 + c < n) ? Mp[(size_t)z * n + a0 + c] : 0.0;
+            sb[zz][c] = (z < nz && b0 + c < n) ? Mp[(size_t)z * n + b0 + c] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int zz = 0; zz < GK; ++zz) {
+            double av[8], bv[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) av[i] = sa[zz][ty + 8 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = sb[zz][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int a = a0 + ty + 8 * i, b = b0 + tx + 16 * j;
+            if (a < n && b < n) {
+                Gp[(size_t)a * n + b] = acc[i][j];
+                if (ta != tb) Gp[(size_t)b * n + a] = acc[i][j];
+            }
+        }
+}
+// y[p][r] = sum_j G[p][r][j] q[p][j]: one warp per row, 8 rows per block
+__global__ void symv_kernel(const double *__restrict__ G, int n, const double *__restrict__ q, size_t ldq, double *__restrict__ y,
+                            int ldy) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, p = blockIdx.y;
+    if (r >= n) return;
+    const double *row = G + ((size_t)p * n + r) * n, *qp = q + (size_t)p * ldq;
+    double a = 0.0;
+    for (int j = lane; j < n; j += 32) a = fma(row[j], qp[j], a);
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) y[(size_t)p * ldy + r] = a;
+}
+__global__ void normalise_kernel(double *__restrict__ u, int nz) {
+    double *up = u + (size_t)blockIdx.x * nz;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) s = fma(up[i], up[i], s);
+    const double nrm = sqrt(block_sum(s));
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) up[i] = nrm > 0.0 ? up[i] / nrm : 0.0;
+}
+
+// ---- batched Lanczos vector kernels: one block per problem; Q[p][EL_M + 1][len], scal[p][2 EL_M] --------------
 __global__ void seed_kernel(double *__restrict__ Q, int nz, size_t qstride) {
     double *q = Q + (size_t)blockIdx.x * qstride;
     double s = 0.0;
@@ -218,7 +291,7 @@ __global__ void dct_denoise_kernel(const double *__restrict__ d0, int M, int nz,
 }
 
 struct LineWork {
-    double *Xs, *W, *Xc, *part, *c, *u, *w, *Q, *scal, *y, *psf, *d0, *line1, *var1;
+    double *Xs, *W, *Xc, *part, *c, *u, *w, *Q, *scal, *y, *psf, *d0, *line1, *var1, *G, *v;
     int *kdim, *centres;
     int nseg;
     size_t qstride;
@@ -234,19 +307,32 @@ int gemv_t(ogn_ctx *ctx, const LineWork &wk, const double *M, int nz, int n, int
 
 // first left singular vectors of the nb matrices Xc[p] into wk.u[p]
 int batched_top_vectors(ogn_ctx *ctx, const LineWork &wk, int nz, int n, int nb, int *matvecs) {
-    const int m = std::min(EL_M, nz);
-    seed_kernel<<<nb, 1024, 0, ctx->stream>>>(wk.Q, nz, wk.qstride);
+    const bool gram = wk.G != nullptr;
+    const int len = gram ? n : nz;   // length of the Lanczos vectors
+    static const int m_cfg = getenv("OGN_LINES_KRYLOV") ? std::max(2, std::min(EL_M, atoi(getenv("OGN_LINES_KRYLOV")))) : EL_M_DEFAULT;
+    const int m = std::min(m_cfg, len);
+    if (gram) {
+        const int ntile = ogn_div_up(n, GT);
+        gram_kernel<<<dim3(ntile * (ntile + 1) / 2, nb), 128, 0, ctx->stream>>>(wk.Xc, nz, n, wk.G, ntile);
+        OGN_LAUNCH_CHECK("gram_kernel");
+    }
+    seed_kernel<<<nb, 1024, 0, ctx->stream>>>(wk.Q, len, wk.qstride);
     OGN_LAUNCH_CHECK("seed_kernel");
     std::vector<double> host((size_t)nb * 2 * EL_M), yall((size_t)nb * EL_M, 0.0), alpha(m), beta(m), y;
     std::vector<int> kdim(nb, m);
     std::vector<char> done(nb, 0);
     for (int cycle = 0; cycle < EL_CYCLES; ++cycle) {
         for (int j = 0; j < m; ++j) {
-            OGN_TRY(gemv_t(ctx, wk, wk.Xc, nz, n, nb, wk.Q + (size_t)j * nz, (int)wk.qstride, wk.c));   // c = X^T q_j
-            gemv_n_kernel<<<dim3(nz, nb), 128, 0, ctx->stream>>>(wk.Xc, nz, n, wk.c, wk.w, nz);       // w = X c
-            OGN_LAUNCH_CHECK("gemv_n_kernel");
+            if (gram) {
+                symv_kernel<<<dim3(ogn_div_up(n, 8), nb), 256, 0, ctx->stream>>>(wk.G, n, wk.Q + (size_t)j * len, wk.qstride, wk.w, len);
+                OGN_LAUNCH_CHECK("symv_kernel");                                                           // w = G q_j
+            } else {
+                OGN_TRY(gemv_t(ctx, wk, wk.Xc, nz, n, nb, wk.Q + (size_t)j * nz, (int)wk.qstride, wk.c));   // c = X^T q_j
+                gemv_n_kernel<<<dim3(nz, nb), 128, 0, ctx->stream>>>(wk.Xc, nz, n, wk.c, n, wk.w, nz);    // w = X c
+                OGN_LAUNCH_CHECK("gemv_n_kernel");
+            }
             ++*matvecs;
-            lanczos_step_kernel<<<nb, 1024, 0, ctx->stream>>>(wk.Q, wk.w, wk.scal, j, nz, wk.qstride);
+            lanczos_step_kernel<<<nb, 1024, 0, ctx->stream>>>(wk.Q, wk.w, wk.scal, j, len, wk.qstride);
             OGN_LAUNCH_CHECK("lanczos_step_kernel");
         }
         OGN_CUDA(cudaMemcpyAsync(host.data(), wk.scal, host.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -270,10 +356,16 @@ int batched_top_vectors(ogn_ctx *ctx, const LineWork &wk, int nz, int n, int nb,
         }
         OGN_CUDA(cudaMemcpyAsync(wk.y, yall.data(), yall.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         OGN_CUDA(cudaMemcpyAsync(wk.kdim, kdim.data(), kdim.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        combine_kernel<<<nb, 1024, 0, ctx->stream>>>(wk.Q, wk.y, wk.kdim, nz, wk.qstride, wk.u, all ? 0 : 1);
+        combine_kernel<<<nb, 1024, 0, ctx->stream>>>(wk.Q, wk.y, wk.kdim, len, wk.qstride, gram ? wk.v : wk.u, all ? 0 : 1);
         OGN_LAUNCH_CHECK("combine_kernel");
         OGN_CUDA(cudaStreamSynchronize(ctx->stream));   // yall / kdim are host vectors reused by the next cycle
         if (all) break;
+    }
+    if (gram) {   // u = X v / |X v|
+        gemv_n_kernel<<<dim3(nz, nb), 128, 0, ctx->stream>>>(wk.Xc, nz, n, wk.v, n, wk.u, nz);
+        OGN_LAUNCH_CHECK("gemv_n_kernel");
+        normalise_kernel<<<nb, 1024, 0, ctx->stream>>>(wk.u, nz);
+        OGN_LAUNCH_CHECK("normalise_kernel");
     }
     return OGN_OK;
 }
@@ -330,12 +422,15 @@ extern "C" int ogn_line_estimates(ogn_ctx *ctx, const void *raw, const void *var
     OGN_TRY(ogn_input(ctx, "el_var", var, vol * es, &d_var));
     OGN_TRY(ogn_input(ctx, "el_psf", psf, (size_t)nz * n * 8, &d_psf));
     OGN_TRY(ogn_input(ctx, "el_centres", centres, (size_t)npos * 2 * sizeof(int), &d_cen));
-    // problems per batch: three [nz][P*P] FP64 matrices each, within ~12 GB of scratch
-    const size_t per = (size_t)nz * n * 8 * 3;
+    // OGN_LINES_NO_GRAM=1: Lanczos on X X^T (length-nz vectors, two passes over X per step) instead of on the Gram matrix
+    static const bool no_gram = getenv("OGN_LINES_NO_GRAM") != nullptr;
+    const int len = std::max(n, nz);
+    // problems per batch: three [nz][P*P] FP64 matrices (+ the Gram matrix) each, within ~12 GB of scratch
+    const size_t per = (size_t)nz * n * 8 * 3 + (no_gram ? 0 : (size_t)n * n * 8);
     const int nb_max = (int)std::max<size_t>(1, std::min<size_t>((size_t)npos, ((size_t)12 << 30) / per));
     LineWork wk;
     wk.nseg = ogn_div_up(nz, EL_ZSEG);
-    wk.qstride = (size_t)(EL_M + 1) * nz;
+    wk.qstride = (size_t)(EL_M + 1) * len;
     wk.psf = const_cast<double *>(static_cast<const double *>(d_psf));
     OGN_TRY(ogn_scratch_t(ctx, "el_Xs", (size_t)nb_max * nz * n, &wk.Xs));
     OGN_TRY(ogn_scratch_t(ctx, "el_W", (size_t)nb_max * nz * n, &wk.W));
@@ -343,7 +438,11 @@ extern "C" int ogn_line_estimates(ogn_ctx *ctx, const void *raw, const void *var
     OGN_TRY(ogn_scratch_t(ctx, "el_part", (size_t)nb_max * wk.nseg * n, &wk.part));
     OGN_TRY(ogn_scratch_t(ctx, "el_c", (size_t)nb_max * n, &wk.c));
     OGN_TRY(ogn_scratch_t(ctx, "el_u", (size_t)nb_max * nz, &wk.u));
-    OGN_TRY(ogn_scratch_t(ctx, "el_w", (size_t)nb_max * nz, &wk.w));
+    OGN_TRY(ogn_scratch_t(ctx, "el_w", (size_t)nb_max * len, &wk.w));
+    OGN_TRY(ogn_scratch_t(ctx, "el_v", (size_t)nb_max * n, &wk.v));
+    wk.G = nullptr;
+    if (!no_gram) OGN_TRY(ogn_scratch_t(ctx, "el_G", (size_t)nb_max * n * n, &wk.G));
+    ctx->variants["step08"] = no_gram ? "lanczos:xxt" : "lanczos:gram";
     OGN_TRY(ogn_scratch_t(ctx, "el_Q", (size_t)nb_max * wk.qstride, &wk.Q));
     OGN_TRY(ogn_scratch_t(ctx, "el_scal", (size_t)nb_max * 2 * EL_M, &wk.scal));
     OGN_TRY(ogn_scratch_t(ctx, "el_y", (size_t)nb_max * EL_M, &wk.y));

@@ -36,7 +36,8 @@ namespace {
 using namespace ogn_lz;
 
 constexpr int PT = 256;
-constexpr int LANCZOS_M = 24;       // Krylov vectors per restart cycle (40 measured slower: most blocks converge in one cycle)
+constexpr int LANCZOS_M = 48;          // most Krylov vectors per restart cycle (layout of Q / scal / y)
+constexpr int LANCZOS_M_DEFAULT = 16;  // ... used unless OGN_PCA_KRYLOV says otherwise (12 / 16 / 24 / 32 / 48: 89 / 89 / 119 / 142 / 233 ms on the probe)
 constexpr int LANCZOS_CYCLES = 200;
 
 template <typename T>
@@ -209,7 +210,8 @@ int gemv_t(ogn_ctx *ctx, const PcaWork &wk, const double *M, int nz, int64_t n, 
 
 // first left singular vector of X [nz][npx] into wk.u (unit norm)
 int top_left_vector(ogn_ctx *ctx, const PcaWork &wk, int nz, int64_t npx, int *matvecs) {
-    const int m = std::min(LANCZOS_M, nz);
+    static const int m_cfg = getenv("OGN_PCA_KRYLOV") ? std::max(2, std::min(LANCZOS_M, atoi(getenv("OGN_PCA_KRYLOV")))) : LANCZOS_M_DEFAULT;
+    const int m = std::min(m_cfg, nz);
     seed_kernel<<<1, 1024, 0, ctx->stream>>>(wk.w, nz);
     OGN_LAUNCH_CHECK("seed_kernel");
     norm_scale_kernel<<<1, 1024, 0, ctx->stream>>>(wk.w, nz, nullptr, wk.Q);
