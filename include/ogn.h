@@ -396,6 +396,18 @@ OGN_API int ogn_line_estimates(ogn_ctx *ctx, const void *raw, const void *var, i
                        const int *centres, int npos, int order_dct,
                        double *line, double *linevar, int *info);
 
+/* The same for weighted mosaics (estimation_line with wght, lib_origin.py:1899-1906): the FSF of a window is
+ * the combination of the fields' FSFs with the weight maps cut to that window, which GridAnalysis forms at
+ * every grid offset (:1713-1717),  psf_eff[p][z][j] = sum_f coef[p][f][j] * psf[f][z][j]  (products rounded and
+ * added in field order, as np.sum(axis=0)).  The host mirror fills `coef`, including the way the reference's
+ * loop re-uses the combined FSF of the previous offset.
+ *   psf    [nf][nz][P][P] float64, host or device
+ *   coef   [npos][nf][P][P] float64, host or device */
+OGN_API int ogn_line_estimates_fields(ogn_ctx *ctx, const void *raw, const void *var, int dtype,
+                       int nz, int ny, int nx, const double *psf, int nf, int P,
+                       const double *coef, const int *centres, int npos, int order_dct,
+                       double *line, double *linevar, int *info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,8 @@ SIGNATURES = {
                                c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'ogn_line_estimates': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                    c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'ogn_line_estimates_fields': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                          c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'ogn_preprocess': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -230,17 +230,30 @@ __global__ void combine_kernel(double *__restrict__ Q, const double *__restrict_
     }
 }
 
+// FSF sample j of wavelength z for one window.  Single field (coef == nullptr): psf[z][j].  Weighted mosaic: the
+// reference combines the fields' FSFs with the weight maps cut to the window, sum_f wgt_f[j] psf_f[z][j]
+// (GridAnalysis, lib_origin.py:1713-1717; products rounded, then added in field order like np.sum(axis=0));
+// `coef` holds the window's [nf][n] factors, psf the fields' cubes [nf][nz][n].
+__device__ __forceinline__ double fsf_sample(const double *__restrict__ psf, const double *__restrict__ coef, int nf, int nz,
+                                             int n, int z, int j) {
+    if (!coef) return psf[(size_t)z * n + j];
+    double a = 0.0;
+    for (int f = 0; f < nf; ++f) a = __dadd_rn(a, __dmul_rn(coef[(size_t)f * n + j], psf[((size_t)f * nz + z) * n + j]));
+    return a;
+}
+
 // residual = Xs - u c^T ; line[z] = varest * sum_j psf W residual ; varest[z] = 1 / sum_j (psf W)^2   (LS_deconv_wgt)
 __global__ void project_deconv_kernel(const double *__restrict__ Xs, const double *__restrict__ W, const double *__restrict__ psf,
-                                      int nz, int n, const double *__restrict__ u, const double *__restrict__ c,
-                                      double *__restrict__ line, double *__restrict__ linevar) {
+                                      const double *__restrict__ coef, int nf, int nz, int n, const double *__restrict__ u,
+                                      const double *__restrict__ c, double *__restrict__ line, double *__restrict__ linevar) {
     const int z = blockIdx.x, p = blockIdx.y;
     const size_t base = ((size_t)p * nz + z) * n;
     const double uz = u[(size_t)p * nz + z];
-    const double *cp = c + (size_t)p * n, *pz = psf + (size_t)z * n;
+    const double *cp = c + (size_t)p * n;
+    const double *cf = coef ? coef + (size_t)p * nf * n : nullptr;
     double num = 0.0, den = 0.0;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const double pw = pz[j] * W[base + j];
+        const double pw = fsf_sample(psf, cf, nf, nz, n, z, j) * W[base + j];
         num = fma(pw, Xs[base + j] - uz * cp[j], num);
         den = fma(pw, pw, den);
     }
@@ -254,17 +267,18 @@ __global__ void project_deconv_kernel(const double *__restrict__ Xs, const doubl
 }
 
 // Xc = (data - psf line) / sqrt(var), rows centred:  Xs - psf line W, minus the row mean
-__global__ void clean_kernel(const double *__restrict__ Xs, const double *__restrict__ W, const double *__restrict__ psf, int nz,
-                             int n, const double *__restrict__ line, double *__restrict__ Xc) {
+__global__ void clean_kernel(const double *__restrict__ Xs, const double *__restrict__ W, const double *__restrict__ psf,
+                             const double *__restrict__ coef, int nf, int nz, int n, const double *__restrict__ line,
+                             double *__restrict__ Xc) {
     const int z = blockIdx.x, p = blockIdx.y;
     const size_t base = ((size_t)p * nz + z) * n;
     const double lz = line[(size_t)p * nz + z];
-    const double *pz = psf + (size_t)z * n;
+    const double *cf = coef ? coef + (size_t)p * nf * n : nullptr;
     double s = 0.0;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
         // conv_wgt multiplies by (|psf| > 0): a no-op for the product psf * line; a NaN line (no valid voxel at this
         // wavelength) times a zero weight is NaN in numpy as well
-        const double v = Xs[base + j] - pz[j] * lz * W[base + j];
+        const double v = Xs[base + j] - fsf_sample(psf, cf, nf, nz, n, z, j) * lz * W[base + j];
         Xc[base + j] = v;
         s += v;
     }
@@ -292,8 +306,9 @@ __global__ void dct_denoise_kernel(const double *__restrict__ d0, int M, int nz,
 
 struct LineWork {
     double *Xs, *W, *Xc, *part, *c, *u, *w, *Q, *scal, *y, *psf, *d0, *line1, *var1, *G, *v;
+    const double *coef;   // weighted mosaics: [npos][nf][P*P] window factors of the fields' FSFs (else nullptr)
     int *kdim, *centres;
-    int nseg;
+    int nseg, nf;
     size_t qstride;
 };
 
@@ -372,17 +387,17 @@ int batched_top_vectors(ogn_ctx *ctx, const LineWork &wk, int nz, int n, int nb,
 
 template <typename T>
 int run_lines(ogn_ctx *ctx, const T *raw, const T *var, int nz, int ny, int nx, int P, const int *d_centres, int nb,
-              int order_dct, const LineWork &wk, double *d_line, double *d_var, int *matvecs) {
-    const int n = P * P;
+              int order_dct, const LineWork &wk, const double *coef, double *d_line, double *d_var, int *matvecs) {
+    const int n = P * P;   // coef: the factors of THIS batch's first window (or nullptr)
     build_kernel<T><<<dim3(nz, nb), LT, 0, ctx->stream>>>(raw, var, nz, ny, nx, P, d_centres, wk.Xs, wk.W, wk.Xc);
     OGN_LAUNCH_CHECK("build_kernel");
     // first PCA: continuum model from the principal vector of the centred, standardised window (:1578-1584)
     OGN_TRY(batched_top_vectors(ctx, wk, nz, n, nb, matvecs));
     OGN_TRY(gemv_t(ctx, wk, wk.Xc, nz, n, nb, wk.u, nz, wk.c));
-    project_deconv_kernel<<<dim3(nz, nb), LT, 0, ctx->stream>>>(wk.Xs, wk.W, wk.psf, nz, n, wk.u, wk.c, wk.line1, wk.var1);
+    project_deconv_kernel<<<dim3(nz, nb), LT, 0, ctx->stream>>>(wk.Xs, wk.W, wk.psf, coef, wk.nf, nz, n, wk.u, wk.c, wk.line1, wk.var1);
     OGN_LAUNCH_CHECK("project_deconv_kernel");
     // remove the first line estimate convolved with the FSF, second PCA (:1589-1598)
-    clean_kernel<<<dim3(nz, nb), LT, 0, ctx->stream>>>(wk.Xs, wk.W, wk.psf, nz, n, wk.line1, wk.Xc);
+    clean_kernel<<<dim3(nz, nb), LT, 0, ctx->stream>>>(wk.Xs, wk.W, wk.psf, coef, wk.nf, nz, n, wk.line1, wk.Xc);
     OGN_LAUNCH_CHECK("clean_kernel");
     OGN_TRY(batched_top_vectors(ctx, wk, nz, n, nb, matvecs));
     if (order_dct >= 0) {
@@ -392,36 +407,33 @@ int run_lines(ogn_ctx *ctx, const T *raw, const T *var, int nz, int ny, int nx, 
     }
     // continuum = U U^T data_st_pca (the UNcentred standardised window, :1606), final LS deconvolution (:1611)
     OGN_TRY(gemv_t(ctx, wk, wk.Xs, nz, n, nb, wk.u, nz, wk.c));
-    project_deconv_kernel<<<dim3(nz, nb), LT, 0, ctx->stream>>>(wk.Xs, wk.W, wk.psf, nz, n, wk.u, wk.c, d_line, d_var);
+    project_deconv_kernel<<<dim3(nz, nb), LT, 0, ctx->stream>>>(wk.Xs, wk.W, wk.psf, coef, wk.nf, nz, n, wk.u, wk.c, d_line, d_var);
     OGN_LAUNCH_CHECK("project_deconv_kernel");
     return OGN_OK;
 }
 
 }  // namespace
 
-// method_PCA_wgt (lib_origin.py:1535-1617) for a batch of P x P x nz windows of the raw cube, i.e. everything
-// GridAnalysis (:1620-1790) computes per grid offset before its scalar criteria.
-//   raw, var     [nz][ny][nx], float32 / float64 (`dtype`), host or device; var = +inf marks invalid voxels
-//   psf          [nz][P][P] float64, single field (host or device)
-//   centres      [npos][2] int32 (y, x): centre of each window; windows may stick out of the image
-//   order_dct    order of the DCT that denoises the second eigenvector (< 0: PCA LS only, order_dct=None)
-//   line, linevar [npos][nz] float64 out (host or device): estimated line and its theoretical variance
-extern "C" int ogn_line_estimates(ogn_ctx *ctx, const void *raw, const void *var, int dtype, int nz, int ny, int nx,
-                                  const double *psf, int P, const int *centres, int npos, int order_dct, double *line,
-                                  double *linevar, int *info) {
+// Shared body of the two entry points: nf = 1 and coef == nullptr for a single field.
+static int line_estimates_impl(ogn_ctx *ctx, const char *who, const void *raw, const void *var, int dtype, int nz, int ny,
+                               int nx, const double *psf, int nf, int P, const double *coef, const int *centres, int npos,
+                               int order_dct, double *line, double *linevar, int *info) {
     if (!ctx) return OGN_ERR_ARG;
-    if (!raw || !var || !psf || !centres || !line || !linevar || nz <= 1 || ny <= 0 || nx <= 0 || npos <= 0 || P < 1 || !(P & 1))
-        return ogn_fail(ctx, OGN_ERR_ARG, "ogn_line_estimates: bad arguments");
-    if (dtype != OGN_F32 && dtype != OGN_F64) return ogn_fail(ctx, OGN_ERR_ARG, "ogn_line_estimates: unknown dtype");
-    if (order_dct + 1 > nz || order_dct > 255) return ogn_fail(ctx, OGN_ERR_ARG, "ogn_line_estimates: order_dct out of range");
+    if (!raw || !var || !psf || !centres || !line || !linevar || nz <= 1 || ny <= 0 || nx <= 0 || npos <= 0 || P < 1 ||
+        !(P & 1) || nf < 1 || (nf > 1 && !coef))
+        return ogn_fail(ctx, OGN_ERR_ARG, "%s: bad arguments", who);
+    if (dtype != OGN_F32 && dtype != OGN_F64) return ogn_fail(ctx, OGN_ERR_ARG, "%s: unknown dtype", who);
+    if (order_dct + 1 > nz || order_dct > 255) return ogn_fail(ctx, OGN_ERR_ARG, "%s: order_dct out of range", who);
     OGN_CUDA(cudaSetDevice(ctx->device));
     const size_t es = dtype == OGN_F64 ? 8 : 4, vol = (size_t)nz * ny * nx;
     const int n = P * P;
     const void *d_raw = nullptr, *d_var = nullptr, *d_psf = nullptr, *d_cen = nullptr;
     OGN_TRY(ogn_input(ctx, "el_raw", raw, vol * es, &d_raw));
     OGN_TRY(ogn_input(ctx, "el_var", var, vol * es, &d_var));
-    OGN_TRY(ogn_input(ctx, "el_psf", psf, (size_t)nz * n * 8, &d_psf));
+    OGN_TRY(ogn_input(ctx, "el_psf", psf, (size_t)nf * nz * n * 8, &d_psf));
     OGN_TRY(ogn_input(ctx, "el_centres", centres, (size_t)npos * 2 * sizeof(int), &d_cen));
+    const void *d_coef = nullptr;
+    if (coef) OGN_TRY(ogn_input(ctx, "el_coef", coef, (size_t)npos * nf * n * 8, &d_coef));
     // OGN_LINES_NO_GRAM=1: Lanczos on X X^T (length-nz vectors, two passes over X per step) instead of on the Gram matrix
     static const bool no_gram = getenv("OGN_LINES_NO_GRAM") != nullptr;
     const int len = std::max(n, nz);
@@ -432,6 +444,8 @@ extern "C" int ogn_line_estimates(ogn_ctx *ctx, const void *raw, const void *var
     wk.nseg = ogn_div_up(nz, EL_ZSEG);
     wk.qstride = (size_t)(EL_M + 1) * len;
     wk.psf = const_cast<double *>(static_cast<const double *>(d_psf));
+    wk.coef = static_cast<const double *>(d_coef);
+    wk.nf = nf;
     OGN_TRY(ogn_scratch_t(ctx, "el_Xs", (size_t)nb_max * nz * n, &wk.Xs));
     OGN_TRY(ogn_scratch_t(ctx, "el_W", (size_t)nb_max * nz * n, &wk.W));
     OGN_TRY(ogn_scratch_t(ctx, "el_Xc", (size_t)nb_max * nz * n, &wk.Xc));
@@ -469,13 +483,41 @@ extern "C" int ogn_line_estimates(ogn_ctx *ctx, const void *raw, const void *var
         const int nb = std::min(nb_max, npos - p0);
         const int *cen = static_cast<const int *>(d_cen) + 2 * p0;
         double *ol = static_cast<double *>(d_line) + (size_t)p0 * nz, *ov = static_cast<double *>(d_lvar) + (size_t)p0 * nz;
+        const double *cf = wk.coef ? wk.coef + (size_t)p0 * nf * n : nullptr;
         if (dtype == OGN_F64)
-            OGN_TRY(run_lines<double>(ctx, (const double *)d_raw, (const double *)d_var, nz, ny, nx, P, cen, nb, order_dct, wk, ol, ov, &matvecs));
+            OGN_TRY(run_lines<double>(ctx, (const double *)d_raw, (const double *)d_var, nz, ny, nx, P, cen, nb, order_dct, wk, cf, ol, ov, &matvecs));
         else
-            OGN_TRY(run_lines<float>(ctx, (const float *)d_raw, (const float *)d_var, nz, ny, nx, P, cen, nb, order_dct, wk, ol, ov, &matvecs));
+            OGN_TRY(run_lines<float>(ctx, (const float *)d_raw, (const float *)d_var, nz, ny, nx, P, cen, nb, order_dct, wk, cf, ol, ov, &matvecs));
     }
     OGN_TRY(ogn_output_commit(ctx, line, d_line, (size_t)npos * nz * 8));
     OGN_TRY(ogn_output_commit(ctx, linevar, d_lvar, (size_t)npos * nz * 8));
     if (info) { info[0] = matvecs; info[1] = nb_max; }
     return ogn_finish_call(ctx);
+}
+
+// method_PCA_wgt (lib_origin.py:1535-1617) for a batch of P x P x nz windows of the raw cube, i.e. everything
+// GridAnalysis (:1620-1790) computes per grid offset before its scalar criteria.
+//   raw, var     [nz][ny][nx], float32 / float64 (`dtype`), host or device; var = +inf marks invalid voxels
+//   psf          [nz][P][P] float64, single field (host or device)
+//   centres      [npos][2] int32 (y, x): centre of each window; windows may stick out of the image
+//   order_dct    order of the DCT that denoises the second eigenvector (< 0: PCA LS only, order_dct=None)
+//   line, linevar [npos][nz] float64 out (host or device): estimated line and its theoretical variance
+extern "C" int ogn_line_estimates(ogn_ctx *ctx, const void *raw, const void *var, int dtype, int nz, int ny, int nx,
+                                  const double *psf, int P, const int *centres, int npos, int order_dct, double *line,
+                                  double *linevar, int *info) {
+    return line_estimates_impl(ctx, "ogn_line_estimates", raw, var, dtype, nz, ny, nx, psf, 1, P, nullptr, centres, npos,
+                               order_dct, line, linevar, info);
+}
+
+// The same for weighted mosaics (wght is not None): the FSF of a window is the combination
+// sum_f coef[p][f][j] psf[f][z][j] of the fields' FSFs, where coef holds the weight maps cut to the window
+// (GridAnalysis, lib_origin.py:1713-1717; the host mirror builds it, including the way the reference's loop
+// compounds the factors from one grid offset to the next).
+//   psf   [nf][nz][P][P] float64;  coef  [npos][nf][P][P] float64 (host or device)
+extern "C" int ogn_line_estimates_fields(ogn_ctx *ctx, const void *raw, const void *var, int dtype, int nz, int ny, int nx,
+                                         const double *psf, int nf, int P, const double *coef, const int *centres, int npos,
+                                         int order_dct, double *line, double *linevar, int *info) {
+    if (ctx && !coef) return ogn_fail(ctx, OGN_ERR_ARG, "ogn_line_estimates_fields: coef is required");
+    return line_estimates_impl(ctx, "ogn_line_estimates_fields", raw, var, dtype, nz, ny, nx, psf, nf, P, coef, centres,
+                               npos, order_dct, line, linevar, info);
 }

@@ -914,26 +914,42 @@ def threshold_rows(ext, threshold, profile=None, which='max', ctx=None):
 # step08: line estimation
 # --------------------------------------------------------------------------
 
-def line_estimates(raw, var, psf, centres, order_dct=30, ctx=None):
+def line_estimates(raw, var, psf, centres, order_dct=30, ctx=None, coef=None):
     """``method_PCA_wgt`` (reference lib_origin.py:1535-1617) on the ``P x P x nz`` windows of ``raw`` / ``var``
     centred at ``centres`` (``(npos, 2)`` array of ``(y, x)``): returns ``(line, linevar)``, float64 arrays
-    ``(npos, nz)``.  One batched device call for all windows."""
+    ``(npos, nz)``.  One batched device call for all windows.
+
+    Weighted mosaics: ``psf`` is ``(nf, nz, P, P)`` (the fields' FSFs) and ``coef`` ``(npos, nf, P, P)`` holds,
+    per window, the factors that combine them, ``sum_f coef[p, f] * psf[f]`` — the weight maps cut to the window,
+    as ``GridAnalysis`` forms them (:1713-1717); :func:`estimation_line` builds it."""
     raw = _as_float_cube(raw)
     v = _as_float_cube(var)
     if _dtype_code(v) != _dtype_code(raw):
         v = v.to(raw.dtype) if _is_torch(v) else v.astype(raw.dtype)
     nz, ny, nx = raw.shape
     psf = _f64_any(psf)
-    if psf.ndim != 3 or psf.shape[0] != nz or psf.shape[1] != psf.shape[2]:
-        raise ValueError('psf must be (nz, P, P): one field (weighted mosaics are not supported here)')
     cen = np.ascontiguousarray(centres, dtype=np.int32).reshape(-1, 2)
+    if coef is None:
+        if psf.ndim != 3 or psf.shape[0] != nz or psf.shape[1] != psf.shape[2]:
+            raise ValueError('psf must be (nz, P, P) for one field; pass (nf, nz, P, P) with coef for a weighted mosaic')
+    else:
+        if psf.ndim != 4 or psf.shape[1] != nz or psf.shape[2] != psf.shape[3]:
+            raise ValueError('psf must be (nf, nz, P, P) when coef is given')
+        coef = _f64_any(coef)
+        if tuple(coef.shape) != (len(cen), psf.shape[0], psf.shape[2], psf.shape[3]):
+            raise ValueError('coef must be (npos, nf, P, P)')
     ctx = _ctx_for(raw, ctx)
     line = np.empty((len(cen), nz), dtype=np.float64)
     lvar = np.empty((len(cen), nz), dtype=np.float64)
     info = np.zeros(2, dtype=np.int32)
-    ctx.check(ctx.lib.ogn_line_estimates(ctx.handle, ptr(raw), ptr(v), _dtype_code(raw), nz, ny, nx, ptr(psf), psf.shape[1],
-                                         ptr(cen), len(cen), -1 if order_dct is None else int(order_dct), ptr(line), ptr(lvar),
-                                         ptr(info)))
+    order = -1 if order_dct is None else int(order_dct)
+    if coef is None:
+        ctx.check(ctx.lib.ogn_line_estimates(ctx.handle, ptr(raw), ptr(v), _dtype_code(raw), nz, ny, nx, ptr(psf), psf.shape[1],
+                                             ptr(cen), len(cen), order, ptr(line), ptr(lvar), ptr(info)))
+    else:
+        ctx.check(ctx.lib.ogn_line_estimates_fields(ctx.handle, ptr(raw), ptr(v), _dtype_code(raw), nz, ny, nx, ptr(psf),
+                                                    psf.shape[0], psf.shape[2], ptr(coef), ptr(cen), len(cen), order,
+                                                    ptr(line), ptr(lvar), ptr(info)))
     return line, lvar
 
 
@@ -946,22 +962,21 @@ def peakdet(v):
     return imax
 
 
-def _grid_criteria(lines, lvars, offsets, cut, psf, y0, x0, z0, size_grid, horiz, horiz_psf, criteria):
+def _grid_criteria(lines, lvars, offsets, cut, psf_core, nl, y0, x0, z0, size_grid, horiz, horiz_psf, criteria):
     """The scalar part of ``GridAnalysis`` (reference lib_origin.py:1680-1790) for one detection, given the line
     estimates of its grid offsets.  ``cut(zsel, dy, dx)`` returns the ``(len(zsel), 2 horiz_psf + 1, 2 horiz_psf + 1)``
-    values of the raw cube around the centre of the window at offset ``(dy, dx)``."""
+    values of the raw cube around the centre of the window at offset ``(dy, dx)``; ``psf_core(k, zsel)`` the same
+    cut of the FSF the ``k``-th offset was estimated with (one FSF for a single field, the weighted combination of
+    that window for a mosaic)."""
     if criteria not in ('flux', 'mse'):
         raise ValueError('Bad criteria: (flux) or (mse)')
     shape = (1 + 2 * size_grid, 1 + 2 * size_grid)
-    nl = lines.shape[1] if len(lines) else psf.shape[0]
     zest = np.zeros(shape)
     fest_00 = np.zeros(shape)
     mse = np.full(shape, np.inf)
     fest_05 = np.zeros(shape)
     mse_5 = np.full(shape, np.inf)
     ind_max = slice(max(0, z0 - 5), min(nl, z0 + 6))
-    longxy = psf.shape[1] // 2
-    inds = slice(longxy - horiz_psf, longxy + 1 + horiz_psf)
     kept = {}
     zidx = np.arange(nl)
     skip_col = set()
@@ -978,11 +993,11 @@ def _grid_criteria(lines, lvars, offsets, cut, psf, y0, x0, z0, size_grid, horiz
         kept[(dy, dx)] = k
         ind_hrz = zidx[slice(maxz - horiz, maxz + horiz + 1)]      # python slice semantics, as the reference
         if criteria == 'mse':
-            lc = psf[ind_hrz][:, inds, inds] * deconv_met[ind_hrz][:, None, None]
+            lc = psf_core(k, ind_hrz) * deconv_met[ind_hrz][:, None, None]
             r1 = cut(ind_hrz, dy, dx)
             mse[dy, dx] = np.sum((r1 - lc) ** 2) / np.sum(r1 ** 2)
         ind_z5 = np.arange(max(0, maxz - 5), min(maxz + 6, nl))
-        lc = psf[ind_z5][:, inds, inds] * deconv_met[ind_z5][:, None, None]
+        lc = psf_core(k, ind_z5) * deconv_met[ind_z5][:, None, None]
         r1 = cut(ind_z5, dy, dx)
         with np.errstate(divide='ignore', invalid='ignore'):
             mse_5[dy, dx] = np.sum((r1 - lc) ** 2) / np.sum(r1 ** 2)
@@ -1003,32 +1018,71 @@ def _grid_criteria(lines, lvars, offsets, cut, psf, y0, x0, z0, size_grid, horiz
             int(zest[wy, wx]))
 
 
+def _window_weights(wght, y0, x0, P, size_grid, offs, ny, nx):
+    """Per-offset factors of the fields' FSFs for one detection of a weighted mosaic, ``(len(offs), nf, P, P)``,
+    restating what the reference's loops do with ``wght`` (lib_origin.py:1899-1906 and :1713-1717):
+
+    * ``estimation_line`` cuts every weight map to the detection's padded minicube (zeros outside the image) and
+      keeps the fields whose cut is not empty; a dropped field has factor 0 here;
+    * at the FIRST grid offset ``GridAnalysis`` forms ``psf = sum_f wgt_f * psf_f`` with the maps cut to that
+      window — and assigns it to the variable the next offsets read, so from the second offset on it computes
+      ``sum_f wgt_f * psf`` with the PREVIOUS combination: the factors of offset k are those of the first one
+      times ``sum_f wgt_f`` of every later offset up to k.  (The ``break`` at :1716 cannot change which offsets
+      take part: it fires only when the +-5 wavelength window around z0 holds at most one sample, which is the
+      same for all offsets of a detection.)  With the step's default ``grid_dxy = 0`` there is one offset."""
+    side = P + 2 * size_grid
+    half = side // 2
+    ya, yb, xa, xb = max(0, y0 - half), min(ny, y0 + half + 1), max(0, x0 - half), min(nx, x0 + half + 1)
+    red = np.zeros((len(wght), side, side))
+    for f, w in enumerate(wght):
+        w = np.asarray(w, dtype=np.float64)
+        if ya < yb and xa < xb and np.sum(w[ya:yb, xa:xb]) > 0:                           # :1901
+            red[f, ya - (y0 - half):yb - (y0 - half), xa - (x0 - half):xb - (x0 - half)] = w[ya:yb, xa:xb]
+    coef = np.zeros((len(offs), len(wght), P, P))
+    for k, (dy, dx) in enumerate(offs):
+        wk = red[:, dy:dy + P, dx:dx + P]
+        coef[k] = wk if k == 0 else coef[k - 1] * wk.sum(axis=0)[None]
+    return coef
+
+
 def estimation_line(Cat1, raw, var, psf, wght=None, wcs=None, wave=None, size_grid=1, criteria='flux', order_dct=30,
-                    horiz_psf=1, horiz=5, ctx=None):
+                    horiz_psf=1, horiz=5, ctx=None, _backend=None):
     """Estimated emission line and re-estimated position of every detection (reference ``estimation_line``,
     lib_origin.py:1805-1938, which calls ``GridAnalysis`` :1620-1790 per detection).  All the windows of all
     detections go through ONE batched device call (:func:`line_estimates`); the scalar criteria run on the host.
 
-    ``Cat1`` needs columns ``x0, y0, z0`` (an astropy Table or a dict of arrays).  Returns ``(cat2, lin_est, var_est)``
-    where ``cat2`` is a dict with the reference's added columns ``x, y, z, residual, flux, num_line`` (plus
-    ``ra, dec, lbda`` when ``wcs`` / ``wave`` are given) next to the input columns."""
-    if wght is not None:
-        raise NotImplementedError('estimation_line on the device covers the single-field case (wght=None)')
+    ``Cat1`` needs columns ``x0, y0, z0`` (an astropy Table or a dict of arrays).  ``psf`` / ``wght`` as in the
+    reference: one ``(nz, P, P)`` FSF and None, or a list of FSFs with the list of the fields' weight maps
+    (:func:`_window_weights`).  Returns ``(cat2, lin_est, var_est)`` where ``cat2`` is a dict with the reference's
+    added columns ``x, y, z, residual, flux, num_line`` (plus ``ra, dec, lbda`` when ``wcs`` / ``wave`` are given)
+    next to the input columns.  ``_backend`` replaces :func:`line_estimates` (CPU tests of this host logic)."""
     nz, ny, nx = raw.shape
     zs, ys, xs = (np.asarray(Cat1[k], dtype=int) for k in ('z0', 'y0', 'x0'))
-    psf_h = psf.detach().cpu().numpy() if _is_torch(psf) else np.asarray(psf, dtype=np.float64)
-    centres, owner = [], []
+    to_host = lambda a: a.detach().cpu().numpy().astype(np.float64) if _is_torch(a) else np.asarray(a, dtype=np.float64)
+    if wght is None:
+        psf_h = to_host(psf)                                                            # (nz, P, P)
+        P = psf_h.shape[1]
+    else:
+        psf_h = np.stack([to_host(f) for f in psf])                                     # (nf, nz, P, P)
+        if len(wght) != len(psf_h):
+            raise ValueError('psf and wght must have the same length')
+        P = psf_h.shape[2]
+    centres, owner, coefs = [], [], []
     for d, (y0, x0) in enumerate(zip(ys, xs)):
         dxl = [dx for dx in range(1 + 2 * size_grid) if 0 <= x0 + dx - size_grid < nx]      # :1696-1699
         dyl = [dy for dy in range(1 + 2 * size_grid) if 0 <= y0 + dy - size_grid < ny]
         offs = [(dy, dx) for dx in dxl for dy in dyl]
         owner.append((len(centres), offs))
         centres += [(y0 + dy - size_grid, x0 + dx - size_grid) for dy, dx in offs]
+        if wght is not None and offs:
+            coefs.append(_window_weights(wght, int(y0), int(x0), P, size_grid, offs, ny, nx))
+    coef = np.concatenate(coefs) if coefs else None
     if centres:
-        lines, lvars = line_estimates(raw, var, psf_h, np.array(centres, dtype=np.int32), order_dct, ctx)
+        lines, lvars = (_backend or line_estimates)(raw, var, psf_h, np.array(centres, dtype=np.int32), order_dct, ctx, coef)
     else:
         lines = lvars = np.zeros((0, nz))
     hp = horiz_psf
+    inds = slice(P // 2 - hp, P // 2 + 1 + hp)
 
     def make_cut(y0, x0):
         def cut(zsel, dy, dx):
@@ -1042,11 +1096,16 @@ def estimation_line(Cat1, raw, var, psf, wght=None, wcs=None, wave=None, size_gr
             return out
         return cut
 
+    def make_psf_core(first):
+        if coef is None:
+            return lambda k, zsel: psf_h[zsel][:, inds, inds]
+        return lambda k, zsel: np.sum(coef[first + k][:, None, inds, inds] * psf_h[:, zsel][:, :, inds, inds], axis=0)
+
     res = []
     for d, (first, offs) in enumerate(owner):
         sl = slice(first, first + len(offs))
-        res.append(_grid_criteria(lines[sl], lvars[sl], offs, make_cut(int(ys[d]), int(xs[d])), psf_h, int(ys[d]), int(xs[d]),
-                                  int(zs[d]), size_grid, horiz, horiz_psf, criteria))
+        res.append(_grid_criteria(lines[sl], lvars[sl], offs, make_cut(int(ys[d]), int(xs[d])), make_psf_core(first), nz,
+                                  int(ys[d]), int(xs[d]), int(zs[d]), size_grid, horiz, horiz_psf, criteria))
     cat2 = {k: np.asarray(Cat1[k]) for k in (Cat1.colnames if hasattr(Cat1, 'colnames') else Cat1.keys())}
     if res:
         flux5, res5, lin_est, var_est, yg, xg, zg = zip(*res)

@@ -84,3 +84,29 @@ def test_line_estimates_float32_device_cubes(scene):
                                       torch.from_numpy(var.astype(np.float32)).cuda(), psf, cen, 30)
     assert np.abs(a - b).max() <= 1e-5 * np.abs(a).max()
     np.testing.assert_allclose(va, vb, rtol=1e-5)
+
+
+@pytest.mark.parametrize('size_grid', [0, 1])
+def test_estimation_line_weighted_mosaic_matches_grid_analysis(size_grid):
+    """Weighted mosaic (``wght`` not None, lib_origin.py:1899-1906, :1713-1717): three fields with different FSFs,
+    an uncovered strip, a field that only touches one corner; the device combines the fields' FSFs per window
+    (``ogn_line_estimates_fields``).  ``size_grid = 0`` is the step's default (``grid_dxy``, steps.py:1082)."""
+    import test_lines_host as th
+    from origin_b200 import lib_origin
+    raw, var, psf, wght, cat = th.make_scene(True)
+    ref = th.reference_grid(raw, var, psf, wght, cat, size_grid, 'flux', 20)
+    cat2, lin_est, var_est = lib_origin.estimation_line(cat, raw, var, psf, wght, None, None, size_grid=size_grid,
+                                                        criteria='flux', order_dct=20, horiz_psf=1, horiz=5)
+    th.check(cat2, lin_est, var_est, ref, 1e-8)
+
+
+def test_line_estimates_fields_equals_single_field_with_unit_weights():
+    """One field with weight 1 everywhere through the weighted entry point = the single-field entry point."""
+    import test_lines_host as th
+    from origin_b200 import lib_origin
+    raw, var, psf, _, cat = th.make_scene(False)
+    cen = np.stack([cat['y0'], cat['x0']], axis=1)
+    a, va = lib_origin.line_estimates(raw, var, psf, cen, 20)
+    b, vb = lib_origin.line_estimates(raw, var, psf[None], cen, 20, coef=np.ones((len(cen), 1) + psf.shape[1:]))
+    assert np.abs(a - b).max() <= 1e-11 * np.abs(a).max()
+    np.testing.assert_allclose(va, vb, rtol=1e-11)
