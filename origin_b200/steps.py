@@ -8,14 +8,16 @@ the thresholding block).  Two levels of drop-in are offered:
 
 ``patch_steps(fused=False)``
     rebinds ``dct_residual``, ``compute_local_max``, ``Correlation_GLR_test``,
-    ``Compute_threshold_purity`` and ``O2test`` in the ``muse_origin.steps``
-    namespace to the B200 implementations of :mod:`origin_b200.lib_origin`;
-    the reference's ``run`` methods stay untouched.
+    ``Compute_threshold_purity``, ``O2test``, ``Compute_GreedyPCA_area`` (step04)
+    and ``estimation_line`` (step08) in the ``muse_origin.steps`` namespace to the
+    B200 implementations of :mod:`origin_b200.lib_origin`; the reference's
+    ``run`` methods stay untouched.
 
 ``patch_steps(fused=True)`` (default)
-    additionally replaces the ``run`` methods of steps 01, 05 and 06 by the
-    fused versions below, which keep intermediates on the device, carry the
-    local extrema as compact lists (:class:`~origin_b200.lib_origin.LocalExtrema`)
+    additionally replaces the ``run`` methods of steps 01, 04, 05 and 06 by the
+    fused versions below, which keep intermediates on the device (``cube_faint``
+    goes from the greedy PCA of step04 into step05 without crossing PCIe), carry
+    the local extrema as compact lists (:class:`~origin_b200.lib_origin.LocalExtrema`)
     and materialise the dense cubes the step API promises
     (``cube_local_max`` ...) from them.  ``Detection.run`` is left as it is
     (its two ``np.where`` blocks then read those dense cubes); INTEGRATION.md
@@ -114,8 +116,13 @@ class LazyProduct:
     nobody reads (``cube_correl_min`` after a fused step06, the dense local-extremum cubes) never cross PCIe.
     """
 
-    def __init__(self, step, name, fetch, kind='cube', shape=None):
-        object.__setattr__(self, '_lazy', dict(step=step, name=name, fetch=fetch, kind=kind, shape=shape))
+    def __init__(self, step, name, fetch, kind='cube', shape=None, device=None):
+        object.__setattr__(self, '_lazy', dict(step=step, name=name, fetch=fetch, kind=kind, shape=shape, device=device))
+
+    def on_device(self):
+        """The CUDA tensor behind the placeholder (None when it only exists as a list), without fetching anything:
+        the next fused step reads this instead of the host copy."""
+        return object.__getattribute__(self, '_lazy')['device']
 
     def materialise(self):
         st = object.__getattribute__(self, '_lazy')
@@ -138,9 +145,12 @@ class LazyProduct:
 
 def _fetch_device(tensor, dtype):
     def fetch():
-        arr = tensor.detach().cpu().numpy() if lo._is_torch(tensor) else np.asarray(tensor)
-        return arr.astype(dtype, copy=False)
+        return _host(tensor).astype(dtype, copy=False)
     return fetch
+
+
+def _host(x):
+    return x.detach().cpu().numpy() if lo._is_torch(x) else np.asarray(x)
 
 
 def _packed_mask(orig):
@@ -185,6 +195,27 @@ def _run_preprocessing(self, orig, dct_order=10, dct_approx=False, pfasegcont=0.
     self.store_image('segmap_merged', segmap)
 
 
+def _run_greedy_pca(self, orig, Noise_population=50, itermax=100, threshold_list=None):
+    """Fused ``ComputeGreedyPCA.run`` (reference steps.py:681-704): the standardised cube is uploaded once, the
+    greedy PCA of every area runs on the device (:func:`origin_b200.lib_origin.Compute_GreedyPCA_area`) and
+    ``cube_faint`` stays there — a :class:`LazyProduct` that the fused step05 reads on the device and that only
+    turns into the reference's float64 ``Cube`` when somebody else looks at it (plots, ``dump``)."""
+    thr = orig.thresO2 if threshold_list is None else threshold_list
+    orig.param['threshold_list'] = thr
+    self._loginfo('Thresholds of the areas: %s', ' '.join('%.2f' % t for t in thr))
+    self._loginfo('Greedy PCA of each area (B200)')
+    torch = lo._torch()
+    std = orig.cube_std._data
+    std = np.ascontiguousarray(std, dtype=np.float32 if std.dtype == np.float32 else np.float64)
+    faint, map_o2, nstop = lo.Compute_GreedyPCA_area(orig.nbAreas, torch.from_numpy(std).cuda(), orig.areamap._data,
+                                                     Noise_population, thr, itermax, orig.testO2)
+    if nstop > 0:
+        self._logwarning('The iteration limit of %d was reached in %d cases', itermax, nstop)
+    setattr(self, 'cube_faint', LazyProduct(self, 'cube_faint', _fetch_device(faint, np.float64), 'cube',
+                                            tuple(faint.shape), device=faint))
+    self.store_image('mapO2', map_o2)
+
+
 def _run_compute_tglr(self, orig, size=3, ncpu=1, pcut=1e-8, pmeansub=True):
     """Fused ``ComputeTGLR.run`` (reference steps.py:756-802); ``ncpu`` is ignored.
 
@@ -193,12 +224,19 @@ def _run_compute_tglr(self, orig, size=3, ncpu=1, pcut=1e-8, pmeansub=True):
     lists; all four are :class:`LazyProduct` attributes that turn into the reference's ``Cube`` objects when
     somebody reads them (the fused step06 reads the lists, ``Detection`` the dense cubes, ``dump`` everything)."""
     self._loginfo('Correlation (B200)')
-    cube = orig.cube_faint._data
+    faint = orig.cube_faint
+    cube = faint.on_device() if isinstance(faint, LazyProduct) else None
     kw = {}
-    if (orig.wfields is None and isinstance(cube, np.ndarray) and cube.dtype == np.float32 and cube.shape[2] % 8 == 0
-            and cube.shape[1] >= 128):
-        kw = dict(mask_bits=_packed_mask(orig), on_device=('correl_min', 'profile'))
-    out = compute_tglr(cube, orig.PSF, orig.wfields, orig.profiles, None if kw else orig.mask, size, pcut, pmeansub, **kw)
+    if cube is not None:
+        # straight from the fused step04: nothing is uploaded; cube_correl is the one product written to the host
+        kw = dict(out=dict(correl=np.empty(tuple(cube.shape), dtype=np.float32)))
+    else:
+        cube = faint._data
+        if (orig.wfields is None and isinstance(cube, np.ndarray) and cube.dtype == np.float32 and cube.shape[2] % 8 == 0
+                and cube.shape[1] >= 128):
+            kw = dict(mask_bits=_packed_mask(orig), on_device=('correl_min', 'profile'))
+    out = compute_tglr(cube, orig.PSF, orig.wfields, orig.profiles, None if 'mask_bits' in kw else orig.mask, size, pcut,
+                       pmeansub, **kw)
     self.store_cube('cube_correl', out['cube_correl'])
     shape = tuple(out['cube_correl'].shape)
     for name, key, dt in (('cube_correl_min', 'cube_correl_min', np.float64), ('cube_profile', 'cube_profile', np.uint8)):
@@ -206,8 +244,8 @@ def _run_compute_tglr(self, orig, size=3, ncpu=1, pcut=1e-8, pmeansub=True):
             setattr(self, name, LazyProduct(self, name, _fetch_device(out[key], dt), 'cube', shape))
         else:
             self.store_cube(name, out[key])
-    self.store_image('maxmap', out['maxmap'])
-    self.store_image('minmap', out['minmap'])
+    self.store_image('maxmap', _host(out['maxmap']))
+    self.store_image('minmap', _host(out['minmap']))
     ext = out['extrema']
     self._ogn_extrema = ext
     self._ogn_profile = out['cube_profile']
@@ -243,6 +281,7 @@ def _run_purity(self, orig, purity=0.9, purity_std=None, threshlist=None, pfaseg
 
 _STEPS_MODULE = None
 _ORIGINALS = {}
+_ABSENT = object()      # the patched module did not have that name
 
 
 def _segmap_gauss(mod):
@@ -269,14 +308,18 @@ def patch_steps(steps_module=None, fused=True):
         'Correlation_GLR_test': lo.Correlation_GLR_test,
         'Compute_threshold_purity': _threshold_purity_astropy,
         'O2test': lo.O2test,
+        'Compute_GreedyPCA_area': lo.Compute_GreedyPCA_area,
+        'estimation_line': _estimation_line_table,
     }
     for name, fn in names.items():
-        _ORIGINALS.setdefault(name, getattr(steps_module, name, None))
+        _ORIGINALS.setdefault(name, getattr(steps_module, name, _ABSENT))
         setattr(steps_module, name, fn)
     if fused:
-        for cls_name, run in (('Preprocessing', _run_preprocessing), ('ComputeTGLR', _run_compute_tglr),
-                              ('ComputePurityThreshold', _run_purity)):
-            cls = getattr(steps_module, cls_name)
+        for cls_name, run in (('Preprocessing', _run_preprocessing), ('ComputeGreedyPCA', _run_greedy_pca),
+                              ('ComputeTGLR', _run_compute_tglr), ('ComputePurityThreshold', _run_purity)):
+            cls = getattr(steps_module, cls_name, None)
+            if cls is None:                 # a stand-in module without that step
+                continue
             _ORIGINALS.setdefault(cls_name + '.run', cls.run)
             cls.run = run
     return dict(_ORIGINALS)
@@ -290,7 +333,10 @@ def unpatch_steps():
         if '.' in key:
             cls_name, attr = key.split('.')
             setattr(getattr(mod, cls_name), attr, val)
-        elif val is not None:
+        elif val is _ABSENT:
+            if hasattr(mod, key):
+                delattr(mod, key)
+        else:
             setattr(mod, key, val)
     _ORIGINALS.clear()
 
@@ -303,3 +349,28 @@ def _threshold_purity_astropy(purity, cube_local_max, cube_local_min, segmap=Non
         return thr, tab.to_astropy()
     except ImportError:
         return thr, tab
+
+
+def _estimation_line_table(Cat1, raw, var, psf, wght, wcs, wave, size_grid=1, criteria='flux', order_dct=30, horiz_psf=1,
+                           horiz=5):
+    """``estimation_line`` with the reference's signature and return types (lib_origin.py:1805-1938, called from
+    ``ComputeSpectra.run``, steps.py:1083-1096): when ``Cat1`` is an astropy Table the result is a copy of it with
+    ``ra, dec, lbda`` updated and the columns ``x, y, z, residual, flux, num_line`` inserted where the reference puts
+    them (:1925-1936); a plain dict of columns comes back as a dict."""
+    cat2, lin_est, var_est = lo.estimation_line(Cat1, raw, var, psf, wght, wcs, wave, size_grid=size_grid, criteria=criteria,
+                                                order_dct=order_dct, horiz_psf=horiz_psf, horiz=horiz)
+    return _cat2_table(Cat1, cat2), lin_est, var_est
+
+
+def _cat2_table(Cat1, cat2):
+    """``Cat2`` in the container ``Cat1`` came in: a dict stays a dict; an astropy Table is copied, gets its sky
+    coordinates updated and the six new columns inserted at the reference's positions (lib_origin.py:1915-1936)."""
+    if not hasattr(Cat1, 'add_columns'):
+        return cat2
+    tab = Cat1.copy()
+    for name in ('ra', 'dec', 'lbda'):
+        if name in cat2:
+            tab[name] = cat2[name]
+    new = [tab.Column(name=name, data=cat2[name]) for name in ('x', 'y', 'z', 'residual', 'flux', 'num_line')]
+    tab.add_columns(new, indexes=[4, 5, 6, 8, 8, 8])
+    return tab

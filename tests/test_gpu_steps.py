@@ -27,6 +27,9 @@ class FakeStep:
     def _loginfo(self, *a):
         self.log.append(a)
 
+    def _logwarning(self, *a):
+        self.log.append(a)
+
     # like the reference's Step.store_cube / store_image (steps.py:284-299): the product becomes an attribute of
     # the STEP; the ORIGIN object finds it there (origin.py:246-253)
     def store_cube(self, name, data, **kw):
@@ -56,7 +59,7 @@ def fake_steps_module():
     mod.compute_segmap_gauss = lambda img, pfa, fwhm, bins='fd': (0.0, (img > np.percentile(img, 97)).astype(int))
     for name in ('dct_residual', 'compute_local_max', 'Correlation_GLR_test', 'Compute_threshold_purity', 'O2test'):
         setattr(mod, name, None)
-    for cls in ('Preprocessing', 'ComputeTGLR', 'ComputePurityThreshold'):
+    for cls in ('Preprocessing', 'ComputeGreedyPCA', 'ComputeTGLR', 'ComputePurityThreshold'):
         setattr(mod, cls, type(cls, (FakeStep,), {'run': lambda self, orig: None}))
     return mod
 
@@ -140,3 +143,57 @@ def test_fused_tglr_keeps_unread_products_on_the_device():
         np.testing.assert_array_equal(orig.maxmap._data, ref['maxmap'])
     finally:
         steps.unpatch_steps()
+
+
+def test_fused_greedy_pca_hands_cube_faint_to_step05_on_the_device():
+    """Fused step04 -> step05 (steps.py:681-704, :756-802): ``cube_faint`` is a LazyProduct backed by a CUDA
+    tensor, the fused ComputeTGLR reads it there (nothing is uploaded, the placeholder survives), and the
+    products equal the host route (``Compute_GreedyPCA_area`` on numpy arrays, then ``step05`` on its result)."""
+    import torch
+    from origin_b200 import lib_origin, steps, synthetic
+    shape = (200, 48, 64)
+    fsf = synthetic.moffat_fsf(shape[0])
+    cube_std, _ = synthetic.faint_cube(shape, fsf, n_src=8, seed=11)
+    cube_std = cube_std.astype(np.float32)
+    rng = np.random.default_rng(3)
+    spec = np.sin(np.arange(shape[0]) / 9.0)[:, None, None]
+    cube_std[:, 5:12, 8:20] += 3.0 * spec * rng.uniform(0.5, 1.5, size=(1, 7, 12)).astype(np.float32)   # a continuum residual
+    mask = synthetic.footprint_mask(shape, seed=2)
+    profs = dictionaries.dico_3fwhm()[0]
+    areamap = np.ones(shape[1:], dtype=int)
+    areamap[:, 32:] = 2
+    o2 = [np.mean(cube_std[:, areamap == a].astype(np.float64) ** 2, axis=0) for a in (1, 2)]
+    thr = [float(np.percentile(t, 90)) for t in o2]
+    mod = fake_steps_module()
+    steps.patch_steps(mod, fused=True)
+    try:
+        assert mod.Compute_GreedyPCA_area is lib_origin.Compute_GreedyPCA_area
+        orig = FakeOrigin(mask=mask, PSF=fsf, wfields=None, profiles=profs, cube_std=FakeData(cube_std),
+                          areamap=FakeData(areamap), nbAreas=2, thresO2=thr, testO2=None)
+        pca, tglr = mod.ComputeGreedyPCA(orig), mod.ComputeTGLR(orig)
+        orig.steps = {'compute_greedy_PCA': pca, 'compute_TGLR': tglr}
+        pca.run(orig)
+        lazy = pca.__dict__['cube_faint']
+        assert isinstance(lazy, steps.LazyProduct) and lazy.on_device().is_cuda and orig.param['threshold_list'] == thr
+        rfaint, rmap, rstop = lib_origin.Compute_GreedyPCA_area(2, cube_std, areamap, 50, thr, 100, None)
+        assert rmap.max() >= 1
+        np.testing.assert_array_equal(pca.mapO2._data, rmap)
+        dev_faint = lazy.on_device().cpu().numpy()
+        assert dev_faint.dtype == np.float32 and np.abs(dev_faint - rfaint).max() <= 1e-5 * np.abs(rfaint).max()
+        tglr.run(orig, pcut=1e-8)
+        assert isinstance(pca.__dict__['cube_faint'], steps.LazyProduct)         # step05 read the device tensor
+        ref = lib_origin.step05(dev_faint, fsf, None, profs, mask, 3, 1e-8, True)
+        assert isinstance(orig.cube_correl._data, np.ndarray)
+        np.testing.assert_allclose(orig.cube_correl._data, ref['correl'], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(orig.maxmap._data, ref['maxmap'], rtol=1e-6, atol=1e-6)
+        ext = tglr._ogn_extrema
+        np.testing.assert_array_equal(ext._host(ext.max_index), ref['extrema'].max_index)
+        np.testing.assert_array_equal(ext._host(ext.min_value), ref['extrema'].min_value)
+        assert isinstance(tglr.__dict__['cube_profile'], steps.LazyProduct)
+        np.testing.assert_array_equal(orig.cube_profile._data, ref['profile'])
+        got = orig.cube_faint._data                                                # materialises: float64, as the reference
+        assert got.dtype == np.float64 and isinstance(pca.__dict__['cube_faint'], FakeData)
+        np.testing.assert_array_equal(got.astype(np.float32), dev_faint)
+    finally:
+        steps.unpatch_steps()
+        assert not hasattr(mod, 'estimation_line')

@@ -79,3 +79,82 @@ def test_drop_in_signatures_equal_the_reference():
     # what the step layer imports by name (steps.py:19-41) is what patch_steps rebinds
     for name in ('dct_residual', 'compute_local_max', 'Correlation_GLR_test', 'Compute_threshold_purity', 'O2test'):
         assert hasattr(rsteps, name)
+
+
+@pytest.mark.skipif(ref_loader.find_reference_file('muse_origin/steps.py') is None,
+                    reason='reference steps.py only exists in the build container')
+def test_step04_step08_drop_ins_keep_the_reference_signatures():
+    """``ComputeGreedyPCA.run`` (steps.py:681), ``Compute_GreedyPCA_area`` (lib_origin.py:769) and
+    ``estimation_line`` (:1805) as ``patch_steps`` rebinds them."""
+    from origin_b200 import lib_origin, steps as osteps
+    rsteps = ref_loader.load_steps()
+    lib = ref_loader.load_lib_origin()
+
+    def params(fn):
+        return [(p.name, p.default) for p in inspect.signature(fn).parameters.values()]
+
+    assert params(osteps._run_greedy_pca) == params(rsteps.ComputeGreedyPCA.run)
+    assert params(osteps._estimation_line_table) == params(lib.estimation_line)
+    ref = params(lib.Compute_GreedyPCA_area)
+    assert params(lib_origin.Compute_GreedyPCA_area)[:len(ref)] == ref
+    for name in ('Compute_GreedyPCA_area', 'estimation_line'):
+        assert hasattr(rsteps, name)                      # imported by name at steps.py:19-41
+
+
+def test_cat2_table_inserts_the_columns_where_the_reference_does():
+    """An astropy-like ``Cat1`` comes back as a copy with ``ra / dec / lbda`` updated and ``x, y, z, residual, flux,
+    num_line`` inserted at indexes 4, 5, 6, 8, 8, 8 of the ORIGINAL column list (lib_origin.py:1925-1936)."""
+    from origin_b200 import steps as osteps
+
+    class FakeColumn:
+        def __init__(self, name, data):
+            self.name, self.data = name, np.asarray(data)
+
+    class Table:
+        Column = FakeColumn                              # astropy's Table carries its Column class the same way
+
+        def __init__(self, cols):
+            self.cols = dict(cols)
+
+        def copy(self):
+            return Table(self.cols)
+
+        def __setitem__(self, key, val):
+            self.cols[key] = np.asarray(val)
+
+        def add_columns(self, cols, indexes):
+            names = list(self.cols)
+            merged = []
+            for i, n in enumerate(names + [None]):       # astropy: each new column goes BEFORE original index i
+                merged += [c.name for c, at in zip(cols, indexes) if at == i]
+                if n is not None:
+                    merged.append(n)
+            new = {c.name: c.data for c in cols}
+            self.cols = {n: new.get(n, self.cols.get(n)) for n in merged}
+
+    cat1 = Table({k: np.arange(2) for k in ('ra', 'dec', 'lbda', 'x0', 'y0', 'z0', 'comp', 'STD', 'T_GLR', 'profile')})
+    cat2 = dict(ra=np.array([1.5, 2.5]), dec=np.array([3.0, 4.0]), lbda=np.array([5000.0, 6000.0]), x=np.array([7, 8]),
+                y=np.array([9, 10]), z=np.array([11, 12]), residual=np.array([0.1, 0.2]), flux=np.array([20.0, 30.0]),
+                num_line=np.array([1, 2]))
+    out = osteps._cat2_table(cat1, cat2)
+    assert out is not cat1 and list(cat1.cols) == ['ra', 'dec', 'lbda', 'x0', 'y0', 'z0', 'comp', 'STD', 'T_GLR', 'profile']
+    # the reference's Cat2 column order (docstring of estimation_line, :1853-1855, with comp / STD kept)
+    assert list(out.cols) == ['ra', 'dec', 'lbda', 'x0', 'x', 'y0', 'y', 'z0', 'z', 'comp', 'STD', 'residual', 'flux',
+                              'num_line', 'T_GLR', 'profile']
+    np.testing.assert_array_equal(out.cols['ra'], cat2['ra'])
+    np.testing.assert_array_equal(out.cols['flux'], cat2['flux'])
+    assert osteps._cat2_table(dict(x0=[1]), cat2) is cat2
+
+
+def test_patch_steps_rebinds_and_restores_names_that_were_absent():
+    import types
+    from origin_b200 import lib_origin, steps as osteps
+    mod = types.ModuleType('stand_in')
+    mod.dct_residual = sentinel = object()
+    osteps.patch_steps(mod, fused=True)                  # no step classes in this stand-in: only the names
+    try:
+        assert mod.estimation_line is osteps._estimation_line_table
+        assert mod.Compute_GreedyPCA_area is lib_origin.Compute_GreedyPCA_area
+    finally:
+        osteps.unpatch_steps()
+    assert mod.dct_residual is sentinel and not hasattr(mod, 'estimation_line') and not hasattr(mod, 'O2test')
