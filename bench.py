@@ -882,6 +882,60 @@ def run_c3(env, hbm_peak, fp32_peak, steps, warmup):
     return res
 
 
+def run_next_rows(env):
+    """SURVEY 8(f) rows 1 and 4 in the driver's run: the step04 greedy PCA of one 3681x96x96 area with twelve continuum
+    sources left in it, and the step08 line estimation of 32 detections (288 windows of 3681x25x25) in it - the
+    workload of tools/pca_lines_probe.py - device-resident, wall clock between synchronisations (both loops are
+    host-driven: the Lanczos restarts read the tridiagonal matrices back).  The unmodified reference on the same
+    inputs on one host core is in profiles/r02_pca_lines_probe_cpu_reference.json (13.3 s; 3.5 s per detection);
+    parity is what tests/test_gpu_pca.py and tests/test_gpu_lines.py check against the reference's own functions."""
+    import torch
+    from origin_b200 import lib_origin as lo, synthetic
+    nz, ny, nx = SHAPE[0], 96, 96
+    rng = np.random.default_rng(11)
+    fsf = synthetic.moffat_fsf(nz)
+    cube = rng.standard_normal((nz, ny, nx)).astype(np.float32)
+    lam = np.linspace(0, 1, nz)
+    for _ in range(12):
+        y0, x0 = int(rng.integers(12, ny - 12)), int(rng.integers(12, nx - 12))
+        spec = rng.uniform(2, 8) * (0.6 + 0.4 * np.cos(rng.uniform(1, 6) * lam + rng.uniform(0, 3)))
+        cube[:, y0 - 12:y0 + 13, x0 - 12:x0 + 13] += (spec[:, None, None] * fsf / fsf.max(axis=(1, 2), keepdims=True)).astype(np.float32)
+    areamap = np.ones((ny, nx), dtype=int)
+    dets = dict(z0=rng.integers(50, nz - 50, 32), y0=rng.integers(0, ny, 32), x0=rng.integers(0, nx, 32))
+    var = (1.0 + 0.3 * np.sin(6 * lam) ** 2)[:, None, None] * np.ones((1, ny, nx))
+    raw = torch.from_numpy((cube * np.sqrt(var)).astype(np.float32)).to(env.dev)
+    var = torch.from_numpy(var.astype(np.float32)).to(env.dev)
+    c = torch.from_numpy(cube).to(env.dev)
+    ctx = env.ctx
+    launches0 = ctx.launch_count
+    test, _, _, thr, _, _ = lo.Compute_PCA_threshold(c.reshape(nz, -1), 0.01)
+    out = {}
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        faint, map_o2, nstop = lo.Compute_GreedyPCA_area(1, c, areamap, 50, [thr], 100, [test], ctx=ctx)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    out['step04_greedy_pca'] = dict(
+        workload='one %dx%dx%d area, 12 continuum sources' % (nz, ny, nx), seconds=dt, iterations=float(map_o2.max()),
+        nuisance_spaxels=int((map_o2 > 0).sum()), nstop=int(nstop), cube_faint_on_device=bool(faint.is_cuda),
+        reference_seconds_one_core=13.35, reference_from='profiles/r02_pca_lines_probe_cpu_reference.json')
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cat2, lin_est, _ = lo.estimation_line(dets, raw, var, fsf, ctx=ctx)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    out['step08_line_estimation'] = dict(
+        workload='32 detections, grid of 9 offsets each = 288 windows of %dx25x25, order_dct 30' % nz, seconds=dt,
+        ms_per_detection=dt * 1e3 / 32, finite_lines=int(sum(np.isfinite(l).all() for l in lin_est)),
+        reference_ms_per_detection_one_core=3489.5, reference_from='profiles/r02_pca_lines_probe_cpu_reference.json')
+    out['gpu_launches'] = int(ctx.launch_count - launches0)
+    del raw, var, c, faint
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_c5(env, steps, warmup):
     """north_star config 5: the 3681x900x900 mosaic-sized cube with Dico_FWHM_2_12 on all ranks, and on rank 0
     alone (1-GPU time), so that the speed-up is timed in one driver run."""
@@ -972,6 +1026,10 @@ def main_gpu(args):
         csteps, cwarm = max(3, min(args.steps, 10)), 3
         if world == 1:
             configs['c3'] = run_c3(env, hbm_peak, fp32_peak, csteps, cwarm)
+            try:                        # the "next" rows of SURVEY 8(f); never at the expense of the line itself
+                configs['next_rows'] = run_next_rows(env)
+            except Exception as exc:  # noqa: BLE001
+                configs['next_rows'] = dict(error=repr(exc)[:300])
         if world == 8:
             c5 = run_c5(env, max(3, min(args.steps, 5)), 2)
             if rank == 0:
