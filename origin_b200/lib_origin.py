@@ -267,13 +267,21 @@ def Compute_GreedyPCA(cube_in, test, thresO2, Noise_population, itermax, ctx=Non
 def Compute_GreedyPCA_area(NbArea, cube_std, areamap, Noise_population, threshold_test, itermax, testO2, ctx=None):
     """Greedy PCA on each area of the field (reference lib_origin.py:769-818): returns
     ``(cube_faint, mapO2, nstop)``.  ``cube_std`` may be a numpy cube (the result is a numpy cube of the same
-    dtype) or a CUDA tensor (float32 from the fused step01: ``cube_faint`` then stays on the device for step05)."""
+    dtype) or a CUDA tensor (float32 from the fused step01: ``cube_faint`` then stays on the device for step05).
+    A numpy cube crosses PCIe twice — up once, all areas run on the device copy, the result comes down once —
+    not once per area."""
     cube = _as_float_cube(cube_std)
     if cube.ndim != 3:
         raise ValueError('cube_std must be (nz, ny, nx)')
     ctx = _ctx_for(cube, ctx)
     areamap = areamap.detach().cpu().numpy() if _is_torch(areamap) else np.asarray(areamap)
-    cube_faint = cube.clone() if _is_torch(cube) else cube.copy()               # :797
+    host_in = not _is_torch(cube)
+    if host_in:
+        torch = _torch()
+        cube_faint = torch.from_numpy(cube).to(torch.device('cuda', ctx.device))    # :797 (the areas only write their own
+        cube = cube_faint                                                            # columns: input and output can share)
+    else:
+        cube_faint = cube.clone()
     map_o2 = np.zeros(cube.shape[1:], dtype=np.float64)
     nstop = 0
     for area_ind in range(1, NbArea + 1):
@@ -286,6 +294,8 @@ def Compute_GreedyPCA_area(NbArea, cube_std, areamap, Noise_population, threshol
                                        cube_faint, ctx)
         map_o2[ksel] = m                                                         # :815
         nstop += k
+    if host_in:
+        cube_faint = cube_faint.cpu().numpy()
     return cube_faint, map_o2, nstop
 
 
