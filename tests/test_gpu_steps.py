@@ -129,8 +129,9 @@ def test_fused_tglr_keeps_unread_products_on_the_device():
         orig = FakeOrigin(mask=mask, PSF=fsf, wfields=None, profiles=profs, cube_faint=FakeData(cube))
         tglr = mod.ComputeTGLR(orig)
         orig.steps = {'compute_TGLR': tglr}
+        assert steps.pack_mask(orig).size == (cube.size + 7) // 8       # a session that re-runs the step packs once
         tglr.run(orig, pcut=1e-8)
-        assert orig._ogn_mask_bits[1].size == (cube.size + 7) // 8
+        assert tglr._ogn_used_mask_bits
         lazy = tglr.__dict__['cube_correl_min']
         assert isinstance(lazy, steps.LazyProduct) and torch.is_tensor(tglr._ogn_profile) and tglr._ogn_profile.is_cuda
         ref = lib_origin.step05(cube, fsf, None, profs, mask, 3, 1e-8, True)
