@@ -14,8 +14,8 @@
 //   gemv_n          y[z] = sum_j M[z][j] c[j]
 //   rank1_scale     X = (X - b c^T) / sum(b^2)                        lib_origin.py:908-909
 //   deflate_*       F -= u c^T fused with the new colsumsq partials   :927 + :930 in one pass over the area
-//   Lanczos (full reorthogonalisation, restarted) on A = X X^T for u; the m x m tridiagonal eigenproblem is solved
-//   on the host by cyclic Jacobi rotations.  svds(k=1) converges its ARPACK iteration to machine precision; the
+//   Lanczos (full reorthogonalisation, restarted) on A = X X^T for u; the top eigenpair of the m x m tridiagonal matrix
+//   is found on the host by Sturm bisection + inverse iteration (ogn_lanczos.cuh).  svds(k=1) converges its ARPACK iteration to machine precision; the
 //   restart loop here stops at a relative residual of 1e-13, so both give the same vector up to sign, and the
 //   projector u u^T does not depend on the sign.
 //

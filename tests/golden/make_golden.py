@@ -6,7 +6,9 @@ Run in the build container only (needs ``/root/reference``):
 
 Every ``*.npz`` written here holds seeded inputs and the outputs of the
 reference's own functions (``lib_origin.dct_residual``, ``Correlation_GLR_test``,
-``compute_local_max``, ``Compute_threshold_purity``, ``DCTMAT``, ``O2test``)
+``compute_local_max``, ``Compute_threshold_purity``, ``DCTMAT``, ``O2test``, and for
+``pca.npz`` / ``lines.npz`` — ``python tests/golden/make_golden.py next`` writes only
+those two — ``Compute_GreedyPCA_area`` and ``GridAnalysis``)
 loaded by ``reference_loader.load_lib_origin``.  The step glue that lives in
 ``steps.py`` (which cannot be imported without mpdaf) is replayed by
 ``_step01_glue`` / ``_step05_glue`` below, line-referenced.
@@ -192,5 +194,118 @@ def main():
          cube_std_plane=g1['cube_std'][100])
 
 
+def next_rows_inputs():
+    """Seeded inputs of the step04 / step08 fixtures, stored as float32 in the fixtures and
+    fed to the reference as the float64 values of those float32 numbers."""
+    # step04: a standardised cube with continuum residuals left in it, two areas
+    rng = np.random.default_rng(21)
+    shape = (100, 20, 24)
+    cube = rng.standard_normal(shape).astype(np.float32)
+    lam = np.linspace(0.0, 1.0, shape[0])
+    for y0, x0, amp, k in ((5, 6, 3.0, 2.0), (14, 17, 4.0, 3.5), (10, 11, 2.5, 5.0)):
+        yy, xx = np.mgrid[:shape[1], :shape[2]]
+        foot = np.exp(-0.5 * ((yy - y0) ** 2 + (xx - x0) ** 2) / 2.0 ** 2)
+        cube += (amp * (0.6 + 0.4 * np.cos(k * lam))[:, None, None] * foot[None]).astype(np.float32)
+    cube[:, 0, :3] = 0.0                                   # fully masked spaxels: test = 0 (the index quirk of :895-903)
+    areamap = np.ones(shape[1:], dtype=np.int16)
+    areamap[:, 12:] = 2
+    # step08: a three-field mosaic with an uncovered strip and a field that only touches one corner
+    rng = np.random.default_rng(7)
+    shape8 = (90, 34, 38)
+    nz, ny, nx = shape8
+    fsf_a = synthetic.moffat_fsf(nz)
+    fsf_b = synthetic.moffat_fsf(nz, fwhm0=4.4, fwhm1=3.5)
+    raw = rng.normal(size=shape8)
+    var = rng.uniform(0.5, 2.0, size=shape8)
+    dets = [(45, 17, 19), (20, 2, 35), (70, 32, 1), (30, 10, 8)]
+    for z0, y0, x0 in dets:
+        zz = np.arange(max(0, z0 - 8), min(nz, z0 + 9))
+        line = 30.0 * np.exp(-0.5 * ((zz - z0) / 1.8) ** 2)
+        ya, yb, xa, xb = max(0, y0 - 12), min(ny, y0 + 13), max(0, x0 - 12), min(nx, x0 + 13)
+        raw[zz[0]:zz[-1] + 1, ya:yb, xa:xb] += line[:, None, None] * fsf_a[z0, ya - y0 + 12:yb - y0 + 12, xa - x0 + 12:xb - x0 + 12] * 25
+    raw = raw.astype(np.float32)
+    var = var.astype(np.float32)
+    var[:, 20:22, 30:33] = np.inf                          # masked voxels (origin.py:262-274)
+    raw[:, 20:22, 30:33] = 0.0
+    yy, xx = np.mgrid[:ny, :nx]
+    w1 = np.clip((xx - 4.0) / (nx - 10.0), 0.0, 1.0)
+    w0 = 1.0 - w1
+    w0[:3] = 0.0
+    w1[:3] = 0.0
+    w2 = np.zeros((ny, nx))
+    w2[28:, 30:] = 0.3
+    return dict(cube=cube, areamap=areamap), dict(raw=raw, var=var, fsf=np.stack([fsf_a, fsf_b, fsf_a * 0.9 + fsf_b * 0.1]),
+                                                  wght=np.stack([w0, w1, w2]), dets=np.array(dets))
+
+
+def grid_analysis(lib, raw, var, psf, wght, dets, size_grid, criteria, order_dct, horiz_psf=1, horiz=5):
+    """``GridAnalysis`` (lib_origin.py:1620-1790) on the padded minicubes ``estimation_line`` builds per detection
+    (:1886-1906; ``overlap_slices`` is astropy's, the padding is restated here)."""
+    nz, ny, nx = raw.shape
+    P = psf.shape[1] if wght is None else psf[0].shape[1]
+    side = P + 2 * size_grid
+    half = side // 2
+    res = []
+    for z, y, x in dets:
+        z, y, x = int(z), int(y), int(x)
+        red_dat = np.zeros((nz, side, side))
+        red_var = np.full((nz, side, side), np.inf)
+        ya, yb, xa, xb = max(0, y - half), min(ny, y + half + 1), max(0, x - half), min(nx, x + half + 1)
+        dst = (slice(ya - (y - half), yb - (y - half)), slice(xa - (x - half), xb - (x - half)))
+        red_dat[(slice(None),) + dst] = raw[:, ya:yb, xa:xb]
+        red_var[(slice(None),) + dst] = var[:, ya:yb, xa:xb]
+        red_psf, red_wgt = psf, None
+        if wght is not None:
+            red_psf, red_wgt = [], []
+            for n, w in enumerate(wght):
+                if np.sum(w[ya:yb, xa:xb]) > 0:                                  # :1901
+                    tmp = np.zeros((side, side))
+                    tmp[dst] = w[ya:yb, xa:xb]
+                    red_wgt.append(tmp)
+                    red_psf.append(psf[n])
+        with warnings.catch_warnings(), np.errstate(all='ignore'):
+            warnings.simplefilter('ignore')
+            res.append(lib.GridAnalysis(red_dat, red_var, red_psf, red_wgt, horiz, size_grid, y, x, z, ny, nx, horiz_psf,
+                                        criteria, order_dct))
+    flux, mse, line, lvar, yy, xx, zz = zip(*res)
+    return dict(flux=np.array(flux), mse=np.array(mse), line=np.array(line), lvar=np.array(lvar), y=np.array(yy),
+                x=np.array(xx), z=np.array(zz))
+
+
+def next_rows_outputs(lib):
+    """What the unmodified reference computes on those inputs: ``Compute_GreedyPCA_area`` (:769-818) and
+    ``GridAnalysis`` for a single field and for the weighted mosaic."""
+    pca_in, lines_in = next_rows_inputs()
+    cube = pca_in['cube'].astype(np.float64)
+    areamap = pca_in['areamap'].astype(int)
+    test = [lib.O2test(cube[:, areamap == a]) for a in (1, 2)]
+    thr = [float(np.percentile(t[t > 0], 80)) for t in test]
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        faint, map_o2, nstop = lib.Compute_GreedyPCA_area(2, cube, areamap, 50, thr, 100, test)
+        faint3, map3, nstop3 = lib.Compute_GreedyPCA_area(2, cube, areamap, 20, thr, 3, test)
+    pca = dict(thr=np.array(thr), test0=test[0], test1=test[1], faint=faint, map_o2=map_o2, nstop=nstop,
+               faint_itermax3=faint3, map_o2_itermax3=map3, nstop_itermax3=nstop3)
+    raw, var = lines_in['raw'].astype(np.float64), lines_in['var'].astype(np.float64)
+    fsf, wght, dets = lines_in['fsf'], lines_in['wght'], lines_in['dets']
+    lines = {}
+    for tag, args in (('single_g1_flux', (fsf[0], None, 1, 'flux', 20)), ('single_g1_mse_pcals', (fsf[0], None, 1, 'mse', None)),
+                      ('mosaic_g0_flux', (list(fsf), list(wght), 0, 'flux', 20)),
+                      ('mosaic_g1_flux', (list(fsf), list(wght), 1, 'flux', 20))):
+        out = grid_analysis(lib, raw, var, args[0], args[1], dets, args[2], args[3], args[4])
+        lines.update({tag + '_' + k: v for k, v in out.items()})
+    return pca_in, pca, lines_in, lines
+
+
+def main_next():
+    lib = load_lib_origin()
+    warnings.simplefilter('ignore', DeprecationWarning)
+    pca_in, pca, lines_in, lines = next_rows_outputs(lib)
+    save('pca', **pca_in, **pca)
+    save('lines', **lines_in, **lines)
+
+
 if __name__ == '__main__':
-    main()
+    if sys.argv[1:] != ['next']:
+        main()
+    main_next()
