@@ -5,7 +5,8 @@ imports this.
 
 The reference (``musevlt/origin``) is pure Python: there is nothing to compile.  Its hot path lives
 in ONE file, ``muse_origin/lib_origin.py``, which only needs numpy / scipy / joblib once the imports
-of astropy, mpdaf, photutils and matplotlib are stubbed (``oracle/ref_loader.py``).  ``/root/reference``
+of astropy, mpdaf, photutils and matplotlib are stubbed (``oracle/ref_loader.py``); the step layer that
+calls it is ``muse_origin/steps.py`` (its ``Step`` / ``DataObj`` machinery runs with the same stubs).  ``/root/reference``
 exists in the build container only, so ``__graft_entry__.build()`` calls :func:`build_ref` there: the
 file is copied UNMODIFIED into the git-ignored ``oracle/_ref/muse_origin/`` (never committed — no
 reference source enters the history), next to a ``PROVENANCE`` note with its sha256.  ``oracle/_ref``
@@ -24,7 +25,8 @@ import shutil
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, '_ref')
 REFERENCE_ROOT = os.environ.get('ORIGIN_REFERENCE_ROOT', '/root/reference')
-FILES = ['muse_origin/lib_origin.py']
+FILES = ['muse_origin/lib_origin.py',      # the hot path: CPU baseline of bench.py, oracle of steps 04 / 08
+         'muse_origin/steps.py']           # the step layer: the drop-in tests run the reference's own Step classes
 
 
 def build_ref(force=False):

@@ -149,7 +149,8 @@ def load_lib_origin():
 
 
 def load_steps():
-    """The reference's ``muse_origin.steps`` module (build container only: ``steps.py`` is not part of
-    ``oracle/_ref``).  Its classes can be inspected; running them needs mpdaf / astropy."""
+    """The reference's ``muse_origin.steps`` module, executed unmodified with mpdaf / astropy stubbed: its ``Step``
+    classes, ``DataObj`` descriptors and ``dump`` run as they are once ``Cube`` / ``Image`` are replaced by plain
+    containers (tests/test_gpu_real_steps.py)."""
     load_lib_origin()
     return _load('muse_origin.steps', 'muse_origin/steps.py')

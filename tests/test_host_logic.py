@@ -158,3 +158,62 @@ def test_patch_steps_rebinds_and_restores_names_that_were_absent():
     finally:
         osteps.unpatch_steps()
     assert mod.dct_residual is sentinel and not hasattr(mod, 'estimation_line') and not hasattr(mod, 'O2test')
+
+
+@pytest.mark.skipif(ref_loader.find_reference_file('muse_origin/steps.py') is None,
+                    reason='reference steps.py only exists in the build container')
+def test_lazy_products_live_in_the_reference_step_machinery(tmp_path):
+    """``patch_steps`` on the REAL ``muse_origin.steps`` module (stub-loaded: mpdaf / astropy are mocks) and a
+    ``LazyProduct`` going through the reference's own ``DataObj`` descriptor (steps.py:121-164), ``store_cube``
+    (:284-294) and ``Step.dump`` (:301-337): the placeholder is handed out untouched, ``dump`` makes it fetch, writes
+    the float64 cube with ``convert_float32=False`` and leaves the file path behind like for any other product."""
+    from origin_b200 import lib_origin, steps as osteps
+    rsteps = ref_loader.load_steps()
+    originals = {c: getattr(rsteps, c).run for c in ('Preprocessing', 'ComputeGreedyPCA', 'ComputeTGLR', 'ComputePurityThreshold')}
+    ref_names = {n: getattr(rsteps, n) for n in ('Correlation_GLR_test', 'estimation_line', 'Compute_GreedyPCA_area')}
+    written = []
+
+    class FakeCube:
+        def __init__(self, data=None, **kw):
+            self.data, self.kw = data, kw
+
+        def write(self, path, **kw):
+            written.append((path, kw, self.data))
+
+    class Orig:
+        wave = wcs = None
+        steps = {}
+
+    real_cube = rsteps.Cube
+    osteps.patch_steps(rsteps, fused=True)
+    try:
+        assert rsteps.ComputeTGLR.run is osteps._run_compute_tglr and rsteps.ComputeGreedyPCA.run is osteps._run_greedy_pca
+        assert rsteps.Correlation_GLR_test is lib_origin.Correlation_GLR_test
+        assert rsteps.estimation_line is osteps._estimation_line_table
+        rsteps.Cube = FakeCube
+        step = rsteps.ComputeTGLR(Orig(), 5, {})
+        fetched = []
+
+        def fetch():
+            fetched.append(1)
+            return np.arange(24, dtype=np.float64).reshape(2, 3, 4)
+
+        step.cube_correl_min = osteps.LazyProduct(step, 'cube_correl_min', fetch, 'cube', (2, 3, 4))     # DataObj.__set__
+        assert isinstance(step.cube_correl_min, osteps.LazyProduct) and step.cube_correl_min.shape == (2, 3, 4)
+        assert step.cube_correl_min.on_device() is None and not fetched                                  # DataObj.__get__
+        step.status = rsteps.Status.RUN
+        step.dump(str(tmp_path))
+        assert fetched == [1] and len(written) == 1
+        path, kw, data = written[0]
+        assert path.endswith('cube_correl_min.fits') and kw == dict(convert_float32=False) and data.dtype == np.float64
+        assert step.__dict__['cube_correl_min'] == path and step.status is rsteps.Status.DUMPED
+        # reading a product materialises it once and replaces the placeholder by the step's own Cube
+        step.cube_profile = osteps.LazyProduct(step, 'cube_profile', lambda: np.zeros((2, 3, 4), np.uint8), 'cube', (2, 3, 4))
+        assert step.cube_profile.data.dtype == np.uint8 and isinstance(step.__dict__['cube_profile'], FakeCube)
+    finally:
+        rsteps.Cube = real_cube
+        osteps.unpatch_steps()
+    for c, run in originals.items():
+        assert getattr(rsteps, c).run is run
+    for n, fn in ref_names.items():
+        assert getattr(rsteps, n) is fn
