@@ -11,7 +11,8 @@ definitions so that step01's ``segmap_merged`` and step06's ``segmap_purity`` ca
   values with ``|x - median| > sigma * std`` rejected, stop when nothing is rejected;
 * the Gaussian fit: Levenberg-Marquardt (MINPACK ``lmder`` through ``scipy.optimize.leastsq``, which is what
   ``LevMarLSQFitter`` calls) on ``amplitude * exp(-(x - mean)^2 / (2 stddev^2))`` with the analytic Jacobian,
-  ``ftol = xtol = gtol = 1e-7`` and at most 100 function evaluations (astropy's ``acc`` / ``maxiter`` defaults).
+  ``xtol = 1e-7`` and at most 100 function evaluations (astropy's ``acc`` / ``maxiter`` defaults; it leaves ``ftol``
+  and ``gtol`` at scipy's own defaults, and so does this).
 
 Parity: UNPINNED — astropy is absent from this image, so the restatement cannot be run against the reference's
 own functions here; ``tests/test_segmap.py`` checks it against closed-form expectations (a Gaussian sample gives
@@ -62,8 +63,7 @@ def fit_gaussian(x, y, amplitude, mean, stddev, acc=1e-7, maxiter=100):
 
     if x.size < 3:
         return float(amplitude), float(mean), float(stddev)
-    p, _ = optimize.leastsq(resid, [amplitude, mean, stddev], Dfun=jac, col_deriv=True, ftol=acc, xtol=acc, gtol=acc,
-                            maxfev=maxiter)
+    p, _ = optimize.leastsq(resid, [amplitude, mean, stddev], Dfun=jac, col_deriv=True, xtol=acc, maxfev=maxiter)
     return float(p[0]), float(p[1]), float(abs(p[2]))
 
 
