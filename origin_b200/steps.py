@@ -8,15 +8,17 @@ the thresholding block).  Two levels of drop-in are offered:
 
 ``patch_steps(fused=False)``
     rebinds ``dct_residual``, ``compute_local_max``, ``Correlation_GLR_test``,
-    ``Compute_threshold_purity``, ``O2test``, ``Compute_GreedyPCA_area`` (step04)
-    and ``estimation_line`` (step08) in the ``muse_origin.steps`` namespace to the
+    ``Compute_threshold_purity``, ``O2test``, ``Compute_PCA_threshold`` (step03),
+    ``Compute_GreedyPCA_area`` (step04) and ``estimation_line`` (step08) in the
+    ``muse_origin.steps`` namespace to the
     B200 implementations of :mod:`origin_b200.lib_origin`; the reference's
     ``run`` methods stay untouched.
 
 ``patch_steps(fused=True)`` (default)
-    additionally replaces the ``run`` methods of steps 01, 04, 05 and 06 by the
+    additionally replaces the ``run`` methods of steps 01, 03, 04, 05 and 06 by the
     fused versions below, which keep intermediates on the device (``cube_faint``
-    goes from the greedy PCA of step04 into step05 without crossing PCIe), carry
+    goes from the greedy PCA of step04 into step05 without crossing PCIe; step03
+    reads its O2 test from the map step01 produced), carry
     the local extrema as compact lists (:class:`~origin_b200.lib_origin.LocalExtrema`)
     and materialise the dense cubes the step API promises
     (``cube_local_max`` ...) from them.  ``Detection.run`` is left as it is
@@ -184,6 +186,7 @@ def _run_preprocessing(self, orig, dct_order=10, dct_approx=False, pfasegcont=0.
     self.store_image('ima_std', out['ima_std'])
     ext = out['extrema_std']
     self._ogn_extrema_std = ext
+    self._ogn_o2map = (out['cube_std'], np.asarray(out['o2map'], dtype=np.float64))    # O2test(cube_std), for step03
     shape = tuple(out['cube_std'].shape)
     setattr(self, 'cube_std_local_max', LazyProduct(self, 'cube_std_local_max', lambda: ext.dense('max'), 'cube', shape))
     setattr(self, 'cube_std_local_min', LazyProduct(self, 'cube_std_local_min', lambda: ext.dense('min'), 'cube', shape))
@@ -201,6 +204,50 @@ def _run_preprocessing(self, orig, dct_order=10, dct_approx=False, pfasegcont=0.
     thresh, map_res = _segmap_gauss(mod)(out['o2map'], pfasegres, mean_fwhm, bins=bins)
     segmap, nlabels = mod.ndi.label((map_cont > 0) | (map_res > 0))
     self.store_image('segmap_merged', segmap)
+
+
+def _run_pca_threshold(self, orig, pfa_test=0.01):
+    """Fused ``ComputePCAThreshold.run`` (reference steps.py:610-631): the O2 test of every area
+    (``Compute_PCA_threshold``, lib_origin.py:821-842: ``O2test(cube_std[:, ksel])``) is read from the map the fused
+    step01 already produced on the device instead of gathering the area's spectra on the host and reducing them again;
+    the Gaussian fit of its distribution is the reference's ``compute_thresh_gaussfit`` (or its restatement when
+    astropy is absent)."""
+    fit = _thresh_gaussfit()
+    pre = orig.steps.get('preprocessing') if hasattr(orig.steps, 'get') else None
+    cached = getattr(pre, '_ogn_o2map', None)
+    std = orig.cube_std._data
+    o2map = None
+    if cached is not None and isinstance(std, np.ndarray) and std.shape == cached[0].shape and std.dtype == cached[0].dtype \
+            and (std is cached[0] or np.may_share_memory(std, cached[0])):
+        o2map = cached[1]                                                        # only for the cube it was made from
+    results = []
+    for area_ind in range(1, orig.nbAreas + 1):
+        ksel = orig.areamap._data == area_ind
+        test = o2map[ksel] if o2map is not None else lo.O2test(np.asarray(std)[:, ksel])
+        hist, edges, thres, mea, sig = fit(test, pfa_test)
+        results.append((test, hist, edges, thres, mea, sig))
+        self._loginfo('Area %d: mean %f, std %f, threshold %f', area_ind, mea, sig, thres)
+    orig.testO2, orig.histO2, orig.binO2, self.thresO2, self.meaO2, self.stdO2 = zip(*results)
+
+
+def _pca_threshold(faint, pfa):
+    """``Compute_PCA_threshold`` (reference lib_origin.py:821-842) with the O2 test from
+    :func:`origin_b200.lib_origin.O2test` (numpy or CUDA tensor) and the fit of :func:`_thresh_gaussfit`."""
+    test = lo.O2test(faint)
+    test = test.detach().cpu().numpy() if lo._is_torch(test) else test
+    return (test,) + tuple(_thresh_gaussfit()(test, pfa))
+
+
+def _thresh_gaussfit():
+    """The reference's ``compute_thresh_gaussfit`` when ``muse_origin`` is really importable (it needs astropy), else
+    the numpy / scipy restatement of :mod:`origin_b200.segmap`."""
+    import sys
+    lib = sys.modules.get('muse_origin.lib_origin')
+    astropy_stats = sys.modules.get('astropy.stats')
+    if lib is not None and type(astropy_stats).__name__ == 'module' and hasattr(lib, 'compute_thresh_gaussfit'):
+        return lib.compute_thresh_gaussfit
+    from . import segmap
+    return segmap.compute_thresh_gaussfit
 
 
 def _run_greedy_pca(self, orig, Noise_population=50, itermax=100, threshold_list=None):
@@ -319,6 +366,7 @@ def patch_steps(steps_module=None, fused=True):
         'Correlation_GLR_test': lo.Correlation_GLR_test,
         'Compute_threshold_purity': _threshold_purity_astropy,
         'O2test': lo.O2test,
+        'Compute_PCA_threshold': _pca_threshold,
         'Compute_GreedyPCA_area': lo.Compute_GreedyPCA_area,
         'estimation_line': _estimation_line_table,
     }
@@ -326,7 +374,8 @@ def patch_steps(steps_module=None, fused=True):
         _ORIGINALS.setdefault(name, getattr(steps_module, name, _ABSENT))
         setattr(steps_module, name, fn)
     if fused:
-        for cls_name, run in (('Preprocessing', _run_preprocessing), ('ComputeGreedyPCA', _run_greedy_pca),
+        for cls_name, run in (('Preprocessing', _run_preprocessing), ('ComputePCAThreshold', _run_pca_threshold),
+                              ('ComputeGreedyPCA', _run_greedy_pca),
                               ('ComputeTGLR', _run_compute_tglr), ('ComputePurityThreshold', _run_purity)):
             cls = getattr(steps_module, cls_name, None)
             if cls is None:                 # a stand-in module without that step

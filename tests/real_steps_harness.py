@@ -68,16 +68,24 @@ def run_pipeline(monkeypatch, mode):
                     areamap=Holder(np.ones(shape[1:], dtype=int)), thresO2=[1e9], testO2=None)      # testO2: set after step01
         param = {}
         pre = orig.add(rsteps.Preprocessing(orig, 1, param))
-        for idx, cls in ((2, rsteps.CreateAreas), (3, rsteps.ComputePCAThreshold)):      # not run here: inputs above
-            orig.add(cls(orig, idx, param)).status = rsteps.Status.RUN
-        orig._dataobjs.pop('areamap', None)                                               # the attribute above is used
+        orig.add(rsteps.CreateAreas(orig, 2, param)).status = rsteps.Status.RUN           # not run: areamap is given above
+        thr_step = orig.add(rsteps.ComputePCAThreshold(orig, 3, param))
         pca = orig.add(rsteps.ComputeGreedyPCA(orig, 4, param))
         tglr = orig.add(rsteps.ComputeTGLR(orig, 5, param))
         pur = orig.add(rsteps.ComputePurityThreshold(orig, 6, param))
         pre()                                                     # Step.__call__: parameters, requirements, status
         assert pre.status is rsteps.Status.RUN and pre.param['dct_order'] == 10
         std64 = np.asarray(orig.cube_std._data, dtype=np.float64)
-        orig.testO2 = [np.mean(std64.reshape(shape[0], -1) ** 2, axis=0)]         # what ComputePCAThreshold.run leaves (:617-633)
+        o2 = np.mean(std64.reshape(shape[0], -1) ** 2, axis=0)
+        if mode == 'reference':                                   # its compute_thresh_gaussfit needs astropy: not run
+            thr_step.status = rsteps.Status.RUN
+            orig.testO2 = [o2]                                    # what ComputePCAThreshold.run leaves (:617-633)
+            fit = None
+        else:
+            thr_step()                                            # step03: O2 test per area + Gaussian fit of its distribution
+            np.testing.assert_allclose(orig.testO2[0], o2, rtol=1e-6)
+            fit = (thr_step.thresO2[0], thr_step.meaO2[0], thr_step.stdO2[0])
+            assert np.isfinite(fit).all() and fit[0] > fit[1] > 0 and len(orig.histO2[0]) + 1 == len(orig.binO2[0])
         pca()
         if fused:
             assert isinstance(pca.__dict__['cube_faint'], steps.LazyProduct) and pca.__dict__['cube_faint'].on_device().is_cuda
@@ -95,7 +103,7 @@ def run_pipeline(monkeypatch, mode):
                    local_max=np.asarray(orig.cube_local_max._data), local_min=np.asarray(orig.cube_local_min._data),
                    std_local_max=np.asarray(orig.cube_std_local_max._data), mapO2=np.asarray(orig.mapO2._data),
                    threshold=orig.param['threshold'], threshold_std=orig.param['threshold_std'],
-                   det_M=np.asarray(pur.Pval['Det_M']), std_det_M=np.asarray(pur.Pval_comp['Det_M']))
+                   det_M=np.asarray(pur.Pval['Det_M']), std_det_M=np.asarray(pur.Pval_comp['Det_M']), pca_fit=fit)
         return g, out
     finally:
         if mode != 'reference':

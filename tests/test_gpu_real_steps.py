@@ -33,3 +33,4 @@ def test_fused_and_rebound_steps_agree(monkeypatch):
         assert np.abs(np.asarray(a[key], dtype=np.float64) - b[key]).max() <= 2e-5 * scale, key
     assert np.mean(a['profile'] == b['profile']) > 0.9999
     assert close_thr(a['threshold'], b['threshold']) and np.abs(a['det_M'] - b['det_M']).max() <= 2
+    np.testing.assert_allclose(a['pca_fit'], b['pca_fit'], rtol=1e-4)     # step03: O2 map of step01 vs the cube reduced again

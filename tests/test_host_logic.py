@@ -94,10 +94,12 @@ def test_step04_step08_drop_ins_keep_the_reference_signatures():
         return [(p.name, p.default) for p in inspect.signature(fn).parameters.values()]
 
     assert params(osteps._run_greedy_pca) == params(rsteps.ComputeGreedyPCA.run)
+    assert params(osteps._run_pca_threshold) == params(rsteps.ComputePCAThreshold.run)
+    assert params(osteps._pca_threshold) == params(lib.Compute_PCA_threshold)
     assert params(osteps._estimation_line_table) == params(lib.estimation_line)
     ref = params(lib.Compute_GreedyPCA_area)
     assert params(lib_origin.Compute_GreedyPCA_area)[:len(ref)] == ref
-    for name in ('Compute_GreedyPCA_area', 'estimation_line'):
+    for name in ('Compute_PCA_threshold', 'Compute_GreedyPCA_area', 'estimation_line'):
         assert hasattr(rsteps, name)                      # imported by name at steps.py:19-41
 
 
@@ -217,3 +219,51 @@ def test_lazy_products_live_in_the_reference_step_machinery(tmp_path):
         assert getattr(rsteps, c).run is run
     for n, fn in ref_names.items():
         assert getattr(rsteps, n) is fn
+
+
+@pytest.mark.skipif(ref_loader.find_reference_file('muse_origin/steps.py') is None,
+                    reason='reference steps.py not present (oracle/_ref)')
+def test_fused_pca_threshold_reads_the_o2_map_of_step01():
+    """Fused step03 on the reference's real ``ComputePCAThreshold`` class (steps.py:572-631): the O2 test of each area
+    comes from the map the fused step01 left (only when it was made from the very cube the step holds), otherwise it
+    is recomputed from the cube like ``Compute_PCA_threshold`` (lib_origin.py:821-842) does; both give what the
+    rebound function gives area by area."""
+    from origin_b200 import steps as osteps
+    rsteps = ref_loader.load_steps()
+    rng = np.random.default_rng(5)
+    cube = rng.standard_normal((60, 24, 30)).astype(np.float32)
+    cube[:, 3:6, 4:9] *= 1.6
+    areamap = np.ones((24, 30), dtype=int)
+    areamap[:, 15:] = 2
+    o2 = np.mean(cube.astype(np.float64) ** 2, axis=0)
+
+    class Holder:
+        def __init__(self, data):
+            self._data = data
+
+    class Orig:
+        pass
+
+    osteps.patch_steps(rsteps, fused=True)
+    try:
+        assert rsteps.ComputePCAThreshold.run is osteps._run_pca_threshold
+        assert rsteps.Compute_PCA_threshold is osteps._pca_threshold
+        expect = [osteps._pca_threshold(cube[:, areamap == a], 0.01) for a in (1, 2)]
+        for cached, marker in (((cube, o2), 1.0), ((cube, o2 * 1.5), 1.5), ((cube.copy(), o2 * 1.5), 1.0), (None, 1.0)):
+            orig = Orig()
+            orig.cube_std, orig.areamap, orig.nbAreas = Holder(cube), Holder(areamap), 2
+            pre = rsteps.Preprocessing(orig, 1, {})
+            if cached is not None:
+                pre._ogn_o2map = cached
+            orig.steps = {'preprocessing': pre}
+            step = rsteps.ComputePCAThreshold(orig, 3, {})
+            step.run(orig)
+            assert len(step.thresO2) == len(orig.testO2) == len(orig.histO2) == len(orig.binO2) == 2
+            for a in range(2):
+                # marker 1.5: the (deliberately scaled) cached map was used; 1.0: the cube was reduced again
+                np.testing.assert_allclose(orig.testO2[a], expect[a][0] * marker, rtol=1e-12)
+            if marker == 1.0:
+                np.testing.assert_allclose(step.thresO2, [e[3] for e in expect], rtol=1e-10)
+                np.testing.assert_allclose(step.meaO2, [e[4] for e in expect], rtol=1e-10)
+    finally:
+        osteps.unpatch_steps()
