@@ -544,7 +544,8 @@ class Job:
     # ---- end to end through the host API with pinned host buffers ------------------------------
     def e2e(self, steps):
         """step05 -> step06 counts -> step07 extraction through the host API, as the fused step mirror calls it
-        (origin_b200.steps._run_compute_tglr): float32 cube and bit-packed mask in pinned HOST memory in; correl,
+        (origin_b200.steps._run_compute_tglr) in a session that packed its mask once (origin_b200.steps.pack_mask) and
+        keeps its buffers page-locked: float32 cube and bit-packed mask in pinned HOST memory in; correl,
         the two maps, the extremum lists, the per-threshold counts and the detection rows back on the HOST;
         correl_min and profile stay on the GPU behind lazy step products (fetched only if somebody reads them)."""
         import torch.distributed as dist
