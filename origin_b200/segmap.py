@@ -14,10 +14,15 @@ definitions so that step01's ``segmap_merged`` and step06's ``segmap_purity`` ca
   ``xtol = 1e-7`` and at most 100 function evaluations (astropy's ``acc`` / ``maxiter`` defaults; it leaves ``ftol``
   and ``gtol`` at scipy's own defaults, and so does this).
 
-Parity: UNPINNED — astropy is absent from this image, so the restatement cannot be run against the reference's
-own functions here; ``tests/test_segmap.py`` checks it against closed-form expectations (a Gaussian sample gives
-back its mean / sigma / threshold) and against direct scipy calls for the morphology.  The step mirror prefers
-the reference's functions whenever ``muse_origin`` imports.
+Parity: PARTLY PINNED.  Everything the reference itself writes in those two functions (positive values only, the
+histogram, the mode / half-maximum start values, the cut at mean + FWHM / 2, the threshold formula, erosion,
+dilation, disc convolution, labelling) is pinned: ``tests/test_segmap.py`` runs the reference's UNMODIFIED function
+bodies with only astropy's three objects (``sigma_clip``, ``Gaussian1D``, ``LevMarLSQFitter``) replaced by shims
+that delegate to the two building blocks above, and the results are identical.  What stays UNPINNED — astropy is
+absent from this image — is exactly the behaviour of those three objects (clipping rule and defaults, the
+Levenberg-Marquardt settings); they are checked against closed-form expectations only (a Gaussian sample gives
+back its mean / sigma / threshold).  The step mirror prefers the reference's functions whenever ``muse_origin``
+really imports.
 """
 
 import numpy as np
