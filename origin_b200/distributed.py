@@ -141,6 +141,7 @@ class PeerGather:
         self.shape = tuple(int(s) for s in global_shape)
         self.nbytes = int(np.prod(self.shape)) * 4
         self.ptrs, self._owned, self._mapped = [], [], []
+        self._torch, self.stagger_us = torch, 0      # close() reads these, also when the mapping below fails
         handles = []
         if self.rank == dst:
             for _ in range(slots):
@@ -170,8 +171,6 @@ class PeerGather:
         if not all(flags):
             self.close()
             raise err if err is not None else RuntimeError('peer mapping failed on another rank')
-        self._torch = torch
-        self.stagger_us = 0
 
     def stagger(self, tile_bytes, link_gbs=650.0, microseconds=None):
         """Let the source ranks take turns on the destination's NVLink ingress: rank r (counted among the sources)
