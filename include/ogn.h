@@ -187,7 +187,7 @@ OGN_API int ogn_step05(ogn_ctx *ctx,
                int64_t *min_index, float *min_value,
                int64_t capacity, int64_t *counts);
 
-/* ogn_step05 for a HOST cube with the mask given bit-packed: mask_bits = numpy.packbits of the flattened
+/* ogn_step05 (ComputeTGLR.run, steps.py:768-802) for a HOST cube with the mask given bit-packed: mask_bits = numpy.packbits of the flattened
  * [nz][ny][nx] boolean mask (MSB first), 1/8 of the bytes on the PCIe link; it is unpacked on the device slab
  * by slab.  nx must be a multiple of 8.  Every product may be a host buffer (copied back slab by slab while
  * later slabs are computed) or a device buffer (written in place, e.g. products the caller fetches lazily). */
@@ -203,7 +203,8 @@ OGN_API int ogn_step05_bits(ogn_ctx *ctx,
                     int64_t *min_index, float *min_value,
                     int64_t capacity, int64_t *counts);
 
-/* ogn_step05 on one spatial tile of a larger field (multi-GPU runs).  `cube` is
+/* ogn_step05 (ComputeTGLR.run, steps.py:768-802; the reference is single-process) on one spatial tile of a
+ * larger field (multi-GPU runs).  `cube` is
  * the [nz][ny][nx] sub-cube cut from the field with its halo;
  *   tile = {gny, gnx, gy0, gx0, oy0, oy1, ox0, ox1}
  * says that spaxel (0,0) of the sub-cube is spaxel (gy0,gx0) of the gny x gnx
@@ -284,7 +285,8 @@ OGN_API int ogn_purity_counts(ogn_ctx *ctx,
                       const double *thresholds, int nthresh,
                       int64_t *n1, int64_t *n0);
 
-/* Synchronisation-free variant for device-resident pipelines (multi-GPU steps): every pointer is a device
+/* Synchronisation-free variant of the same counting loop (lib_origin.py:1443-1449) for device-resident pipelines
+ * (multi-GPU steps): every pointer is a device
  * pointer; the lists are the capacity-sized buffers of an ogn_step05 / ogn_step05_tile / ogn_local_extrema
  * call whose `counts` output was a DEVICE array (such a call does not synchronise either), and
  * list_counts is that array: the kernels read the true list lengths from it.  n1 / n0 can be handed to
