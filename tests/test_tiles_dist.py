@@ -131,3 +131,29 @@ def test_purity_threshold_allreduce_world2():
         np.testing.assert_array_equal(lsum, np.full(4, 3.0))
         np.testing.assert_array_equal(lcnt, np.full(4, 2.0))
         assert calls >= 4                               # counts, two maxima, image, histogram, lambda sums
+
+
+def test_owned_extrema_torch_and_numpy_branches_agree():
+    """``owned_extrema`` has a numpy branch (host lists) and a torch branch (device lists of the asynchronous steps):
+    same owned subset, same global indices, same order, for every tile of a ragged plan."""
+    import torch
+    from origin_b200 import distributed as ogd, lib_origin
+    nz, ny, nx = 7, 37, 53
+    rng = np.random.default_rng(3)
+    for t in tiles.plan_tiles(ny, nx, 6, 5):
+        th, tw = t.shape
+        n = nz * th * tw
+        mi = np.sort(rng.choice(n, size=n // 9, replace=False)).astype(np.int64)
+        ni = np.sort(rng.choice(n, size=n // 11, replace=False)).astype(np.int64)
+        mv, nv = rng.normal(size=mi.size).astype(np.float32), rng.normal(size=ni.size).astype(np.float32)
+        a = ogd.owned_extrema(lib_origin.LocalExtrema((nz, th, tw), mi, mv, ni, nv), t, (nz, ny, nx))
+        b = ogd.owned_extrema(lib_origin.LocalExtrema((nz, th, tw), torch.from_numpy(mi), torch.from_numpy(mv),
+                                                      torch.from_numpy(ni), torch.from_numpy(nv)), t, (nz, ny, nx))
+        np.testing.assert_array_equal(a.max_index, b.max_index.numpy())
+        np.testing.assert_array_equal(a.max_value, b.max_value.numpy())
+        np.testing.assert_array_equal(a.min_index, b.min_index.numpy())
+        np.testing.assert_array_equal(a.min_value, b.min_value.numpy())
+        assert a.shape == b.shape == (nz, ny, nx) and len(a.max_index) > 0
+        z, y, x = np.unravel_index(a.max_index, (nz, ny, nx))
+        assert y.min() >= t.y0 and y.max() < t.y1 and x.min() >= t.x0 and x.max() < t.x1
+        assert np.all(np.diff(a.max_index.reshape(-1)) != 0)
